@@ -1,0 +1,338 @@
+// Grid construction for a ragged batch of clouds, plus the small utility kernels of the C ABI.
+// This is the GPU counterpart of pcl::search::KdTree::setInputCloud, which the reference runs in
+// setInputSource / setInputTarget (fast_apdgicp/include/fast_gicp/gicp/impl/fast_apdgicp_impl.hpp:96,106)
+// and again in pcl::Registration::initCompute: a uniform voxel grid per cloud, points counting-sorted
+// by cell, built entirely on the device (no host round trip: the cell size is chosen on the GPU
+// from the bounding box and a per-cloud cell budget).
+//
+// Pipeline (all kernels are tile-driven: one CTA per (cloud, chunk of points)):
+//   bbox -> grid_params -> count -> scan -> scatter -> cell_sort
+// cell_sort orders every cell's run by original index so the layout, and with it every later
+// summation order, is deterministic regardless of atomic scheduling.
+#include "apd_internal.h"
+
+namespace apd {
+
+namespace {
+
+constexpr int kTileThreads = 256;
+
+__device__ __forceinline__ unsigned enc_f(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void bbox_init_kernel(unsigned* bbox, int n_clouds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_clouds * 6) bbox[i] = (i % 6 < 3) ? 0xFFFFFFFFu : 0u;
+}
+
+__global__ void __launch_bounds__(kTileThreads) bbox_kernel(CloudSetView cs, const int4* __restrict__ tiles, unsigned* __restrict__ bbox) {
+  const int4 tile = tiles[blockIdx.x];
+  const int base = cs.pt_off[tile.x];
+  unsigned mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  for (int i = threadIdx.x; i < tile.z; i += blockDim.x) {
+    const float4 p = cs.pts[base + tile.y + i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const unsigned e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        mn[a] = min(mn[a], e[a]);
+        mx[a] = max(mx[a], e[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
+    mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      atomicMin(&bbox[tile.x * 6 + a], mn[a]);
+      atomicMax(&bbox[tile.x * 6 + 3 + a], mx[a]);
+    }
+  }
+}
+
+// One thread per cloud: bounding box -> cell edge h and grid dimensions with nx*ny*nz <= cell_cap.
+__global__ void grid_params_kernel(CloudSetView cs, const unsigned* __restrict__ bbox, const int* __restrict__ cell_cap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cs.n_clouds) return;
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; a++) {
+    const unsigned l = bbox[c * 6 + a], h = bbox[c * 6 + 3 + a];
+    if (l > h) { lo[a] = 0.f; hi[a] = 0.f; }  // no finite point
+    else { lo[a] = dec_f(l); hi[a] = dec_f(h); }
+  }
+  const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  const long long cap = max(cell_cap[c], 1);
+  // start from the edge that spends the whole budget on the box volume, then grow until it fits
+  const float emax = fmaxf(fmaxf(ex, ey), ez);
+  const float floor_h = fmaxf(emax * 1e-4f, 1e-6f);
+  const float dx = fmaxf(ex, floor_h), dy = fmaxf(ey, floor_h), dz = fmaxf(ez, floor_h);
+  float h = fmaxf(cbrtf(dx * dy * dz / (float)cap), floor_h);
+  int nx = 1, ny = 1, nz = 1;
+  for (int it = 0; it < 4096; it++) {
+    const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
+    if (fx * fy * fz <= (float)cap && fx < 2e9f && fy < 2e9f && fz < 2e9f) {
+      nx = (int)fx; ny = (int)fy; nz = (int)fz;
+      if ((long long)nx * ny * nz <= cap) break;
+    }
+    h *= 1.02f;
+  }
+  if ((long long)nx * ny * nz > cap) { nx = ny = nz = 1; h = fmaxf(emax, floor_h) * 2.f; }
+  GridParams g;
+  g.lox = lo[0]; g.loy = lo[1]; g.loz = lo[2];
+  g.h = h;
+  g.inv_h = 1.0f / h;
+  g.nx = nx; g.ny = ny; g.nz = nz;
+  g.ncells = nx * ny * nz;
+  float amax = 0.f;
+  for (int a = 0; a < 3; a++) amax = fmaxf(amax, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+  g.slack = 4e-6f * (amax + emax + h) + 1e-30f;
+  cs.grid[c] = g;
+}
+
+__global__ void __launch_bounds__(kTileThreads) count_kernel(CloudSetView cs, const int4* __restrict__ tiles, int* __restrict__ cellid) {
+  const int4 tile = tiles[blockIdx.x];
+  const int base = cs.pt_off[tile.x];
+  const GridParams g = cs.grid[tile.x];
+  unsigned* cells = cs.cells + cs.cell_off[tile.x];
+  for (int i = threadIdx.x; i < tile.z; i += blockDim.x) {
+    const float4 p = cs.pts[base + tile.y + i];
+    const int cell = cell_index(g, p.x, p.y, p.z);
+    cellid[base + tile.y + i] = cell;
+    atomicAdd(&cells[cell], 1u);
+  }
+}
+
+// One CTA per cloud: in-place exclusive scan of the ncells+1 counters; a copy goes to `cursor`.
+__global__ void __launch_bounds__(1024) scan_kernel(CloudSetView cs, unsigned* __restrict__ cursor) {
+  __shared__ unsigned warp_sums[32];
+  __shared__ unsigned carry;
+  const int c = blockIdx.x;
+  const long long off = cs.cell_off[c];
+  unsigned* cells = cs.cells + off;
+  unsigned* cur = cursor + off;
+  const int total = cs.grid[c].ncells + 1;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  // coalesced chunks of blockDim elements: block-wide scan per chunk with a running carry
+  for (int start = 0; start < total; start += blockDim.x) {
+    const int i = start + threadIdx.x;
+    const unsigned v = (i < total) ? cells[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if ((threadIdx.x & 31) >= d) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const unsigned w = warp_sums[threadIdx.x];
+      unsigned wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+        if (threadIdx.x >= d) wi += t;
+      }
+      warp_sums[threadIdx.x] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const unsigned excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < total) {
+      cells[i] = excl;
+      cur[i] = excl;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads) scatter_kernel(CloudSetView cs, const int4* __restrict__ tiles, const int* __restrict__ cellid,
+                                                               unsigned* __restrict__ cursor) {
+  const int4 tile = tiles[blockIdx.x];
+  const int base = cs.pt_off[tile.x];
+  unsigned* cur = cursor + cs.cell_off[tile.x];
+  for (int i = threadIdx.x; i < tile.z; i += blockDim.x) {
+    const int li = tile.y + i;
+    const float4 p = cs.pts[base + li];
+    const unsigned pos = atomicAdd(&cur[cellid[base + li]], 1u);
+    cs.spts[base + pos] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)li));
+  }
+}
+
+// One thread per cell: order the cell's run by original index (runs are a handful of points).
+__global__ void cell_sort_kernel(CloudSetView cs, int cloud_begin) {
+  const int c = cloud_begin + blockIdx.y;
+  if (c >= cs.n_clouds) return;
+  const int ncells = cs.grid[c].ncells;
+  const unsigned* cells = cs.cells + cs.cell_off[c];
+  float4* sp = cs.spts + cs.pt_off[c];
+  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncells; cell += gridDim.x * blockDim.x) {
+    const int s = (int)cells[cell], e = (int)cells[cell + 1];
+    for (int i = s + 1; i < e; i++) {
+      const float4 v = sp[i];
+      const unsigned key = __float_as_uint(v.w);
+      int j = i - 1;
+      while (j >= s && __float_as_uint(sp[j].w) > key) {
+        sp[j + 1] = sp[j];
+        j--;
+      }
+      sp[j + 1] = v;
+    }
+  }
+}
+
+__global__ void pack_points_kernel(const float* __restrict__ xyz, int stride_floats, long long n, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = xyz + i * stride_floats;
+  out[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+
+// pcl::transformPointCloud(*input_, output, T) at lsq_registration_impl.hpp:79 (float arithmetic)
+__global__ void transform_points_kernel(const float4* __restrict__ pts, int n, const float* __restrict__ T, float* __restrict__ out, int out_stride_floats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = pts[i];
+  float* o = out + (size_t)i * out_stride_floats;
+  o[0] = xform_row_rn(T[0], T[1], T[2], T[3], a.x, a.y, a.z);
+  o[1] = xform_row_rn(T[4], T[5], T[6], T[7], a.x, a.y, a.z);
+  o[2] = xform_row_rn(T[8], T[9], T[10], T[11], a.x, a.y, a.z);
+}
+
+// sorted 6-double covariances -> Eigen::Matrix4d layout (16 doubles, symmetric so row/column order is moot) in original order
+__global__ void cov_export_kernel(CloudSetView cs, int cloud, double* __restrict__ out16) {
+  const int n = cs.pt_off[cloud + 1] - cs.pt_off[cloud];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int gi = cs.pt_off[cloud] + i;
+  const unsigned orig = __float_as_uint(cs.spts[gi].w);
+  const double2 a = cs.cov0[gi], b = cs.cov1[gi], c = cs.cov2[gi];
+  double* o = out16 + (size_t)orig * 16;
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = 0;
+  o[4] = a.y; o[5] = b.y; o[6] = c.x; o[7] = 0;
+  o[8] = b.x; o[9] = c.x; o[10] = c.y; o[11] = 0;
+  o[12] = 0; o[13] = 0; o[14] = 0; o[15] = 0;
+}
+
+__global__ void cov_import_kernel(CloudSetView cs, int cloud, const double* __restrict__ in16) {
+  const int n = cs.pt_off[cloud + 1] - cs.pt_off[cloud];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int gi = cs.pt_off[cloud] + i;
+  const unsigned orig = __float_as_uint(cs.spts[gi].w);
+  const double* o = in16 + (size_t)orig * 16;
+  cs.cov0[gi] = make_double2(o[0], o[1]);
+  cs.cov1[gi] = make_double2(o[2], o[5]);
+  cs.cov2[gi] = make_double2(o[6], o[10]);
+}
+
+// correspondences_ / sq_distances_ / mahalanobis_ of the last linearize in ORIGINAL source order with
+// ORIGINAL target indices (fast_apdgicp.hpp:102-105)
+__global__ void corr_export_kernel(AlignBatch b, int slot, int s, int t, int* __restrict__ corr_out, float* __restrict__ sqd_out, double* __restrict__ m16_out) {
+  const int ns = b.src.pt_off[s + 1] - b.src.pt_off[s];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  const size_t si = (size_t)slot * b.scratch.max_src + i;
+  const unsigned orig = __float_as_uint(b.src.spts[b.src.pt_off[s] + i].w);
+  const int c = b.scratch.corr[si];
+  if (corr_out) corr_out[orig] = (c >= 0) ? (int)__float_as_uint(b.tgt.spts[b.tgt.pt_off[t] + c].w) : -1;
+  if (sqd_out) sqd_out[orig] = b.scratch.sqd[si];
+  if (m16_out) {
+    double* o = m16_out + (size_t)orig * 16;
+    for (int j = 0; j < 16; j++) o[j] = 0.0;
+    if (c >= 0) {
+      const double2 m0 = b.scratch.m0[si], m1 = b.scratch.m1[si], m2 = b.scratch.m2[si];
+      o[0] = m0.x; o[1] = m0.y; o[2] = m1.x;
+      o[4] = m0.y; o[5] = m1.y; o[6] = m2.x;
+      o[8] = m1.x; o[9] = m2.x; o[10] = m2.y;
+    }
+  }
+}
+
+}  // namespace
+
+#define APD_LAUNCH_CHECK()                      \
+  do {                                          \
+    if (st) st->launches++;                     \
+    cudaError_t e_ = cudaGetLastError();        \
+    if (e_ != cudaSuccess) return e_;           \
+  } while (0)
+
+cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, const int4* tiles, int n_tiles, const int* cell_cap, long long total_cells,
+                              int max_cloud_points, cudaStream_t stream, LaunchStats* st) {
+  (void)max_cloud_points;
+  if (cs.n_clouds == 0 || n_tiles == 0) return cudaSuccess;
+  cudaError_t e = cudaMemsetAsync(cs.cells, 0, sizeof(unsigned) * (size_t)total_cells, stream);
+  if (e != cudaSuccess) return e;
+  bbox_init_kernel<<<(cs.n_clouds * 6 + 255) / 256, 256, 0, stream>>>(ws.bbox, cs.n_clouds);
+  APD_LAUNCH_CHECK();
+  bbox_kernel<<<n_tiles, kTileThreads, 0, stream>>>(cs, tiles, ws.bbox);
+  APD_LAUNCH_CHECK();
+  grid_params_kernel<<<(cs.n_clouds + 127) / 128, 128, 0, stream>>>(cs, ws.bbox, cell_cap);
+  APD_LAUNCH_CHECK();
+  count_kernel<<<n_tiles, kTileThreads, 0, stream>>>(cs, tiles, ws.cellid);
+  APD_LAUNCH_CHECK();
+  scan_kernel<<<cs.n_clouds, 1024, 0, stream>>>(cs, ws.cursor);
+  APD_LAUNCH_CHECK();
+  scatter_kernel<<<n_tiles, kTileThreads, 0, stream>>>(cs, tiles, ws.cellid, ws.cursor);
+  APD_LAUNCH_CHECK();
+  for (int c0 = 0; c0 < cs.n_clouds; c0 += 32768) {
+    const int ny = min(cs.n_clouds - c0, 32768);
+    // enough threads to cover the largest per-cloud table once for batches; grid-stride otherwise
+    const long long avg_cells = total_cells / cs.n_clouds + 1;
+    const long long want_bx = (avg_cells + 255) / 256;
+    const int bx = (int)(want_bx < 4096 ? want_bx : 4096);
+    cell_sort_kernel<<<dim3(bx, ny), 256, 0, stream>>>(cs, c0);
+    APD_LAUNCH_CHECK();
+  }
+  return cudaSuccess;
+}
+
+cudaError_t launch_pack_points(const float* xyz, int stride_floats, long long n, float4* out, cudaStream_t stream, LaunchStats* st) {
+  if (n == 0) return cudaSuccess;
+  pack_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(xyz, stride_floats, n, out);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_transform_points(const float4* pts, int n, const float* T16, float* out, int out_stride_floats, cudaStream_t stream, LaunchStats* st) {
+  if (n == 0) return cudaSuccess;
+  transform_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n, T16, out, out_stride_floats);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_cov_export(const CloudSetView& cs, int cloud, double* out16, cudaStream_t stream, LaunchStats* st) {
+  // n is read on the device; size the grid from the set total (clouds exported this way are single-cloud sets)
+  const int n = cs.total_points;
+  if (n == 0) return cudaSuccess;
+  cov_export_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cs, cloud, out16);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_cov_import(const CloudSetView& cs, int cloud, const double* in16, cudaStream_t stream, LaunchStats* st) {
+  const int n = cs.total_points;
+  if (n == 0) return cudaSuccess;
+  cov_import_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cs, cloud, in16);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_corr_export(const AlignBatch& b, int slot, int s, int t, int* corr_out, float* sqd_out, double* m16_out, cudaStream_t stream, LaunchStats* st) {
+  const int n = b.scratch.max_src;  // >= the source size; the kernel bounds itself
+  if (n == 0) return cudaSuccess;
+  corr_export_kernel<<<(n + 255) / 256, 256, 0, stream>>>(b, slot, s, t, corr_out, sqd_out, m16_out);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+}  // namespace apd

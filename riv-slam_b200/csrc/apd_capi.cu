@@ -1,0 +1,1003 @@
+// C ABI of the B200-native FastAPDGICP path (include/apdgicp_b200.h): handle and cloud-set
+// management, parameter plumbing and launch orchestration. No computation happens on the host:
+// every entry point either moves bytes or enqueues the kernels of apd_build.cu / apd_knn_cov.cu /
+// apd_align.cu on the handle's stream. There is no CPU fallback; without a device apd_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "apd_internal.h"
+
+using namespace apd;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return e; }
+    cap = want;
+    return cudaSuccess;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct apd_cloudset_s {
+  int n_clouds = 0;
+  long long total = 0;
+  int max_n = 0, min_n = 0;
+  long long total_cells = 0;
+  std::vector<int> h_off;
+  DevBuf pt_off, cell_off, pts, spts, cells, grid, cov0, cov1, cov2, cell_cap, tiles_build, tiles_knn;
+  int n_tiles_build = 0, n_tiles_knn = 0;
+  bool grid_built = false, cov_valid = false;
+  int cov_k = -1, cov_reg = -1;
+  bool staged = false;      // every cloud's grid fits the shared-memory staging area
+  size_t staged_smem = 0;   // bytes needed for the largest cloud
+  CloudSetView view() const {
+    CloudSetView v;
+    v.n_clouds = n_clouds;
+    v.total_points = (int)total;
+    v.pt_off = pt_off.as<int>();
+    v.cell_off = cell_off.as<long long>();
+    v.pts = pts.as<float4>();
+    v.spts = spts.as<float4>();
+    v.cells = cells.as<unsigned>();
+    v.grid = grid.as<GridParams>();
+    v.cov0 = cov0.as<double2>();
+    v.cov1 = cov1.as<double2>();
+    v.cov2 = cov2.as<double2>();
+    return v;
+  }
+};
+
+struct apd_context {
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  apd_params prm;
+  std::string err;
+  std::shared_ptr<apd_cloudset_s> src, tgt;
+  uint64_t src_key = 0, tgt_key = 0;
+  LaunchStats stats;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  // tunables (apd_set_option)
+  double cells_per_point = 8.0;
+  int team_size = 0;      // 0 = automatic
+  int force_unstaged = 0;
+  int max_teams_opt = 0;  // 0 = as many as fit
+  // scratch (grow-only)
+  DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
+      counters, grid_partials, misc, knn_tmp, cov_tmp;
+  int scratch_slots = 0, scratch_max_src = 0;
+  // last single-pair alignment
+  bool has_last = false;
+  apd_result last;
+  double final_hessian[36];
+  std::vector<double> lm_trace;
+  bool last_lin_valid = false;  // scratch slot 0 holds correspondences of the current src/tgt
+  long long work_lin = 0, work_err = 0, work_pairs = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(apd_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      cudaGetLastError();                                                                            \
+      return fail(h, APD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+    }                                                                                                \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+DeviceParams device_params(const apd_params& p) {
+  DeviceParams d;
+  d.k = p.k_correspondences;
+  d.regularization = p.regularization;
+  d.max_iterations = p.max_iterations;
+  d.optimizer = p.optimizer;
+  d.lm_max_iterations = p.lm_max_iterations;
+  d.corr_thr2 = p.max_corr_dist * p.max_corr_dist;  // product in double (fast_apdgicp_impl.hpp:156)
+  // smallest float not below the double threshold: pruning with it can never drop a candidate that passes the gate
+  float f = (float)d.corr_thr2;
+  if (!(d.corr_thr2 < 3.0e38)) f = INFINITY;
+  else if ((double)f < d.corr_thr2) f = std::nextafterf(f, INFINITY);
+  d.corr_limit2 = f;
+  d.rotation_epsilon = p.rotation_epsilon;
+  d.transformation_epsilon = p.transformation_epsilon;
+  d.lm_init_lambda_factor = p.lm_init_lambda_factor;
+  d.dist_var = p.dist_var;
+  d.sin_az = std::sin(p.azimuth_var / 180 * M_PI);
+  d.sin_el = std::sin(p.elevation_var / 180 * M_PI);
+  return d;
+}
+
+size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem() - 512; }
+
+// Build the device-side description of a ragged batch: offsets, per-cloud cell budgets, tile lists.
+int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
+  const int nc = cs->n_clouds;
+  std::vector<int> cap(nc);
+  std::vector<long long> cell_off(nc + 1);
+  const size_t budget = staging_budget(h);
+  bool staged = !h->force_unstaged;
+  size_t need_max = 0;
+  cs->max_n = 0;
+  cs->min_n = nc ? INT32_MAX : 0;
+  for (int c = 0; c < nc; c++) {
+    const int n = cs->h_off[c + 1] - cs->h_off[c];
+    cs->max_n = std::max(cs->max_n, n);
+    cs->min_n = std::min(cs->min_n, n);
+    long long want = std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n));
+    want = std::min<long long>(want, 1ll << 28);
+    cap[c] = (int)want;
+  }
+  // staging needs 16 B per point + 2 B per cell entry, and local indices that fit 16 bits
+  if (staged) {
+    for (int c = 0; c < nc && staged; c++) {
+      const long long n = cs->h_off[c + 1] - cs->h_off[c];
+      if (n >= 65535 || (size_t)(16 * n + 2 * (2 * n + 2) + 32) > budget) { staged = false; break; }
+      const long long room = ((long long)budget - 16 * n - 32) / 2 - 1;
+      cap[c] = (int)std::min<long long>(cap[c], room);
+      need_max = std::max(need_max, (size_t)(16 * n + 2 * ((long long)cap[c] + 1) + 16));
+    }
+  }
+  if (!staged) {  // undo any clamping done while probing
+    for (int c = 0; c < nc; c++) {
+      const int n = cs->h_off[c + 1] - cs->h_off[c];
+      long long want = std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n));
+      cap[c] = (int)std::min<long long>(want, 1ll << 28);
+    }
+    need_max = 0;
+  }
+  cs->staged = staged && nc > 0;
+  cs->staged_smem = (need_max + 15) & ~(size_t)15;
+  long long off = 0;
+  for (int c = 0; c < nc; c++) {
+    cell_off[c] = off;
+    off += (long long)cap[c] + 1;
+  }
+  cell_off[nc] = off;
+  cs->total_cells = off;
+
+  // tiles for the per-point build kernels: 1024 points per CTA
+  std::vector<int4> tb;
+  for (int c = 0; c < nc; c++) {
+    const int n = cs->h_off[c + 1] - cs->h_off[c];
+    for (int s = 0; s < n; s += 1024) tb.push_back(int4{c, s, std::min(1024, n - s), 0});
+  }
+  // tiles for kNN + covariance: whole clouds per CTA when the batch alone fills the GPU, otherwise
+  // split so that about two waves of CTAs exist
+  std::vector<int4> tk;
+  const long long target_ctas = 2ll * h->sm_count;
+  long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 128);
+  tile_q = std::max<long long>(tile_q, 1);
+  for (int c = 0; c < nc; c++) {
+    const int n = cs->h_off[c + 1] - cs->h_off[c];
+    for (long long s = 0; s < n; s += tile_q) tk.push_back(int4{c, (int)s, (int)std::min<long long>(tile_q, n - s), 0});
+  }
+  cs->n_tiles_build = (int)tb.size();
+  cs->n_tiles_knn = (int)tk.size();
+
+  CK(cs->pt_off.reserve(sizeof(int) * (nc + 1)));
+  CK(cs->cell_off.reserve(sizeof(long long) * (nc + 1)));
+  CK(cs->cell_cap.reserve(sizeof(int) * std::max(nc, 1)));
+  CK(cs->grid.reserve(sizeof(GridParams) * std::max(nc, 1)));
+  CK(cs->tiles_build.reserve(sizeof(int4) * std::max<size_t>(tb.size(), 1)));
+  CK(cs->tiles_knn.reserve(sizeof(int4) * std::max<size_t>(tk.size(), 1)));
+  CK(cs->pts.reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
+  CK(cs->spts.reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
+  CK(cs->cov0.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
+  CK(cs->cov1.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
+  CK(cs->cov2.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
+  CK(cs->cells.reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->total_cells, 1)));
+  // small tables: synchronous copies from stack/heap vectors are fine (the vectors die at return)
+  CK(cudaMemcpyAsync(cs->pt_off.p, cs->h_off.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(cs->cell_off.p, cell_off.data(), sizeof(long long) * (nc + 1), cudaMemcpyHostToDevice, h->stream));
+  if (nc) CK(cudaMemcpyAsync(cs->cell_cap.p, cap.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, h->stream));
+  if (!tb.empty()) CK(cudaMemcpyAsync(cs->tiles_build.p, tb.data(), sizeof(int4) * tb.size(), cudaMemcpyHostToDevice, h->stream));
+  if (!tk.empty()) CK(cudaMemcpyAsync(cs->tiles_knn.p, tk.data(), sizeof(int4) * tk.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int cloudset_fill(apd_handle h, apd_cloudset_s* cs, const float* xyz, int stride_bytes, int mem) {
+  const long long n = cs->total;
+  if (n == 0) return APD_OK;
+  if (stride_bytes == 16) {
+    CK(cudaMemcpyAsync(cs->pts.p, xyz, sizeof(float4) * n, mem == APD_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    return APD_OK;
+  }
+  const float* dev_xyz = xyz;
+  if (mem == APD_MEM_HOST) {
+    const size_t bytes = (size_t)(n - 1) * stride_bytes + 12;
+    CK(h->raw_upload.reserve(bytes + 16));
+    CK(cudaMemcpyAsync(h->raw_upload.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+    dev_xyz = h->raw_upload.as<float>();
+  }
+  CK(launch_pack_points(dev_xyz, stride_bytes / 4, n, cs->pts.as<float4>(), h->stream, &h->stats));
+  return APD_OK;
+}
+
+int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
+  if (cs->grid_built || cs->n_clouds == 0) { cs->grid_built = true; return APD_OK; }
+  CK(h->ws_bbox.reserve(sizeof(unsigned) * 6 * cs->n_clouds));
+  CK(h->ws_cellid.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
+  CK(h->ws_cursor.reserve(sizeof(unsigned) * (size_t)cs->total_cells));
+  BuildWorkspace ws{h->ws_bbox.as<unsigned>(), h->ws_cellid.as<int>(), h->ws_cursor.as<unsigned>()};
+  CK(launch_grid_build(cs->view(), ws, cs->tiles_build.as<int4>(), cs->n_tiles_build, cs->cell_cap.as<int>(), cs->total_cells, cs->max_n, h->stream, &h->stats));
+  cs->grid_built = true;
+  return APD_OK;
+}
+
+int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
+  const int k = h->prm.k_correspondences;
+  if (k < 1 || k > 32) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences must be in [1, 32]");
+  if (h->prm.regularization < 0 || h->prm.regularization > 4) return fail(h, APD_ERR_INVALID, "unknown regularization method");
+  int rc = cloudset_build_grid(h, cs);
+  if (rc) return rc;
+  if (cs->cov_valid && cs->cov_k == k && cs->cov_reg == h->prm.regularization && !knn_out) return APD_OK;
+  if (cs->cov_valid && cs->cov_k < 0 && !knn_out) return APD_OK;  // covariances injected by the caller (setSource/TargetCovariances)
+  const DeviceParams dp = device_params(h->prm);
+  CK(launch_knn_cov(cs->view(), cs->tiles_knn.as<int4>(), cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
+  cs->cov_valid = true;
+  cs->cov_k = k;
+  cs->cov_reg = h->prm.regularization;
+  return APD_OK;
+}
+
+int make_cloudset(apd_handle h, const float* xyz, int stride_bytes, const int32_t* offsets, int n_clouds, int mem, std::shared_ptr<apd_cloudset_s>* out) {
+  if (n_clouds < 0 || (n_clouds > 0 && !offsets)) return fail(h, APD_ERR_INVALID, "bad cloud offsets");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(h, APD_ERR_INVALID, "stride_bytes must be a multiple of 4 and at least 12");
+  auto cs = std::make_shared<apd_cloudset_s>();
+  cs->n_clouds = n_clouds;
+  cs->h_off.assign(n_clouds + 1, 0);
+  for (int c = 0; c <= n_clouds && n_clouds > 0; c++) {
+    cs->h_off[c] = offsets[c] - offsets[0];
+    if (c && cs->h_off[c] < cs->h_off[c - 1]) return fail(h, APD_ERR_INVALID, "cloud offsets must be non-decreasing");
+  }
+  cs->total = cs->h_off[n_clouds];
+  if (cs->total > 0 && !xyz) return fail(h, APD_ERR_INVALID, "null point pointer");
+  int rc = cloudset_layout(h, cs.get());
+  if (rc) return rc;
+  const float* first = xyz ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(xyz) + (size_t)(n_clouds ? offsets[0] : 0) * stride_bytes) : nullptr;
+  rc = cloudset_fill(h, cs.get(), first, stride_bytes, mem);
+  if (rc) return rc;
+  *out = cs;
+  return APD_OK;
+}
+
+int ensure_align_scratch(apd_handle h, int slots, int max_src) {
+  if (slots <= h->scratch_slots && max_src <= h->scratch_max_src) return APD_OK;
+  slots = std::max(slots, h->scratch_slots);
+  max_src = std::max(max_src, h->scratch_max_src);
+  const size_t n = (size_t)slots * max_src;
+  CK(h->sc_corr.reserve(sizeof(int) * n));
+  CK(h->sc_sqd.reserve(sizeof(float) * n));
+  CK(h->sc_m0.reserve(sizeof(double2) * n));
+  CK(h->sc_m1.reserve(sizeof(double2) * n));
+  CK(h->sc_m2.reserve(sizeof(double2) * n));
+  h->scratch_slots = slots;
+  h->scratch_max_src = max_src;
+  return APD_OK;
+}
+
+struct TeamPlan {
+  int kind = TEAM_CTA, size = 1, teams = 1;
+  bool staged = false;
+  size_t smem = 0;
+};
+
+// Pick the launch shape for n_pairs pairs: one CTA per pair when the batch fills the GPU, clusters
+// (or the whole cooperative grid for very large sources) when few pairs must be made fast.
+int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tgt, int n_pairs, TeamPlan* plan) {
+  TeamPlan p;
+  p.staged = tgt->staged;
+  p.smem = p.staged ? tgt->staged_smem : 0;
+  int size = h->team_size;
+  if (size <= 0) {
+    size = 1;
+    while (size < 8 && (long long)n_pairs * size * 2 <= h->sm_count) size *= 2;
+    // a CTA pass handles kAlignThreads points at a time: no point in more CTAs than that
+    while (size > 1 && (long long)src->max_n < (long long)(size / 2) * kAlignThreads) size /= 2;
+  }
+  if (!p.staged && h->team_size <= 0 && n_pairs == 1 && src->max_n > 16 * kAlignThreads * 2) {
+    // large source against a large target: the whole GPU on one pair
+    const int max_blocks = align_max_teams(TEAM_GRID, 0, false, 0);
+    if (max_blocks >= 2) {
+      p.kind = TEAM_GRID;
+      p.size = std::min(max_blocks, (src->max_n + kAlignThreads - 1) / kAlignThreads);
+      p.teams = 1;
+      *plan = p;
+      return APD_OK;
+    }
+  }
+  if (size > 1) {
+    if (size > 16) size = 16;
+    int fit = align_max_teams(TEAM_CLUSTER, size, p.staged, p.smem);
+    while (fit < 1 && size > 1) {
+      size /= 2;
+      fit = size > 1 ? align_max_teams(TEAM_CLUSTER, size, p.staged, p.smem) : 0;
+    }
+    if (size > 1) {
+      p.kind = TEAM_CLUSTER;
+      p.size = size;
+      p.teams = std::max(1, std::min(n_pairs, fit));
+      if (h->max_teams_opt > 0) p.teams = std::min(p.teams, h->max_teams_opt);
+      *plan = p;
+      return APD_OK;
+    }
+  }
+  const int fit = align_max_teams(TEAM_CTA, 1, p.staged, p.smem);
+  if (fit < 1) return fail(h, APD_ERR_CUDA, "align kernel does not fit on this device");
+  p.kind = TEAM_CTA;
+  p.size = 1;
+  p.teams = std::max(1, std::min(n_pairs, fit));
+  if (h->max_teams_opt > 0) p.teams = std::min(p.teams, h->max_teams_opt);
+  *plan = p;
+  return APD_OK;
+}
+
+struct AlignCall {
+  apd_cloudset_s *src, *tgt;
+  const int32_t *src_idx = nullptr, *tgt_idx = nullptr;  // host
+  const float* guesses = nullptr;                        // host, n_pairs*16
+  int n_pairs = 0;
+  int mode = 0;
+  int min_points = 0;
+  double max_range = DBL_MAX;
+  bool want_trace = false;
+  bool want_hessian = false;
+};
+
+// Enqueue the align kernel for a batch; results land in h->results (device).
+int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, TeamPlan* used_plan = nullptr) {
+  int rc = cloudset_prepare(h, c.src);
+  if (rc) return rc;
+  if (c.tgt != c.src) {
+    rc = cloudset_prepare(h, c.tgt);
+    if (rc) return rc;
+  }
+  const int np = c.n_pairs;
+  TeamPlan plan;
+  rc = plan_teams(h, c.src, c.tgt, np, &plan);
+  if (rc) return rc;
+  rc = ensure_align_scratch(h, plan.kind == TEAM_GRID ? 1 : plan.teams, std::max(c.src->max_n, 1));
+  if (rc) return rc;
+  CK(h->results.reserve(sizeof(apd_result) * np));
+  CK(h->counters.reserve(sizeof(unsigned long long) * 4));
+  CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * 4, h->stream));
+  AlignBatch b;
+  memset(&b, 0, sizeof(b));
+  b.src = c.src->view();
+  b.tgt = c.tgt->view();
+  if (c.src_idx) {
+    CK(h->idx_src.reserve(sizeof(int) * np));
+    CK(cudaMemcpyAsync(h->idx_src.p, c.src_idx, sizeof(int) * np, cudaMemcpyHostToDevice, h->stream));
+    b.src_idx = h->idx_src.as<int>();
+  }
+  if (c.tgt_idx) {
+    CK(h->idx_tgt.reserve(sizeof(int) * np));
+    CK(cudaMemcpyAsync(h->idx_tgt.p, c.tgt_idx, sizeof(int) * np, cudaMemcpyHostToDevice, h->stream));
+    b.tgt_idx = h->idx_tgt.as<int>();
+  }
+  if (c.guesses) {
+    CK(h->guesses.reserve(sizeof(float) * 16 * np));
+    CK(cudaMemcpyAsync(h->guesses.p, c.guesses, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, h->stream));
+    b.guesses = h->guesses.as<float>();
+  }
+  b.out = h->results.as<apd_result>();
+  if (c.want_hessian || c.mode == 1) {
+    CK(h->fh.reserve(sizeof(double) * 36 * np));
+    CK(h->lin_b.reserve(sizeof(double) * 6 * np));
+    CK(cudaMemsetAsync(h->fh.p, 0, sizeof(double) * 36 * np, h->stream));
+    b.final_hessian = h->fh.as<double>();
+    b.lin_b = h->lin_b.as<double>();
+  }
+  if (c.want_trace) {
+    b.trace_rows = std::max(1, std::min(4096, h->prm.max_iterations * std::max(1, h->prm.lm_max_iterations)));
+    CK(h->trace.reserve(sizeof(double) * 8 * b.trace_rows * np));
+    CK(h->trace_count.reserve(sizeof(int) * np));
+    CK(cudaMemsetAsync(h->trace_count.p, 0, sizeof(int) * np, h->stream));
+    b.trace = h->trace.as<double>();
+    b.trace_count = h->trace_count.as<int>();
+  }
+  b.n_pairs = np;
+  b.work_counter = reinterpret_cast<int*>(h->counters.as<unsigned long long>() + 2);
+  b.counters = h->counters.as<unsigned long long>();
+  if (plan.kind == TEAM_GRID) {
+    CK(h->grid_partials.reserve(sizeof(double) * 2 * plan.size * kNRed));
+    b.grid_partials = h->grid_partials.as<double>();
+  }
+  b.scratch.max_src = h->scratch_max_src;
+  b.scratch.corr = h->sc_corr.as<int>();
+  b.scratch.sqd = h->sc_sqd.as<float>();
+  b.scratch.m0 = h->sc_m0.as<double2>();
+  b.scratch.m1 = h->sc_m1.as<double2>();
+  b.scratch.m2 = h->sc_m2.as<double2>();
+  b.prm = device_params(h->prm);
+  b.mode = c.mode;
+  b.min_points = c.min_points;
+  b.max_range = c.max_range;
+  CK(launch_align(b, plan.kind, plan.size, plan.teams, plan.staged, plan.smem, h->stream, &h->stats));
+  if (used) *used = b;
+  if (used_plan) *used_plan = plan;
+  return APD_OK;
+}
+
+int fetch_counters(apd_handle h, int np) {
+  unsigned long long c[4];
+  CK(cudaMemcpyAsync(c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->work_lin = (long long)c[0];
+  h->work_err = (long long)c[1];
+  h->work_pairs = np;
+  return APD_OK;
+}
+
+int set_cloud(apd_handle h, bool is_source, const float* xyz, int stride_bytes, int n, uint64_t key, int mem) {
+  if (n < 0) return fail(h, APD_ERR_INVALID, "negative point count");
+  auto& slot = is_source ? h->src : h->tgt;
+  auto& slot_key = is_source ? h->src_key : h->tgt_key;
+  auto& other = is_source ? h->tgt : h->src;
+  auto& other_key = is_source ? h->tgt_key : h->src_key;
+  h->last_lin_valid = false;
+  if (key != 0 && slot && slot_key == key && slot->total == n) return APD_OK;  // same pointer: fast_apdgicp_impl.hpp:91,102
+  if (key != 0 && other && other_key == key && other->total == n) {
+    slot = other;  // the other slot already holds this cloud: share its grid and covariances
+    slot_key = key;
+    return APD_OK;
+  }
+  const int32_t off[2] = {0, n};
+  std::shared_ptr<apd_cloudset_s> cs;
+  int rc = make_cloudset(h, xyz, stride_bytes, off, 1, mem, &cs);
+  if (rc) return rc;
+  slot = cs;
+  slot_key = key;
+  h->has_last = false;
+  return APD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int apd_abi_version(void) { return APDGICP_B200_ABI_VERSION; }
+
+int apd_default_params(apd_params* p) {
+  if (!p) return APD_ERR_INVALID;
+  p->k_correspondences = 20;
+  p->regularization = APD_REG_PLANE;
+  p->max_iterations = 64;
+  p->optimizer = APD_OPT_LEVENBERG_MARQUARDT;
+  p->lm_max_iterations = 10;
+  p->num_threads = 0;
+  p->max_corr_dist = (double)FLT_MAX;
+  p->rotation_epsilon = 2e-3;
+  p->transformation_epsilon = 5e-4;
+  p->lm_init_lambda_factor = 1e-9;
+  p->dist_var = 0.86;
+  p->azimuth_var = 0.5;
+  p->elevation_var = 1.0;
+  return APD_OK;
+}
+
+int apd_create(int device_id, apd_handle* out) {
+  if (!out) return APD_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    g_err = "no CUDA device: apdgicp_b200 has no CPU path";
+    return APD_ERR_NO_DEVICE;
+  }
+  if (device_id < 0 || device_id >= count) {
+    g_err = "device id out of range";
+    return APD_ERR_INVALID;
+  }
+  apd_handle h = new (std::nothrow) apd_context();
+  if (!h) return APD_ERR_INVALID;
+  h->device = device_id;
+  DeviceGuard guard(device_id);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess || prop.major < 10) {
+    g_err = "apdgicp_b200 is built for sm_100a (Blackwell B200) only";
+    delete h;
+    return APD_ERR_NO_DEVICE;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_err = "cudaStreamCreate failed";
+    delete h;
+    return APD_ERR_CUDA;
+  }
+  h->stream = h->own_stream;
+  apd_default_params(&h->prm);
+  memset(&h->last, 0, sizeof(h->last));
+  for (int i = 0; i < 36; i++) h->final_hessian[i] = (i % 7 == 0) ? 1.0 : 0.0;  // final_hessian_.setIdentity(), lsq_registration_impl.hpp:23
+  *out = h;
+  return APD_OK;
+}
+
+int apd_destroy(apd_handle h) {
+  if (!h) return APD_OK;
+  DeviceGuard guard(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->src.reset();
+  h->tgt.reset();
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return APD_OK;
+}
+
+const char* apd_last_error(apd_handle h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int apd_set_stream(apd_handle h, void* cuda_stream) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return APD_OK;
+}
+
+int apd_set_params(apd_handle h, const apd_params* p) {
+  if (!h || !p) return APD_ERR_INVALID;
+  if (p->k_correspondences < 1) return fail(h, APD_ERR_INVALID, "k_correspondences < 1");
+  if (p->k_correspondences > 32) return fail(h, APD_ERR_UNSUPPORTED, "k_correspondences > 32 is not supported");
+  if (p->regularization < 0 || p->regularization > 4) return fail(h, APD_ERR_INVALID, "unknown regularization method");
+  if (p->optimizer < 0 || p->optimizer > 1) return fail(h, APD_ERR_INVALID, "unknown optimizer");
+  h->prm = *p;
+  h->last_lin_valid = false;
+  return APD_OK;
+}
+
+int apd_get_params(apd_handle h, apd_params* p) {
+  if (!h || !p) return APD_ERR_INVALID;
+  *p = h->prm;
+  return APD_OK;
+}
+
+int apd_set_option(apd_handle h, const char* name, double value) {
+  if (!h || !name) return APD_ERR_INVALID;
+  const std::string n(name);
+  if (n == "cells_per_point") { if (!(value > 0)) return fail(h, APD_ERR_INVALID, "cells_per_point must be positive"); h->cells_per_point = value; }
+  else if (n == "team_size") h->team_size = (int)value;
+  else if (n == "force_unstaged") h->force_unstaged = value != 0;
+  else if (n == "max_teams") h->max_teams_opt = (int)value;
+  else return fail(h, APD_ERR_INVALID, "unknown option " + n);
+  return APD_OK;
+}
+
+int apd_set_source(apd_handle h, const float* xyz, int stride_bytes, int n, uint64_t cache_key, int mem) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  return set_cloud(h, true, xyz, stride_bytes, n, cache_key, mem);
+}
+
+int apd_set_target(apd_handle h, const float* xyz, int stride_bytes, int n, uint64_t cache_key, int mem) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  return set_cloud(h, false, xyz, stride_bytes, n, cache_key, mem);
+}
+
+int apd_swap_source_and_target(apd_handle h) {
+  if (!h) return APD_ERR_INVALID;
+  std::swap(h->src, h->tgt);
+  std::swap(h->src_key, h->tgt_key);
+  h->last_lin_valid = false;  // correspondences_.clear(), fast_apdgicp_impl.hpp:73
+  return APD_OK;
+}
+
+int apd_clear_source(apd_handle h) {
+  if (!h) return APD_ERR_INVALID;
+  h->src.reset();
+  h->src_key = 0;
+  h->last_lin_valid = false;
+  return APD_OK;
+}
+
+int apd_clear_target(apd_handle h) {
+  if (!h) return APD_ERR_INVALID;
+  h->tgt.reset();
+  h->tgt_key = 0;
+  h->last_lin_valid = false;
+  return APD_OK;
+}
+
+static int single_pair_checks(apd_handle h) {
+  if (!h->src || !h->tgt || h->src->total == 0 || h->tgt->total == 0) return fail(h, APD_ERR_NO_INPUT, "source or target cloud not set");
+  const int k = h->prm.k_correspondences;
+  const bool src_needs = !(h->src->cov_valid && h->src->cov_k < 0);
+  const bool tgt_needs = !(h->tgt->cov_valid && h->tgt->cov_k < 0);
+  if ((src_needs && h->src->total < k) || (tgt_needs && h->tgt->total < k)) return fail(h, APD_ERR_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
+  return APD_OK;
+}
+
+int apd_compute_covariances(apd_handle h) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  const int k = h->prm.k_correspondences;
+  for (auto* cs : {h->src.get(), h->tgt.get()}) {
+    if (!cs || cs->total == 0) continue;
+    if (!(cs->cov_valid && cs->cov_k < 0) && cs->total < k) return fail(h, APD_ERR_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
+    int rc = cloudset_prepare(h, cs);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_align(apd_handle h, const float guess[16], apd_result* out) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  // pcl::Registration::align resets converged_ and final_transformation_ before anything else
+  memset(&h->last, 0, sizeof(h->last));
+  for (int i = 0; i < 16; i++) h->last.T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  h->last.fitness = DBL_MAX;
+  h->has_last = false;
+  h->lm_trace.clear();
+  int rc = single_pair_checks(h);
+  if (rc) {
+    h->last.status = rc;
+    if (out) *out = h->last;
+    return rc;
+  }
+  AlignCall c;
+  c.src = h->src.get();
+  c.tgt = h->tgt.get();
+  c.guesses = guess;
+  c.n_pairs = 1;
+  c.want_trace = true;
+  c.want_hessian = true;
+  AlignBatch b;
+  rc = run_align(h, c, &b);
+  if (rc) return rc;
+  int n_rows = 0;
+  double fh[36];
+  CK(cudaMemcpyAsync(&h->last, h->results.p, sizeof(apd_result), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(&n_rows, h->trace_count.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(fh, h->fh.p, sizeof(fh), cudaMemcpyDeviceToHost, h->stream));
+  rc = fetch_counters(h, 1);
+  if (rc) return rc;
+  if (n_rows > 0) {
+    h->lm_trace.resize((size_t)n_rows * 8);
+    CK(cudaMemcpy(h->lm_trace.data(), h->trace.p, sizeof(double) * 8 * n_rows, cudaMemcpyDeviceToHost));
+  }
+  bool any = false;
+  for (int i = 0; i < 36; i++) any |= fh[i] != 0.0;
+  if (any) memcpy(h->final_hessian, fh, sizeof(fh));  // only an accepted step writes final_hessian_
+  h->has_last = true;
+  h->last_lin_valid = true;
+  if (out) *out = h->last;
+  return APD_OK;
+}
+
+int apd_fitness(apd_handle h, double max_range, double* score) {
+  if (!h || !score) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (!h->src || !h->tgt || h->src->total == 0 || h->tgt->total == 0) return fail(h, APD_ERR_NO_INPUT, "source or target cloud not set");
+  int rc = cloudset_build_grid(h, h->src.get());
+  if (rc) return rc;
+  rc = cloudset_build_grid(h, h->tgt.get());
+  if (rc) return rc;
+  float T[16];
+  if (h->has_last) memcpy(T, h->last.T, sizeof(T));
+  else for (int i = 0; i < 16; i++) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  const int blocks = std::max(1, std::min(2 * h->sm_count, (int)((h->src->total + 255) / 256)));
+  CK(h->misc.reserve(sizeof(double) * (2 * blocks + 2) + sizeof(float) * 16));
+  double* partials = h->misc.as<double>();
+  double* res = partials + 2 * blocks;
+  float* dT = reinterpret_cast<float*>(res + 2);
+  CK(cudaMemcpyAsync(dT, T, sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, max_range, partials, blocks, res, h->stream, &h->stats));
+  double r[2];
+  CK(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *score = r[0];
+  return APD_OK;
+}
+
+int apd_transform_source(apd_handle h, const float T[16], float* out_xyz, int out_stride_bytes, int mem) {
+  if (!h || !out_xyz) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (!h->src || h->src->total == 0) return fail(h, APD_ERR_NO_INPUT, "source cloud not set");
+  if (out_stride_bytes < 12 || out_stride_bytes % 4) return fail(h, APD_ERR_INVALID, "bad output stride");
+  const int n = (int)h->src->total;
+  float Th[16];
+  if (T) memcpy(Th, T, sizeof(Th));
+  else if (h->has_last) memcpy(Th, h->last.T, sizeof(Th));
+  else for (int i = 0; i < 16; i++) Th[i] = (i % 5 == 0) ? 1.f : 0.f;
+  CK(h->misc.reserve(sizeof(float) * 16 + 64));
+  float* dT = h->misc.as<float>();
+  CK(cudaMemcpyAsync(dT, Th, sizeof(Th), cudaMemcpyHostToDevice, h->stream));
+  if (mem == APD_MEM_DEVICE) {
+    CK(launch_transform_points(h->src->pts.as<float4>(), n, dT, out_xyz, out_stride_bytes / 4, h->stream, &h->stats));
+    CK(cudaStreamSynchronize(h->stream));
+    return APD_OK;
+  }
+  CK(h->cov_tmp.reserve(sizeof(float) * 3 * (size_t)n));
+  CK(launch_transform_points(h->src->pts.as<float4>(), n, dT, h->cov_tmp.as<float>(), 3, h->stream, &h->stats));
+  if (out_stride_bytes == 12) {
+    CK(cudaMemcpyAsync(out_xyz, h->cov_tmp.p, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CK(cudaMemcpy2DAsync(out_xyz, out_stride_bytes, h->cov_tmp.p, 12, 12, n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_linearize(apd_handle h, const float pose[16], double H[36], double b[6], double* error) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  int rc = single_pair_checks(h);
+  if (rc) return rc;
+  AlignCall c;
+  c.src = h->src.get();
+  c.tgt = h->tgt.get();
+  c.guesses = pose;
+  c.n_pairs = 1;
+  c.mode = 1;
+  rc = run_align(h, c);
+  if (rc) return rc;
+  apd_result r;
+  double Hh[36], bh[6];
+  CK(cudaMemcpyAsync(&r, h->results.p, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(Hh, h->fh.p, sizeof(Hh), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(bh, h->lin_b.p, sizeof(bh), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (H) memcpy(H, Hh, sizeof(Hh));
+  if (b) memcpy(b, bh, sizeof(bh));
+  if (error) *error = r.error;
+  h->last_lin_valid = true;
+  return APD_OK;
+}
+
+int apd_get_final_hessian(apd_handle h, double H[36]) {
+  if (!h || !H) return APD_ERR_INVALID;
+  memcpy(H, h->final_hessian, sizeof(h->final_hessian));
+  return APD_OK;
+}
+
+int apd_get_knn(apd_handle h, int which, int32_t* idx_out) {
+  if (!h || !idx_out) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  apd_cloudset_s* cs = which ? h->tgt.get() : h->src.get();
+  if (!cs || cs->total == 0) return fail(h, APD_ERR_NO_INPUT, "cloud not set");
+  const int k = h->prm.k_correspondences;
+  if (cs->total < k) return fail(h, APD_ERR_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
+  CK(h->knn_tmp.reserve(sizeof(int) * (size_t)cs->total * k));
+  const bool injected = cs->cov_valid && cs->cov_k < 0;
+  if (injected) return fail(h, APD_ERR_UNSUPPORTED, "covariances were injected by the caller; kNN sets are not available");
+  int rc = cloudset_prepare(h, cs, h->knn_tmp.as<int>());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(idx_out, h->knn_tmp.p, sizeof(int) * (size_t)cs->total * k, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_get_covariances(apd_handle h, int which, double* c16_out) {
+  if (!h || !c16_out) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  apd_cloudset_s* cs = which ? h->tgt.get() : h->src.get();
+  if (!cs || cs->total == 0) return fail(h, APD_ERR_NO_INPUT, "cloud not set");
+  if (!(cs->cov_valid && cs->cov_k < 0) && cs->total < h->prm.k_correspondences)
+    return fail(h, APD_ERR_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
+  int rc = cloudset_prepare(h, cs);
+  if (rc) return rc;
+  CK(h->cov_tmp.reserve(sizeof(double) * 16 * (size_t)cs->total));
+  CK(launch_cov_export(cs->view(), 0, h->cov_tmp.as<double>(), h->stream, &h->stats));
+  CK(cudaMemcpyAsync(c16_out, h->cov_tmp.p, sizeof(double) * 16 * (size_t)cs->total, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_set_covariances(apd_handle h, int which, const double* c16, int n) {
+  if (!h || !c16) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  apd_cloudset_s* cs = which ? h->tgt.get() : h->src.get();
+  if (!cs || cs->total == 0) return fail(h, APD_ERR_NO_INPUT, "cloud not set");
+  if (n != cs->total) return fail(h, APD_ERR_INVALID, "covariance count does not match the cloud size");
+  int rc = cloudset_build_grid(h, cs);
+  if (rc) return rc;
+  CK(h->cov_tmp.reserve(sizeof(double) * 16 * (size_t)n));
+  CK(cudaMemcpyAsync(h->cov_tmp.p, c16, sizeof(double) * 16 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  CK(launch_cov_import(cs->view(), 0, h->cov_tmp.as<double>(), h->stream, &h->stats));
+  CK(cudaStreamSynchronize(h->stream));
+  cs->cov_valid = true;
+  cs->cov_k = -1;  // marks "provided by the caller": never recomputed
+  cs->cov_reg = -1;
+  h->last_lin_valid = false;
+  return APD_OK;
+}
+
+static int export_corr(apd_handle h, int32_t* corr_out, float* sq_dist_out, double* m16_out) {
+  if (!h->last_lin_valid || !h->src || !h->tgt) return fail(h, APD_ERR_NO_INPUT, "no linearization has run on the current clouds");
+  const int n = (int)h->src->total;
+  CK(h->cov_tmp.reserve(sizeof(double) * 16 * (size_t)n));
+  CK(h->knn_tmp.reserve(sizeof(int) * 2 * (size_t)n));
+  AlignBatch b;
+  memset(&b, 0, sizeof(b));
+  b.src = h->src->view();
+  b.tgt = h->tgt->view();
+  b.scratch.max_src = h->scratch_max_src;
+  b.scratch.corr = h->sc_corr.as<int>();
+  b.scratch.sqd = h->sc_sqd.as<float>();
+  b.scratch.m0 = h->sc_m0.as<double2>();
+  b.scratch.m1 = h->sc_m1.as<double2>();
+  b.scratch.m2 = h->sc_m2.as<double2>();
+  int* dcorr = h->knn_tmp.as<int>();
+  float* dsqd = reinterpret_cast<float*>(dcorr + n);
+  CK(launch_corr_export(b, 0, 0, 0, dcorr, dsqd, m16_out ? h->cov_tmp.as<double>() : nullptr, h->stream, &h->stats));
+  if (corr_out) CK(cudaMemcpyAsync(corr_out, dcorr, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (sq_dist_out) CK(cudaMemcpyAsync(sq_dist_out, dsqd, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (m16_out) CK(cudaMemcpyAsync(m16_out, h->cov_tmp.p, sizeof(double) * 16 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_get_correspondences(apd_handle h, int32_t* corr_out, float* sq_dist_out) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  return export_corr(h, corr_out, sq_dist_out, nullptr);
+}
+
+int apd_get_mahalanobis(apd_handle h, double* m16_out) {
+  if (!h || !m16_out) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  return export_corr(h, nullptr, nullptr, m16_out);
+}
+
+int apd_get_lm_trace(apd_handle h, double* rows8, int max_rows, int* n_rows) {
+  if (!h) return APD_ERR_INVALID;
+  const int n = (int)(h->lm_trace.size() / 8);
+  if (n_rows) *n_rows = n;
+  if (rows8 && max_rows > 0) memcpy(rows8, h->lm_trace.data(), sizeof(double) * 8 * std::min(n, max_rows));
+  return APD_OK;
+}
+
+// ---- batched path ----
+
+int apd_cloudset_create(apd_handle h, const float* xyz, int stride_bytes, const int32_t* offsets, int n_clouds, int mem, apd_cloudset* out) {
+  if (!h || !out) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  std::shared_ptr<apd_cloudset_s> cs;
+  int rc = make_cloudset(h, xyz, stride_bytes, offsets, n_clouds, mem, &cs);
+  if (rc) return rc;
+  // hand the caller a heap-allocated shared_ptr so the set's lifetime is explicit
+  *out = reinterpret_cast<apd_cloudset>(new std::shared_ptr<apd_cloudset_s>(cs));
+  return APD_OK;
+}
+
+static apd_cloudset_s* deref(apd_cloudset cs) { return cs ? reinterpret_cast<std::shared_ptr<apd_cloudset_s>*>(cs)->get() : nullptr; }
+
+int apd_cloudset_destroy(apd_handle h, apd_cloudset cs) {
+  if (!h) return APD_ERR_INVALID;
+  if (!cs) return APD_OK;
+  DeviceGuard guard(h->device);
+  cudaStreamSynchronize(h->stream);
+  delete reinterpret_cast<std::shared_ptr<apd_cloudset_s>*>(cs);
+  return APD_OK;
+}
+
+int apd_cloudset_prepare(apd_handle h, apd_cloudset cs) {
+  if (!h || !cs) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  return cloudset_prepare(h, deref(cs));
+}
+
+int apd_align_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int32_t* src_idx, const int32_t* tgt_idx, const float* guesses, int n_pairs,
+                    apd_result* out, int out_mem) {
+  if (!h || !src || !tgt || !out || n_pairs < 0) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (n_pairs == 0) return APD_OK;
+  apd_cloudset_s* s = deref(src);
+  apd_cloudset_s* t = deref(tgt);
+  for (int i = 0; i < n_pairs; i++) {
+    const int si = src_idx ? src_idx[i] : i, ti = tgt_idx ? tgt_idx[i] : i;
+    if (si < 0 || si >= s->n_clouds || ti < 0 || ti >= t->n_clouds) return fail(h, APD_ERR_INVALID, "pair index out of range");
+  }
+  AlignCall c;
+  c.src = s;
+  c.tgt = t;
+  c.src_idx = src_idx;
+  c.tgt_idx = tgt_idx;
+  c.guesses = guesses;
+  c.n_pairs = n_pairs;
+  c.min_points = h->prm.k_correspondences;
+  int rc = run_align(h, c);
+  if (rc) return rc;
+  h->last_lin_valid = false;
+  if (out_mem == APD_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(out, h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToDevice, h->stream));
+    h->work_pairs = n_pairs;
+    return APD_OK;
+  }
+  CK(cudaMemcpyAsync(out, h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToHost, h->stream));
+  return fetch_counters(h, n_pairs);
+}
+
+int apd_batch_align(apd_handle h, const float* pts_src, const int32_t* off_src, const float* pts_tgt, const int32_t* off_tgt, int stride_bytes,
+                    const float* guesses, int n_pairs, apd_result* out) {
+  if (!h || !out || n_pairs < 0) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (n_pairs == 0) return APD_OK;
+  std::shared_ptr<apd_cloudset_s> s, t;
+  int rc = make_cloudset(h, pts_src, stride_bytes, off_src, n_pairs, APD_MEM_HOST, &s);
+  if (rc) return rc;
+  rc = make_cloudset(h, pts_tgt, stride_bytes, off_tgt, n_pairs, APD_MEM_HOST, &t);
+  if (rc) return rc;
+  AlignCall c;
+  c.src = s.get();
+  c.tgt = t.get();
+  c.guesses = guesses;
+  c.n_pairs = n_pairs;
+  c.min_points = h->prm.k_correspondences;
+  rc = run_align(h, c);
+  if (rc) return rc;
+  h->last_lin_valid = false;
+  CK(cudaMemcpyAsync(out, h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToHost, h->stream));
+  return fetch_counters(h, n_pairs);
+}
+
+int apd_synchronize(apd_handle h) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_get_launch_count(apd_handle h, int64_t* n) {
+  if (!h || !n) return APD_ERR_INVALID;
+  *n = h->stats.launches;
+  return APD_OK;
+}
+
+int apd_get_work_counters(apd_handle h, int64_t* linearize_passes, int64_t* error_passes, int64_t* pairs) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (h->work_pairs > 0 && h->work_lin == 0 && h->counters.p) {  // a device-output call: counters not fetched yet
+    int rc = fetch_counters(h, (int)h->work_pairs);
+    if (rc) return rc;
+  }
+  if (linearize_passes) *linearize_passes = h->work_lin;
+  if (error_passes) *error_passes = h->work_err;
+  if (pairs) *pairs = h->work_pairs;
+  return APD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// Uniform voxel grid over one cloud and the exact ring-expansion neighbour search on it.
+// Replaces pcl::search::KdTree::nearestKSearch (FLANN, exact, sorted) as the reference uses it at
+// fast_apdgicp/include/fast_gicp/gicp/impl/fast_apdgicp_impl.hpp:151 (1-NN per iteration) and :316
+// (k-NN for covariances). Result order is ascending (d2, original index); d2 is the fp32
+// L2_Simple value with no FMA contraction, so index sets are bit-exact against the CPU oracle.
+//
+// Layout: points are sorted by linear cell id (x fastest), so the cells x0..x1 of one (y,z) row are
+// ONE contiguous run of points: a ring of the search is visited as (2r+1)^2 row lookups, not
+// (2r+1)^3 cell lookups. spts[i].w carries the point's original index (bit pattern).
+#pragma once
+#include "apd_math.cuh"
+
+namespace apd {
+
+struct GridParams {
+  float lox, loy, loz;  // lower corner
+  float h, inv_h;       // cell edge
+  int nx, ny, nz;
+  int ncells;
+  float slack;          // absolute safety margin for cell-boundary bounds (covers fp32 rounding of cell assignment)
+};
+
+// A cloud as the kernels see it. CellT is uint32_t in global memory and uint16_t when the table is
+// staged in shared memory for clouds below 65536 points.
+template <typename CellT>
+struct GridView {
+  const float4* spts;   // sorted points of this cloud
+  const CellT* cells;   // ncells+1 exclusive prefix sums (local indices)
+  GridParams g;
+  int n;
+};
+
+APD_HD int imax(int a, int b) { return a > b ? a : b; }
+APD_HD int imin(int a, int b) { return a < b ? a : b; }
+
+APD_HD int cell_coord(float p, float lo, float inv_h, int n) {
+  const float f = floorf(fmul(fsub(p, lo), inv_h));
+  // NaN and -inf -> 0, +inf -> n-1
+  return (f >= 0.0f) ? ((f < (float)(n - 1)) ? (int)f : (n - 1)) : 0;
+}
+
+APD_HD int cell_index(const GridParams& g, float x, float y, float z) {
+  const int cx = cell_coord(x, g.lox, g.inv_h, g.nx);
+  const int cy = cell_coord(y, g.loy, g.inv_h, g.ny);
+  const int cz = cell_coord(z, g.loz, g.inv_h, g.nz);
+  return (cz * g.ny + cy) * g.nx + cx;
+}
+
+// ---- visitors ----
+// Keys are (float bits of d2) << 32 | original index: d2 >= +0, so unsigned integer order on the key
+// IS the (d2, index) lexicographic order.
+APD_HD unsigned long long make_key(float d2, unsigned idx) { return ((unsigned long long)f2u(d2) << 32) | idx; }
+#define APD_KEY_INF 0x7F800000FFFFFFFFull
+
+template <int K>
+struct TopK {
+  unsigned long long key[K];
+  APD_HD void init() {
+#pragma unroll
+    for (int i = 0; i < K; i++) key[i] = APD_KEY_INF;
+  }
+  APD_HD float bound2() const { return u2f((unsigned)(key[K - 1] >> 32)); }
+  APD_HD void offer(float d2, unsigned idx, int /*pos*/) {
+    const unsigned long long k = make_key(d2, idx);
+    if (k < key[K - 1]) {
+      key[K - 1] = k;
+#pragma unroll
+      for (int j = K - 1; j > 0; j--) {
+        const unsigned long long a = key[j - 1], b = key[j];
+        const bool sw = b < a;
+        key[j - 1] = sw ? b : a;
+        key[j] = sw ? a : b;
+      }
+    }
+  }
+};
+
+struct Top1 {
+  unsigned long long key;
+  int pos;  // sorted position of the best point
+  APD_HD void init() { key = APD_KEY_INF; pos = -1; }
+  APD_HD float bound2() const { return u2f((unsigned)(key >> 32)); }
+  APD_HD void offer(float d2, unsigned idx, int p) {
+    const unsigned long long k = make_key(d2, idx);
+    if (k < key) { key = k; pos = p; }
+  }
+};
+
+template <typename CellT, typename Visitor>
+APD_HD void visit_run(const GridView<CellT>& G, int c0, int c1, float qx, float qy, float qz, Visitor& vis) {
+  const int s = (int)G.cells[c0];
+  const int e = (int)G.cells[c1];
+  for (int p = s; p < e; p++) {
+    const float4 t = G.spts[p];
+    vis.offer(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), f2u(t.w), p);
+  }
+}
+
+// Exact search. `limit2` bounds the radius of interest (squared): once every unvisited point is
+// provably farther than both the visitor's current bound and limit2, the search stops. Pass
+// +inf for an unbounded search. NaN query coordinates fall into cell 0 and produce NaN distances,
+// which never beat a key (the visitor stays empty), like a kd-tree that finds nothing.
+template <typename CellT, typename Visitor>
+APD_HD void grid_search(const GridView<CellT>& G, float qx, float qy, float qz, float limit2, Visitor& vis) {
+  const GridParams& g = G.g;
+  const int cx = cell_coord(qx, g.lox, g.inv_h, g.nx);
+  const int cy = cell_coord(qy, g.loy, g.inv_h, g.ny);
+  const int cz = cell_coord(qz, g.loz, g.inv_h, g.nz);
+  const int rmax = imax(imax(imax(cx, g.nx - 1 - cx), imax(cy, g.ny - 1 - cy)), imax(cz, g.nz - 1 - cz));
+  for (int r = 0; r <= rmax; r++) {
+    const int z0 = imax(cz - r, 0), z1 = imin(cz + r, g.nz - 1);
+    const int y0 = imax(cy - r, 0), y1 = imin(cy + r, g.ny - 1);
+    const int xa = cx - r, xb = cx + r;
+    const int x0 = imax(xa, 0), x1 = imin(xb, g.nx - 1);
+    for (int z = z0; z <= z1; z++) {
+      // lower bound of |dz| to any point of this z-slab (0 for the query's own slab)
+      float dz = 0.f;
+      if (z < cz) dz = qz - (g.loz + (float)(z + 1) * g.h);
+      else if (z > cz) dz = (g.loz + (float)z * g.h) - qz;
+      dz = fmaxf(dz - g.slack, 0.f);
+      const bool zface = (z == cz - r) || (z == cz + r);
+      for (int y = y0; y <= y1; y++) {
+        float dy = 0.f;
+        if (y < cy) dy = qy - (g.loy + (float)(y + 1) * g.h);
+        else if (y > cy) dy = (g.loy + (float)y * g.h) - qy;
+        dy = fmaxf(dy - g.slack, 0.f);
+        // whole row out of reach (strictly farther than the current bound): skip. 0.99999 absorbs the
+        // rounding of this bound itself; the bound is re-read per row so it tightens inside a ring.
+        if ((dz * dz + dy * dy) * 0.99999f > fminf(vis.bound2(), limit2)) continue;
+        const bool face = zface || (y == cy - r) || (y == cy + r);
+        const int rowbase = (z * g.ny + y) * g.nx;
+        if (face) {
+          // the full x-run of this ring belongs to the shell (r == 0: the query's own cell)
+          visit_run(G, rowbase + x0, rowbase + x1 + 1, qx, qy, qz, vis);
+        } else {
+          // interior row: only the two end cells at x = cx-r and cx+r are new
+          if (xa >= 0) visit_run(G, rowbase + xa, rowbase + xa + 1, qx, qy, qz, vis);
+          if (xb <= g.nx - 1) visit_run(G, rowbase + xb, rowbase + xb + 1, qx, qy, qz, vis);
+        }
+      }
+    }
+    // Every unvisited point lies outside the cube of cells [c-r, c+r] along at least one axis, hence
+    // at least `reach` away, where reach = min over the cube faces that still have cells beyond them
+    // of the distance from the query to that face. Stop when that clears the current bound.
+    float reach = FLT_MAX;
+    if (cx - r > 0) reach = fminf(reach, qx - (g.lox + (float)(cx - r) * g.h));
+    if (cx + r < g.nx - 1) reach = fminf(reach, (g.lox + (float)(cx + r + 1) * g.h) - qx);
+    if (cy - r > 0) reach = fminf(reach, qy - (g.loy + (float)(cy - r) * g.h));
+    if (cy + r < g.ny - 1) reach = fminf(reach, (g.loy + (float)(cy + r + 1) * g.h) - qy);
+    if (cz - r > 0) reach = fminf(reach, qz - (g.loz + (float)(cz - r) * g.h));
+    if (cz + r < g.nz - 1) reach = fminf(reach, (g.loz + (float)(cz + r + 1) * g.h) - qz);
+    if (reach == FLT_MAX) break;  // the cube covers the whole grid
+    reach = reach - g.slack;
+    if (reach > 0.f) {
+      const float reach2 = reach * reach * 0.99999f;
+      if (reach2 > fminf(vis.bound2(), limit2)) break;
+    }
+  }
+}
+
+}  // namespace apd

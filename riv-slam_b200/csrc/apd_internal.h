@@ -1,0 +1,109 @@
+// Internal interface between the C ABI (apd_capi.cu) and the kernel launchers
+// (apd_build.cu, apd_knn_cov.cu, apd_align.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/apdgicp_b200.h"
+#include "apd_grid.cuh"
+
+namespace apd {
+
+// Device-side description of a ragged batch of clouds ("cloud set"). All arrays live in HBM.
+struct CloudSetView {
+  int n_clouds;
+  int total_points;
+  const int* pt_off;          // [n_clouds+1] point offsets
+  const long long* cell_off;  // [n_clouds+1] offsets into `cells`; cloud c owns grid[c].ncells+1 entries from cell_off[c]
+  float4* pts;                // original order, (x, y, z, 1)
+  float4* spts;               // cell-sorted, w = original local index (bit pattern)
+  unsigned* cells;            // per-cloud exclusive prefix sums of cell populations (local indices)
+  GridParams* grid;           // [n_clouds]
+  double2* cov0;              // sorted order: (xx, xy)
+  double2* cov1;              //               (xz, yy)
+  double2* cov2;              //               (yz, zz)
+};
+
+struct DeviceParams {
+  int k;
+  int regularization;
+  int max_iterations;
+  int optimizer;
+  int lm_max_iterations;
+  float corr_limit2;        // float upper bound of max_corr_dist^2 for search pruning
+  double corr_thr2;         // max_corr_dist^2 (double product, fast_apdgicp_impl.hpp:156)
+  double rotation_epsilon;
+  double transformation_epsilon;
+  double lm_init_lambda_factor;
+  double dist_var;
+  double sin_az;            // sin(azimuth_var / 180 * pi)
+  double sin_el;            // sin(elevation_var / 180 * pi)
+};
+
+// Per concurrent pair slot scratch of the align kernel (sorted-source order).
+struct AlignScratch {
+  int max_src;        // points per slot
+  int* corr;          // [slots * max_src] sorted position in the target, -1 = none
+  float* sqd;         // [slots * max_src]
+  double2* m0;        // Mahalanobis (xx, xy)
+  double2* m1;        //             (xz, yy)
+  double2* m2;        //             (yz, zz)
+};
+
+enum TeamKind { TEAM_CTA = 0, TEAM_CLUSTER = 1, TEAM_GRID = 2 };
+constexpr int kAlignThreads = 512;
+constexpr int kKnnThreads = 512;
+constexpr int kNRed = 30;  // doubles per reduction record (see apd_align.cu)
+
+struct AlignBatch {
+  CloudSetView src, tgt;
+  const int* src_idx;      // [n_pairs] or nullptr (identity map)
+  const int* tgt_idx;
+  const float* guesses;    // [n_pairs*16] row-major or nullptr (identity)
+  apd_result* out;         // [n_pairs] device
+  double* final_hessian;   // [n_pairs*36] or nullptr
+  double* lin_b;           // [n_pairs*6] or nullptr (mode 1: the gradient of evaluateCost)
+  double* trace;           // [n_pairs * trace_rows * 8] or nullptr
+  int* trace_count;        // [n_pairs] or nullptr
+  int trace_rows;
+  int n_pairs;
+  int* work_counter;       // dynamic pair fetch (TEAM_CTA)
+  unsigned long long* counters;  // [0] linearize passes, [1] error passes
+  double* grid_partials;   // TEAM_GRID: [2 * gridDim.x * kNRed]
+  AlignScratch scratch;
+  DeviceParams prm;
+  int min_points;          // pairs with a cloud smaller than this report APD_ERR_TOO_FEW_POINTS (k; 0 = no check)
+  int mode;                // 0 = align, 1 = linearize only (evaluateCost): out->error, final_hessian, lin_b
+  double max_range;        // fitness gate (getFitnessScore max_range)
+};
+
+struct LaunchStats {
+  long long launches = 0;
+};
+
+// ---- launchers (all asynchronous on `stream`) ----
+struct BuildWorkspace {
+  unsigned* bbox;    // [6 * n_clouds]
+  int* cellid;       // [total_points]
+  unsigned* cursor;  // [total_cells]
+};
+// tiles: device int4 (cloud, first point, count, 0) covering every point of the set
+cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, const int4* tiles, int n_tiles, const int* cell_cap /*device [n_clouds]*/,
+                              long long total_cells, int max_cloud_points, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
+                           int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,
+                         LaunchStats* st);
+cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& tgt, int t, const float* T16 /*device*/, double max_range,
+                           double* partials /*device [2*blocks]*/, int blocks, double* out /*device [2]: score, count*/, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_pack_points(const float* xyz, int stride_floats, long long n, float4* out, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_transform_points(const float4* pts, int n, const float* T16 /*device*/, float* out, int out_stride_floats, cudaStream_t stream, LaunchStats* st);
+// gather/scatter between original and sorted order for the covariance getters / setters
+cudaError_t launch_cov_export(const CloudSetView& cs, int cloud, double* out16 /*device n*16*/, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_cov_import(const CloudSetView& cs, int cloud, const double* in16 /*device n*16*/, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_corr_export(const AlignBatch& b, int slot, int s /*source cloud*/, int t /*target cloud*/, int* corr_out, float* sqd_out, double* m16_out, cudaStream_t stream, LaunchStats* st);
+
+size_t align_static_smem();
+int align_max_teams(int team_kind, int team_size, bool stage_target, size_t smem_bytes);
+
+}  // namespace apd

@@ -1,0 +1,153 @@
+// k-nearest-neighbour search fused with covariance estimation and regularisation:
+// FastAPDGICP::calculate_covariances, fast_apdgicp/include/fast_gicp/gicp/impl/fast_apdgicp_impl.hpp:303-363.
+//
+// One thread per query point, queries taken in cell-sorted order so the lanes of a warp walk the
+// same neighbourhood. For clouds that fit, the whole grid (sorted float4 points + a uint16 cell
+// table) is staged once per CTA in shared memory and every candidate read is an LDS; larger clouds
+// read the same structures from HBM/L2. The top-k list lives in registers as 64-bit
+// (d2 bits << 32 | index) keys, which makes the (d2, index) order a single integer compare.
+// The covariance follows the reference's arithmetic in the reference's order (fp64, one rounding
+// per operation) so that the Jacobi sweep sees the same matrix as the CPU oracle.
+#include <cstdint>
+
+#include "apd_internal.h"
+
+namespace apd {
+
+namespace {
+
+// fast_apdgicp_impl.hpp:326-359
+__device__ __forceinline__ Sym3 regularize(const Sym3& cov, int method) {
+  if (method == APD_REG_NONE) return cov;
+  if (method == APD_REG_FROBENIUS) {
+    Sym3 C = cov;
+    C.xx = dadd(C.xx, 1e-3); C.yy = dadd(C.yy, 1e-3); C.zz = dadd(C.zz, 1e-3);
+    Sym3 Ci = inverse(C);
+    const double fro = sqrt(Ci.xx * Ci.xx + Ci.yy * Ci.yy + Ci.zz * Ci.zz + 2.0 * (Ci.xy * Ci.xy + Ci.xz * Ci.xz + Ci.yz * Ci.yz));
+    Ci.xx /= fro; Ci.xy /= fro; Ci.xz /= fro; Ci.yy /= fro; Ci.yz /= fro; Ci.zz /= fro;
+    return inverse(Ci);
+  }
+  double w[3], V[9], values[3];
+  sym_eig3(cov, w, V);
+  if (method == APD_REG_PLANE) {
+    values[0] = 1.0; values[1] = 1.0; values[2] = 1e-3;
+  } else if (method == APD_REG_MIN_EIG) {
+    for (int i = 0; i < 3; i++) values[i] = fmax(w[i], 1e-3);
+  } else {  // NORMALIZED_MIN_EIG
+    const double mx = fmax(w[0], fmax(w[1], w[2]));
+    for (int i = 0; i < 3; i++) values[i] = fmax(w[i] / mx, 1e-3);
+  }
+  return recompose(V, values);
+}
+
+template <int K, bool STAGED>
+__global__ void __launch_bounds__(kKnnThreads, 1)
+knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int4 tile = tiles[blockIdx.x];
+  const int c = tile.x;
+  const int base = cs.pt_off[c];
+  const int n = cs.pt_off[c + 1] - base;
+  const GridParams g = cs.grid[c];
+  const float4* gspts = cs.spts + base;
+  const unsigned* gcells = cs.cells + cs.cell_off[c];
+
+  typedef typename std::conditional<STAGED, uint16_t, unsigned>::type CellT;
+  GridView<CellT> G;
+  G.g = g;
+  G.n = n;
+  if (STAGED) {
+    float4* s_pts = reinterpret_cast<float4*>(smem_raw);
+    uint16_t* s_cells = reinterpret_cast<uint16_t*>(smem_raw + sizeof(float4) * (size_t)n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_pts[i] = gspts[i];
+    for (int i = threadIdx.x; i <= g.ncells; i += blockDim.x) s_cells[i] = (uint16_t)gcells[i];
+    __syncthreads();
+    G.spts = s_pts;
+    G.cells = reinterpret_cast<const CellT*>(s_cells);
+  } else {
+    G.spts = gspts;
+    G.cells = reinterpret_cast<const CellT*>(gcells);
+  }
+
+  const float4* opts = cs.pts + base;  // original order, for the neighbour gather
+  const double inv_div = (double)k;
+  for (int q = tile.y + threadIdx.x; q < tile.y + tile.z; q += blockDim.x) {
+    const float4 p = G.spts[q];
+    const unsigned self = __float_as_uint(p.w);
+    TopK<K> tk;
+    tk.init();
+    grid_search(G, p.x, p.y, p.z, __int_as_float(0x7f800000), tk);
+
+    // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324)
+    double mx = 0.0, my = 0.0, mz = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (j < k) {
+        unsigned idx = (unsigned)(tk.key[j] & 0xFFFFFFFFull);
+        if (idx >= (unsigned)n) idx = self;  // non-finite query: no neighbour found
+        const float4 nb = opts[idx];
+        mx = dadd(mx, (double)nb.x);
+        my = dadd(my, (double)nb.y);
+        mz = dadd(mz, (double)nb.z);
+      }
+    }
+    mx = mx / inv_div; my = my / inv_div; mz = mz / inv_div;
+    Sym3 cov{0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (j < k) {
+        unsigned idx = (unsigned)(tk.key[j] & 0xFFFFFFFFull);
+        if (idx >= (unsigned)n) idx = self;
+        const float4 nb = opts[idx];
+        const double dx = dsub((double)nb.x, mx), dy = dsub((double)nb.y, my), dz = dsub((double)nb.z, mz);
+        cov.xx = dadd(cov.xx, dmul(dx, dx));
+        cov.xy = dadd(cov.xy, dmul(dx, dy));
+        cov.xz = dadd(cov.xz, dmul(dx, dz));
+        cov.yy = dadd(cov.yy, dmul(dy, dy));
+        cov.yz = dadd(cov.yz, dmul(dy, dz));
+        cov.zz = dadd(cov.zz, dmul(dz, dz));
+      }
+    }
+    cov.xx /= inv_div; cov.xy /= inv_div; cov.xz /= inv_div; cov.yy /= inv_div; cov.yz /= inv_div; cov.zz /= inv_div;
+    const Sym3 r = regularize(cov, method);
+    cs.cov0[base + q] = make_double2(r.xx, r.xy);
+    cs.cov1[base + q] = make_double2(r.xz, r.yy);
+    cs.cov2[base + q] = make_double2(r.yz, r.zz);
+    if (knn_out) {
+      int* row = knn_out + ((size_t)base + self) * k;
+#pragma unroll
+      for (int j = 0; j < K; j++)
+        if (j < k) row[j] = (int)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
+    }
+  }
+}
+
+template <int K>
+cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm, int* knn_out,
+                     cudaStream_t stream) {
+  if (staged) {
+    cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
+  } else {
+    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm, int* knn_out,
+                           cudaStream_t stream, LaunchStats* st) {
+  if (n_tiles == 0) return cudaSuccess;
+  if (st) st->launches++;
+  const int k = prm.k;
+  if (k <= 8) return launch_k<8>(cs, tiles, n_tiles, staged, smem_bytes, prm, knn_out, stream);
+  if (k <= 10) return launch_k<10>(cs, tiles, n_tiles, staged, smem_bytes, prm, knn_out, stream);
+  if (k <= 15) return launch_k<15>(cs, tiles, n_tiles, staged, smem_bytes, prm, knn_out, stream);
+  if (k <= 20) return launch_k<20>(cs, tiles, n_tiles, staged, smem_bytes, prm, knn_out, stream);
+  if (k <= 32) return launch_k<32>(cs, tiles, n_tiles, staged, smem_bytes, prm, knn_out, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace apd

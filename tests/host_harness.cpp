@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE — compiles the product's search/math headers (riv-slam_b200/csrc/apd_grid.cuh,
+// apd_math.cuh) as plain C++ so the exact ring-expansion search, the Jacobi eigen-solver, the LDL^T
+// solve and so3_exp can be unit-tested on a machine without a GPU. Nothing here is shipped or
+// called by the product; the GPU parity tests remain the real gate.
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC tests/host_harness.cpp -o tests/_host_harness.so
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../riv-slam_b200/csrc/apd_grid.cuh"
+
+using namespace apd;
+
+namespace {
+
+struct HostGrid {
+  std::vector<float4> spts;
+  std::vector<unsigned> cells;
+  GridParams g;
+};
+
+// same rules as grid_params_kernel / count / scan / scatter / cell_sort in apd_build.cu
+HostGrid build(const float* xyz, int n, int cell_cap) {
+  HostGrid G;
+  float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  bool any = false;
+  for (int i = 0; i < n; i++) {
+    const float* p = xyz + 3 * i;
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+    for (int a = 0; a < 3; a++) {
+      if (!any) { lo[a] = hi[a] = p[a]; }
+      lo[a] = std::min(lo[a], p[a]);
+      hi[a] = std::max(hi[a], p[a]);
+    }
+    any = true;
+  }
+  const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+  const long long cap = std::max(cell_cap, 1);
+  const float emax = std::max(std::max(ex, ey), ez);
+  const float floor_h = std::max(emax * 1e-4f, 1e-6f);
+  const float dx = std::max(ex, floor_h), dy = std::max(ey, floor_h), dz = std::max(ez, floor_h);
+  float h = std::max(cbrtf(dx * dy * dz / (float)cap), floor_h);
+  int nx = 1, ny = 1, nz = 1;
+  for (int it = 0; it < 4096; it++) {
+    const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
+    if (fx * fy * fz <= (float)cap && fx < 2e9f && fy < 2e9f && fz < 2e9f) {
+      nx = (int)fx; ny = (int)fy; nz = (int)fz;
+      if ((long long)nx * ny * nz <= cap) break;
+    }
+    h *= 1.02f;
+  }
+  GridParams& g = G.g;
+  g.lox = lo[0]; g.loy = lo[1]; g.loz = lo[2];
+  g.h = h; g.inv_h = 1.0f / h;
+  g.nx = nx; g.ny = ny; g.nz = nz; g.ncells = nx * ny * nz;
+  float amax = 0.f;
+  for (int a = 0; a < 3; a++) amax = std::max(amax, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+  g.slack = 4e-6f * (amax + emax + h) + 1e-30f;
+  std::vector<int> cid(n);
+  G.cells.assign(g.ncells + 1, 0);
+  for (int i = 0; i < n; i++) {
+    cid[i] = cell_index(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    G.cells[cid[i] + 1]++;
+  }
+  for (int c = 0; c < g.ncells; c++) G.cells[c + 1] += G.cells[c];
+  std::vector<unsigned> cur(G.cells.begin(), G.cells.end() - 1);
+  G.spts.resize(n);
+  for (int i = 0; i < n; i++) G.spts[cur[cid[i]]++] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], u2f((unsigned)i));  // ascending index per cell
+  return G;
+}
+
+template <int K>
+void knn_t(const HostGrid& HG, const float* q, int nq, int k, int* idx, float* d2) {
+  GridView<unsigned> G{HG.spts.data(), HG.cells.data(), HG.g, (int)HG.spts.size()};
+  for (int i = 0; i < nq; i++) {
+    TopK<K> tk;
+    tk.init();
+    grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], INFINITY, tk);
+    for (int j = 0; j < k; j++) {
+      idx[(size_t)i * k + j] = (int)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
+      d2[(size_t)i * k + j] = u2f((unsigned)(tk.key[j] >> 32));
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hh_knn(const float* cloud_xyz, int n, int cell_cap, const float* q, int nq, int k, int* idx, float* d2) {
+  const HostGrid G = build(cloud_xyz, n, cell_cap);
+  if (k <= 10) knn_t<10>(G, q, nq, k, idx, d2);
+  else if (k <= 20) knn_t<20>(G, q, nq, k, idx, d2);
+  else knn_t<32>(G, q, nq, k, idx, d2);
+  return G.g.ncells;
+}
+
+// bounded 1-NN: idx = -1 when nothing lies within limit2 (the search may stop early)
+void hh_nn1(const float* cloud_xyz, int n, int cell_cap, const float* q, int nq, float limit2, int* idx, float* d2) {
+  const HostGrid HG = build(cloud_xyz, n, cell_cap);
+  GridView<unsigned> G{HG.spts.data(), HG.cells.data(), HG.g, n};
+  for (int i = 0; i < nq; i++) {
+    Top1 v;
+    v.init();
+    grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], limit2, v);
+    idx[i] = v.pos >= 0 ? (int)f2u(HG.spts[v.pos].w) : -1;
+    d2[i] = v.bound2();
+  }
+}
+
+void hh_sym_eig3(const double* c6, double* w3, double* V9) {
+  Sym3 A{c6[0], c6[1], c6[2], c6[3], c6[4], c6[5]};
+  sym_eig3(A, w3, V9);
+}
+
+void hh_ldlt6(const double* A36, const double* rhs, double* x) {
+  double A[36];
+  memcpy(A, A36, sizeof(A));
+  ldlt6_solve(A, rhs, x);
+}
+
+void hh_so3_exp(const double* w, double* R9) { so3_exp_matrix(w, R9); }
+}
