@@ -234,3 +234,49 @@ def make_sequence(config: int, seq_index: int, n_scans: int, n_points: int = 500
 def relative_gt(poses, t: int) -> np.ndarray:
     """Ground-truth transform mapping scan t+1 coordinates into scan t coordinates."""
     return np.linalg.inv(poses[t]) @ poses[t + 1]
+
+
+# ---------------------------------------------------------------------------------------------
+# Benchmark-scale sequences: every scan has its own seed, so scans can be generated in parallel
+# ---------------------------------------------------------------------------------------------
+
+def _drive_poses(n_scans: int, speed: float, rng: np.random.Generator):
+    poses = []
+    x, y, yaw, yaw_rate = 0.0, 1.0, 0.0, 0.0
+    for t in range(n_scans):
+        poses.append(pose_matrix([x, y, 0.0], [0.2 * np.sin(0.05 * t), 0.2 * np.cos(0.07 * t), yaw]))
+        step = speed * (1.0 + 0.2 * np.sin(0.03 * t)) + rng.normal(0.0, 0.02)
+        yaw_rate = float(np.clip(0.9 * yaw_rate + rng.normal(0.0, 0.15), -2.0, 2.0))
+        yaw_rate -= 0.05 * yaw + 0.2 * (y - 1.0)
+        yaw += float(np.clip(yaw_rate, -3.0, 3.0))
+        x += step * np.cos(np.deg2rad(yaw))
+        y += step * np.sin(np.deg2rad(yaw))
+    return poses
+
+
+def _drive_scan(args):
+    config, seq_index, t, n_scans, n_points, speed, voxel = args
+    rng0 = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
+    length = speed * n_scans * 1.15 + 140.0
+    scene = make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False)
+    poses = _drive_poses(n_scans, speed, rng0)
+    rng = np.random.Generator(np.random.PCG64([pair_seed(config, seq_index), t + 1]))
+    return scan(scene, poses[t], n_points, rng, voxel=voxel)
+
+
+def make_drive(config: int, seq_index: int, n_scans: int, n_points: int = 5000, speed: float = 0.5,
+               voxel: float | None = 0.1, workers: int = 0):
+    """Like :func:`make_sequence` but scan t draws from its own stream PCG64([seed, t+1]), so the scans
+    can be generated by a process pool. Returns (scans, poses)."""
+    rng0 = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
+    length = speed * n_scans * 1.15 + 140.0
+    make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False)  # advance the stream exactly as the workers do
+    poses = _drive_poses(n_scans, speed, rng0)
+    jobs = [(config, seq_index, t, n_scans, n_points, speed, voxel) for t in range(n_scans)]
+    if workers and workers > 1 and n_scans > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, n_scans)) as pool:
+            scans = pool.map(_drive_scan, jobs, chunksize=max(1, n_scans // (4 * workers)))
+    else:
+        scans = [_drive_scan(j) for j in jobs]
+    return scans, poses

@@ -33,8 +33,10 @@ def _oracle(params=None, **extra):
 
 
 def _rot_angle(Ra, Rb):
+    # small-angle safe: sin(angle) from the skew part (arccos of the trace loses half the digits near 0)
     R = Ra.astype(np.float64) @ Rb.astype(np.float64).T
-    return float(np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1)))
+    v = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.arcsin(min(1.0, np.linalg.norm(v))))
 
 
 def _assert_same_transform(T, T_ref):
