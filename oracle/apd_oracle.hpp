@@ -123,8 +123,9 @@ public:
   }
   void swapSourceAndTarget() {  // APD_I:68-75
     src_.swap(tgt_);
-    src_tree_.build(&src_);
-    tgt_tree_.build(&tgt_);
+    std::swap(src_tree_, tgt_tree_);  // source_kdtree_.swap(target_kdtree_), APD_I:71
+    src_tree_.rebind(&src_);
+    tgt_tree_.rebind(&tgt_);
     src_covs_.swap(tgt_covs_);
     src_knn_.swap(tgt_knn_);
     corr_.clear();

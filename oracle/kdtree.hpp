@@ -73,6 +73,7 @@ public:
     nodes_.reserve(n / 4 + 16);
     if (n > 0) build_rec(0, n);
   }
+  void rebind(const std::vector<P3>* pts) { pts_ = pts; }  // same points, moved to another vector
   bool empty() const { return pts_ == nullptr || pts_->empty(); }
   const std::vector<P3>* cloud() const { return pts_; }
 

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -17,20 +19,73 @@ using namespace apd;
 
 namespace {
 
+// Grow-only cache of device allocations shared by a handle and its cloud sets: cudaMalloc/cudaFree
+// cost milliseconds and serialise the device, so blocks released by one step are handed to the next.
+// All work of a handle is ordered on one stream, which makes reuse of a released block safe.
+struct Pool {
+  std::multimap<size_t, void*> free_;
+  std::mutex m;
+  ~Pool() {
+    for (auto& kv : free_) cudaFree(kv.second);
+  }
+  static size_t bucket(size_t bytes) {
+    const size_t g = bytes <= (64u << 10) ? 512 : (bytes <= (16u << 20) ? (64u << 10) : (1u << 20));
+    return (bytes + g - 1) / g * g;
+  }
+  cudaError_t acquire(size_t bytes, void** p, size_t* cap) {
+    const size_t want = bucket(bytes);
+    {
+      std::lock_guard<std::mutex> lk(m);
+      auto it = free_.lower_bound(want);
+      if (it != free_.end() && it->first <= want + want / 2 + (1u << 20)) {
+        *p = it->second;
+        *cap = it->first;
+        free_.erase(it);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+      cudaGetLastError();
+      {
+        std::lock_guard<std::mutex> lk(m);
+        for (auto& kv : free_) cudaFree(kv.second);
+        free_.clear();
+      }
+      e = cudaMalloc(p, want);
+      if (e != cudaSuccess) return e;
+    }
+    *cap = want;
+    return cudaSuccess;
+  }
+  void release(void* p, size_t cap) {
+    std::lock_guard<std::mutex> lk(m);
+    free_.emplace(cap, p);
+  }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  std::shared_ptr<Pool> pool;
+  ~DevBuf() { drop(); }
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
+  void drop() {
+    if (!p) return;
+    if (pool) pool->release(p, cap);
+    else cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    const size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
+    drop();
+    if (pool) return pool->acquire(bytes, &p, &cap);
+    cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) { p = nullptr; return e; }
-    cap = want;
+    cap = bytes;
     return cudaSuccess;
   }
   template <typename T> T* as() const { return static_cast<T*>(p); }
@@ -50,6 +105,9 @@ struct apd_cloudset_s {
   int cov_k = -1, cov_reg = -1;
   bool staged = false;      // every cloud's grid fits the shared-memory staging area
   size_t staged_smem = 0;   // bytes needed for the largest cloud
+  explicit apd_cloudset_s(const std::shared_ptr<Pool>& pool) {
+    for (DevBuf* b : {&pt_off, &cell_off, &pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &cell_cap, &tiles_build, &tiles_knn}) b->pool = pool;
+  }
   CloudSetView view() const {
     CloudSetView v;
     v.n_clouds = n_clouds;
@@ -72,6 +130,7 @@ struct apd_context {
   cudaStream_t stream = nullptr, own_stream = nullptr;
   apd_params prm;
   std::string err;
+  std::shared_ptr<Pool> pool = std::make_shared<Pool>();
   std::shared_ptr<apd_cloudset_s> src, tgt;
   uint64_t src_key = 0, tgt_key = 0;
   LaunchStats stats;
@@ -282,7 +341,7 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
 int make_cloudset(apd_handle h, const float* xyz, int stride_bytes, const int32_t* offsets, int n_clouds, int mem, std::shared_ptr<apd_cloudset_s>* out) {
   if (n_clouds < 0 || (n_clouds > 0 && !offsets)) return fail(h, APD_ERR_INVALID, "bad cloud offsets");
   if (stride_bytes < 12 || stride_bytes % 4) return fail(h, APD_ERR_INVALID, "stride_bytes must be a multiple of 4 and at least 12");
-  auto cs = std::make_shared<apd_cloudset_s>();
+  auto cs = std::make_shared<apd_cloudset_s>(h->pool);
   cs->n_clouds = n_clouds;
   cs->h_off.assign(n_clouds + 1, 0);
   for (int c = 0; c <= n_clouds && n_clouds > 0; c++) {
