@@ -159,7 +159,7 @@ int apd_batch_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
 int apd_synchronize(apd_handle h);
 
 /* ---- tuning knobs with no counterpart in the reference (results never depend on them) ----
- *   "cells_per_point"  voxel-grid cell budget per point (default 8)
+ *   "cells_per_point"  voxel-grid cell budget per point (default 4)
  *   "team_size"        CTAs cooperating on one pair: 0 = automatic, 1 = one CTA, 2..16 = cluster
  *   "force_unstaged"   1 = never stage the target grid in shared memory
  *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit) */

@@ -1,0 +1,159 @@
+// Drop-in for fast_gicp::FastAPDGICP<pcl::PointXYZI, pcl::PointXYZI>
+// (reference fast_apdgicp/include/fast_gicp/gicp/fast_apdgicp.hpp:33-110, impl/fast_apdgicp_impl.hpp).
+// Same class name, namespace, include path and public surface, so
+//   #include <fast_gicp/gicp/fast_apdgicp.hpp>
+// in radar_graph_slam/src/radar_graph_slam/registrations.cpp:38-50 picks this header up when this
+// repository's include/ directory precedes the reference's, and the nodelets keep holding a
+// pcl::Registration<PointXYZI, PointXYZI>::Ptr. Header-only: everything forwards to the C ABI of
+// libapdgicp_b200.so (kNN, covariances, APD Mahalanobis, H/b reduction and the LM loop all run on
+// the GPU). There is no CPU fallback.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include <fast_gicp/gicp/lsq_registration.hpp>
+
+namespace fast_gicp {
+
+template <typename PointSource, typename PointTarget>
+class FastAPDGICP : public LsqRegistration<PointSource, PointTarget> {
+public:
+  using Scalar = float;
+  using Lsq = LsqRegistration<PointSource, PointTarget>;
+  using Matrix4 = typename Lsq::Matrix4;
+  using PointCloudSource = typename Lsq::PointCloudSource;
+  using PointCloudSourcePtr = typename PointCloudSource::Ptr;
+  using PointCloudSourceConstPtr = typename PointCloudSource::ConstPtr;
+  using PointCloudTarget = typename Lsq::PointCloudTarget;
+  using PointCloudTargetPtr = typename PointCloudTarget::Ptr;
+  using PointCloudTargetConstPtr = typename PointCloudTarget::ConstPtr;
+  using CovarianceList = std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>>;
+#ifdef PCL_VERSION_CALC
+#if PCL_VERSION >= PCL_VERSION_CALC(1, 10, 0)
+  using Ptr = pcl::shared_ptr<FastAPDGICP<PointSource, PointTarget>>;
+  using ConstPtr = pcl::shared_ptr<const FastAPDGICP<PointSource, PointTarget>>;
+#else
+  using Ptr = boost::shared_ptr<FastAPDGICP<PointSource, PointTarget>>;
+  using ConstPtr = boost::shared_ptr<const FastAPDGICP<PointSource, PointTarget>>;
+#endif
+#else
+  using Ptr = std::shared_ptr<FastAPDGICP<PointSource, PointTarget>>;
+  using ConstPtr = std::shared_ptr<const FastAPDGICP<PointSource, PointTarget>>;
+#endif
+
+protected:
+  using Lsq::handle_;
+  using Lsq::params_;
+  using pcl::Registration<PointSource, PointTarget, Scalar>::input_;
+  using pcl::Registration<PointSource, PointTarget, Scalar>::target_;
+  using pcl::Registration<PointSource, PointTarget, Scalar>::corr_dist_threshold_;
+
+public:
+  explicit FastAPDGICP(int device = 0) : Lsq(device) {
+    this->reg_name_ = "FastAPDGICP";
+    corr_dist_threshold_ = std::numeric_limits<float>::max();  // fast_apdgicp_impl.hpp:23
+  }
+  ~FastAPDGICP() override {}
+
+  // fast_apdgicp_impl.hpp:34-65
+  void setNumThreads(int n) { params_.num_threads = n; }  // kept for source compatibility; the GPU path ignores it
+  void setCorrespondenceRandomness(int k) { params_.k_correspondences = k; invalidate_covariances(); }
+  void setRegularizationMethod(RegularizationMethod method) { params_.regularization = static_cast<int>(method); invalidate_covariances(); }
+  void setAzimuthVar(double var) { params_.azimuth_var = var; }
+  void setElevationVar(double var) { params_.elevation_var = var; }
+  void setDistVar(double var) { params_.dist_var = var; }
+
+  // fast_apdgicp_impl.hpp:68-87
+  void swapSourceAndTarget() override {
+    input_.swap(target_);
+    source_covs_.swap(target_covs_);
+    std::swap(src_dirty_, tgt_dirty_);
+    std::swap(src_covs_injected_, tgt_covs_injected_);
+    if (handle_) apd_swap_source_and_target(handle_);
+    this->target_cloud_updated_ = true;  // PCL rebuilds its own tree_ on the next align
+  }
+  void clearSource() override {
+    input_.reset();
+    source_covs_.clear();
+    src_covs_injected_ = false;
+    if (handle_) apd_clear_source(handle_);
+  }
+  void clearTarget() override {
+    target_.reset();
+    target_covs_.clear();
+    tgt_covs_injected_ = false;
+    if (handle_) apd_clear_target(handle_);
+  }
+
+  // fast_apdgicp_impl.hpp:90-108: identical pointer -> nothing to do; otherwise the cloud is uploaded
+  // (lazily, at the next align) with the pointer as the device cache key, so the scan that was the
+  // source of the previous registration keeps its grid and covariances when it becomes the target.
+  void setInputSource(const PointCloudSourceConstPtr& cloud) override {
+    if (input_ == cloud) return;
+    pcl::Registration<PointSource, PointTarget, Scalar>::setInputSource(cloud);
+    source_covs_.clear();
+    src_covs_injected_ = false;
+    src_dirty_ = true;
+  }
+  void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
+    if (target_ == cloud) return;
+    pcl::Registration<PointSource, PointTarget, Scalar>::setInputTarget(cloud);
+    target_covs_.clear();
+    tgt_covs_injected_ = false;
+    tgt_dirty_ = true;
+  }
+
+  // fast_apdgicp_impl.hpp:111-118
+  virtual void setSourceCovariances(const CovarianceList& covs) { source_covs_ = covs; src_covs_injected_ = true; src_cov_dirty_ = true; }
+  virtual void setTargetCovariances(const CovarianceList& covs) { target_covs_ = covs; tgt_covs_injected_ = true; tgt_cov_dirty_ = true; }
+  // fast_apdgicp.hpp:68-74 (the reference returns the host copies; here they are fetched from the device on demand)
+  const CovarianceList& getSourceCovariances() { fetch_covariances(0, input_ ? input_->points.size() : 0, source_covs_); return source_covs_; }
+  const CovarianceList& getTargetCovariances() { fetch_covariances(1, target_ ? target_->points.size() : 0, target_covs_); return target_covs_; }
+
+protected:
+  bool sync_inputs() override {
+    if (!Lsq::sync_inputs()) return false;
+    if (!input_ || !target_ || input_->points.empty() || target_->points.empty()) return false;
+    // target first: when it is the previous source the device moves its data across instead of re-uploading
+    if (tgt_dirty_) {
+      if (apd_set_target(handle_, reinterpret_cast<const float*>(target_->points.data()), (int)sizeof(PointTarget), (int)target_->points.size(),
+                         reinterpret_cast<uint64_t>(target_.get()), APD_MEM_HOST) != APD_OK) return false;
+      tgt_dirty_ = false;
+    }
+    if (src_dirty_) {
+      if (apd_set_source(handle_, reinterpret_cast<const float*>(input_->points.data()), (int)sizeof(PointSource), (int)input_->points.size(),
+                         reinterpret_cast<uint64_t>(input_.get()), APD_MEM_HOST) != APD_OK) return false;
+      src_dirty_ = false;
+    }
+    if (src_cov_dirty_ && src_covs_injected_ && source_covs_.size() == input_->points.size()) {
+      if (apd_set_covariances(handle_, 0, reinterpret_cast<const double*>(source_covs_.data()), (int)source_covs_.size()) != APD_OK) return false;
+      src_cov_dirty_ = false;
+    }
+    if (tgt_cov_dirty_ && tgt_covs_injected_ && target_covs_.size() == target_->points.size()) {
+      if (apd_set_covariances(handle_, 1, reinterpret_cast<const double*>(target_covs_.data()), (int)target_covs_.size()) != APD_OK) return false;
+      tgt_cov_dirty_ = false;
+    }
+    return true;
+  }
+
+  void invalidate_covariances() {
+    // k / regularisation changed: device covariances are recomputed lazily (apd_set_params marks them stale)
+    if (!src_covs_injected_) source_covs_.clear();
+    if (!tgt_covs_injected_) target_covs_.clear();
+  }
+
+  void fetch_covariances(int which, size_t n, CovarianceList& out) {
+    if ((which == 0 ? src_covs_injected_ : tgt_covs_injected_) || !handle_ || n == 0) return;
+    if (!sync_inputs()) return;
+    out.resize(n);
+    // Eigen::Matrix4d is 16 contiguous doubles; the matrices are symmetric, so row/column order is immaterial
+    if (apd_get_covariances(handle_, which, reinterpret_cast<double*>(out.data())) != APD_OK) out.clear();
+  }
+
+  CovarianceList source_covs_, target_covs_;
+  bool src_dirty_ = false, tgt_dirty_ = false;
+  bool src_covs_injected_ = false, tgt_covs_injected_ = false;
+  bool src_cov_dirty_ = false, tgt_cov_dirty_ = false;
+};
+
+}  // namespace fast_gicp

@@ -137,7 +137,7 @@ struct apd_context {
   int sm_count = 0;
   size_t smem_optin = 0;
   // tunables (apd_set_option)
-  double cells_per_point = 8.0;
+  double cells_per_point = 4.0;
   int team_size = 0;      // 0 = automatic
   int force_unstaged = 0;
   int max_teams_opt = 0;  // 0 = as many as fit
