@@ -48,7 +48,10 @@ class Scene:
 
 
 def make_scene(rng: np.random.Generator, x_min=-20.0, x_max=120.0, far_wall=True, scale=1.0,
-               boxes_per_100m=40, poles_per_100m=60) -> Scene:
+               boxes_per_100m=40, poles_per_100m=60, clear_radius=3.0, clear_lane=None) -> Scene:
+    """Random static world. Obstacles that would swallow the sensor are dropped: everything within
+    ``clear_radius`` (scaled) of the origin, and, for drives, everything intersecting the lane
+    ``clear_lane = (y_lo, y_hi)`` the vehicle moves in."""
     length = (x_max - x_min)
     nb = max(1, int(round(boxes_per_100m * length / 100.0 / scale)))
     npole = max(1, int(round(poles_per_100m * length / 100.0 / scale)))
@@ -61,6 +64,13 @@ def make_scene(rng: np.random.Generator, x_min=-20.0, x_max=120.0, far_wall=True
     pxy = np.stack([rng.uniform(x_min, x_max, npole), rng.uniform(wy_n + 0.3, wy_p - 0.3, npole)], axis=1)
     pr = rng.uniform(0.08, 0.25, npole) * scale
     ph = -2.0 + rng.uniform(2.0, 6.0, npole) * scale
+    cr = clear_radius * scale
+    keep_b = ~((lo[:, 0] < cr) & (hi[:, 0] > -cr) & (lo[:, 1] < cr) & (hi[:, 1] > -cr))
+    keep_p = np.hypot(pxy[:, 0], pxy[:, 1]) > cr + pr
+    if clear_lane is not None:
+        keep_b &= ~((lo[:, 1] < clear_lane[1]) & (hi[:, 1] > clear_lane[0]))
+        keep_p &= ~((pxy[:, 1] - pr < clear_lane[1]) & (pxy[:, 1] + pr > clear_lane[0]))
+    lo, hi, pxy, pr, ph = lo[keep_b], hi[keep_b], pxy[keep_p], pr[keep_p], ph[keep_p]
     return Scene(ground_z=-2.0, wall_y_pos=wy_p, wall_y_neg=wy_n,
                  far_wall_x=(x_min + 80.0 * scale if far_wall else np.inf),
                  box_lo=lo, box_hi=hi, pole_xy=pxy, pole_r=pr, pole_h=ph, scale=scale)
@@ -213,7 +223,7 @@ def make_sequence(config: int, seq_index: int, n_scans: int, n_points: int = 500
     """
     rng = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
     length = speed * n_scans * 1.15 + 140.0
-    scene = make_scene(rng, x_min=-20.0, x_max=length, far_wall=False)
+    scene = make_scene(rng, x_min=-20.0, x_max=length, far_wall=False, clear_lane=(-1.0, 3.0))
     poses = []
     x, y, z, yaw = 0.0, 1.0, 0.0, 0.0
     yaw_rate = 0.0
@@ -258,7 +268,7 @@ def _drive_scan(args):
     config, seq_index, t, n_scans, n_points, speed, voxel = args
     rng0 = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
     length = speed * n_scans * 1.15 + 140.0
-    scene = make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False)
+    scene = make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False, clear_lane=(-1.0, 3.0))
     poses = _drive_poses(n_scans, speed, rng0)
     rng = np.random.Generator(np.random.PCG64([pair_seed(config, seq_index), t + 1]))
     return scan(scene, poses[t], n_points, rng, voxel=voxel)
@@ -270,7 +280,7 @@ def make_drive(config: int, seq_index: int, n_scans: int, n_points: int = 5000, 
     can be generated by a process pool. Returns (scans, poses)."""
     rng0 = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
     length = speed * n_scans * 1.15 + 140.0
-    make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False)  # advance the stream exactly as the workers do
+    make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False, clear_lane=(-1.0, 3.0))  # advance the stream exactly as the workers do
     poses = _drive_poses(n_scans, speed, rng0)
     jobs = [(config, seq_index, t, n_scans, n_points, speed, voxel) for t in range(n_scans)]
     if workers and workers > 1 and n_scans > 1:
