@@ -182,7 +182,7 @@ struct TargetView {
 template <typename CellT>
 __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts,
                                                     const double2* __restrict__ c0, const double2* __restrict__ c1, const double2* __restrict__ c2,
-                                                    int begin, int end, size_t sbase) {
+                                                    int begin, int end, size_t sbase, bool seeded) {
   const float* Tf = S.Tf;
   const float r00 = Tf[0], r01 = Tf[1], r02 = Tf[2], t0 = Tf[3];
   const float r10 = Tf[4], r11 = Tf[5], r12 = Tf[6], t1 = Tf[7];
@@ -194,7 +194,18 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const A
     const float qz = xform_row_rn(r20, r21, r22, t2, a.x, a.y, a.z);
     Top1 v;
     v.init();
-    grid_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);
+    // From the second linearization on, the previous correspondence seeds the search: its distance
+    // from the new query bounds the nearest neighbour, so one pass over the rows of that ball is
+    // exact (grid_ball_search); a point that had none searches the ball of the gate radius.
+    const int prev = seeded ? B.scratch.corr[sbase + i] : -2;
+    if (prev >= 0) {
+      const float4 t = T.G.spts[prev];
+      grid_ball_search(T.G, qx, qy, qz, fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2), v);
+    } else if (prev == -1 && B.prm.corr_limit2 < 3.0e38f) {
+      grid_ball_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);
+    } else {
+      grid_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);
+    }
     const float d2 = v.bound2();
     const bool ok = v.pos >= 0 && (double)d2 < B.prm.corr_thr2;
     B.scratch.corr[sbase + i] = ok ? v.pos : -1;
@@ -263,7 +274,7 @@ __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const doubl
 // pcl::Registration::getFitnessScore(max_range): mean squared 1-NN distance of the transformed source
 template <typename CellT>
 __device__ __forceinline__ void fitness_pass(const AlignBatch& B, const AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
-                                             double (&acc)[kNRed]) {
+                                             size_t sbase, bool seeded, double (&acc)[kNRed]) {
   const float* Tf = S.Tf;
   for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
     const float4 a = sspts[i];
@@ -272,7 +283,13 @@ __device__ __forceinline__ void fitness_pass(const AlignBatch& B, const AlignSha
     const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
     Top1 v;
     v.init();
-    grid_search(T.G, qx, qy, qz, __int_as_float(0x7f800000), v);
+    const int prev = seeded ? B.scratch.corr[sbase + i] : -1;
+    if (prev >= 0) {  // seeded by the correspondence of the last linearization
+      const float4 t = T.G.spts[prev];
+      grid_ball_search(T.G, qx, qy, qz, sqdist_rn(qx, qy, qz, t.x, t.y, t.z), v);
+    } else {
+      grid_search(T.G, qx, qy, qz, __int_as_float(0x7f800000), v);
+    }
     if (v.pos >= 0 && (double)v.bound2() <= B.max_range) {
       acc[0] += (double)v.bound2();
       acc[1] += 1.0;
@@ -374,7 +391,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     for (int it = 0; have_input && it < (B.mode == 1 ? 1 : P.max_iterations); it++) {
       iterations = it;
       // ---- linearize(x0) ----
-      correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase);
+      correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
 #pragma unroll
       for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
       accumulate_pass<true>(B, S.x0, T, sspts, begin, end, sbase, acc);
@@ -482,7 +499,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     // ---- final_transformation_ = x0.cast<float>() (:78) and getFitnessScore ----
 #pragma unroll
     for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-    if (have_input && B.mode == 0) fitness_pass(B, S, T, sspts, begin, end, acc);
+    if (have_input && B.mode == 0) fitness_pass(B, S, T, sspts, begin, end, sbase, P.max_iterations > 0, acc);
     team_reduce<TEAM, 2>(acc, S, tc);
     if (leader) {
       apd_result r;

@@ -158,4 +158,51 @@ APD_HD void grid_search(const GridView<CellT>& G, float qx, float qy, float qz, 
   }
 }
 
+// Exact search inside a ball whose squared radius `B` is KNOWN to contain the answer (the k-th
+// neighbour for a TopK visitor, the nearest neighbour for Top1): one pass over the (y,z) rows that
+// intersect the ball, each row's run trimmed in x to the ball's chord. No ring bookkeeping and no
+// early termination are needed because B already bounds the result. B comes from
+//   - the triangle inequality between consecutive queries, r_k(q') <= r_k(q) + |q - q'|, or
+//   - the distance to a seed point (the previous iteration's correspondence).
+// Correctness only needs cell_coord to be monotone (it is: fsub, fmul by a positive constant and
+// floorf are monotone) and the radius below to be rounded up; points farther than B are dropped
+// before they reach the visitor, so a visitor that is not yet full never fills up with them.
+template <typename CellT, typename Visitor>
+APD_HD void grid_ball_search(const GridView<CellT>& G, float qx, float qy, float qz, float B, Visitor& vis) {
+  const GridParams& g = G.g;
+  const float rad = sqrtf(B) * 1.00002f + g.slack;
+  const float rad2 = rad * rad * 1.00002f;
+  const int z0 = cell_coord(qz - rad, g.loz, g.inv_h, g.nz), z1 = cell_coord(qz + rad, g.loz, g.inv_h, g.nz);
+  const int y0 = cell_coord(qy - rad, g.loy, g.inv_h, g.ny), y1 = cell_coord(qy + rad, g.loy, g.inv_h, g.ny);
+  for (int z = z0; z <= z1; z++) {
+    const float zl = g.loz + (float)z * g.h;
+    const float dz = fmaxf(fmaxf(zl - qz, qz - (zl + g.h)) - g.slack, 0.f);  // lower bound of |dz| into this slab
+    const float remz = rad2 - dz * dz;
+    if (remz < 0.f) continue;
+    for (int y = y0; y <= y1; y++) {
+      const float yl = g.loy + (float)y * g.h;
+      const float dy = fmaxf(fmaxf(yl - qy, qy - (yl + g.h)) - g.slack, 0.f);
+      const float rem = remz - dy * dy;
+      if (rem < 0.f) continue;
+      const float w = sqrtf(rem) + g.slack;  // half chord of the ball in this row (rounded up via rad2)
+      const int xa = cell_coord(qx - w, g.lox, g.inv_h, g.nx), xb = cell_coord(qx + w, g.lox, g.inv_h, g.nx);
+      const int rowbase = (z * g.ny + y) * g.nx;
+      const int s = (int)G.cells[rowbase + xa];
+      const int e = (int)G.cells[rowbase + xb + 1];
+      for (int p = s; p < e; p++) {
+        const float4 t = G.spts[p];
+        const float d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
+        if (d2 <= B) vis.offer(d2, f2u(t.w), p);
+      }
+    }
+  }
+}
+
+// Upper bound of the squared k-th neighbour distance of q' from the result at q (triangle
+// inequality), inflated so that fp32 rounding of either distance can never make it too small.
+APD_HD float chained_bound2(float rk2_prev, float step2) {
+  const float r = sqrtf(rk2_prev) + sqrtf(step2);
+  return r * r * 1.0002f + 1e-30f;
+}
+
 }  // namespace apd

@@ -38,6 +38,7 @@ struct DeviceParams {
   double dist_var;
   double sin_az;            // sin(azimuth_var / 180 * pi)
   double sin_el;            // sin(elevation_var / 180 * pi)
+  float chain_ratio2;       // kNN: chain a query to the previous one only if |step|^2 <= ratio * r_k^2 (tuning, results identical)
 };
 
 // Per concurrent pair slot scratch of the align kernel (sorted-source order).

@@ -84,9 +84,56 @@ void knn_t(const HostGrid& HG, const float* q, int nq, int k, int* idx, float* d
   }
 }
 
+// the kNN kernel's per-thread schedule: the first query by ring expansion, the following ones inside
+// the ball given by the triangle inequality from the previous result (chunks of `chunk` queries)
+template <int K>
+void knn_chained_t(const HostGrid& HG, int chunk, int k, int* idx, float* d2) {
+  GridView<unsigned> G{HG.spts.data(), HG.cells.data(), HG.g, (int)HG.spts.size()};
+  const int n = (int)HG.spts.size();
+  for (int q0 = 0; q0 < n; q0 += chunk) {
+    float px = 0, py = 0, pz = 0, prk2 = -1.f;
+    for (int q = q0; q < std::min(n, q0 + chunk); q++) {
+      const float4 p = HG.spts[q];
+      TopK<K> tk;
+      tk.init();
+      if (prk2 >= 0.f) grid_ball_search(G, p.x, p.y, p.z, chained_bound2(prk2, sqdist_rn(p.x, p.y, p.z, px, py, pz)), tk);
+      else grid_search(G, p.x, p.y, p.z, INFINITY, tk);
+      px = p.x; py = p.y; pz = p.z; prk2 = tk.bound2();
+      const unsigned self = f2u(p.w);
+      for (int j = 0; j < k; j++) {
+        idx[(size_t)self * k + j] = (int)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
+        d2[(size_t)self * k + j] = u2f((unsigned)(tk.key[j] >> 32));
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// self-kNN of a cloud with the chained-ball schedule; rows in ORIGINAL point order
+void hh_knn_chained(const float* cloud_xyz, int n, int cell_cap, int chunk, int k, int* idx, float* d2) {
+  const HostGrid G = build(cloud_xyz, n, cell_cap);
+  if (k <= 10) knn_chained_t<10>(G, chunk, k, idx, d2);
+  else if (k <= 20) knn_chained_t<20>(G, chunk, k, idx, d2);
+  else knn_chained_t<32>(G, chunk, k, idx, d2);
+}
+
+// seeded 1-NN: ball of radius |q - cloud[seed]| (seed < 0: ball of radius sqrt(limit2))
+void hh_nn1_seeded(const float* cloud_xyz, int n, int cell_cap, const float* q, int nq, const int* seed, float limit2, int* idx, float* d2) {
+  const HostGrid HG = build(cloud_xyz, n, cell_cap);
+  GridView<unsigned> G{HG.spts.data(), HG.cells.data(), HG.g, n};
+  for (int i = 0; i < nq; i++) {
+    Top1 v;
+    v.init();
+    float B = limit2;
+    if (seed[i] >= 0) B = sqdist_rn(q[3 * i], q[3 * i + 1], q[3 * i + 2], cloud_xyz[3 * seed[i]], cloud_xyz[3 * seed[i] + 1], cloud_xyz[3 * seed[i] + 2]);
+    grid_ball_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], B, v);
+    idx[i] = v.pos >= 0 ? (int)f2u(HG.spts[v.pos].w) : -1;
+    d2[i] = v.bound2();
+  }
+}
 
 int hh_knn(const float* cloud_xyz, int n, int cell_cap, const float* q, int nq, int k, int* idx, float* d2) {
   const HostGrid G = build(cloud_xyz, n, cell_cap);

@@ -387,3 +387,60 @@ def test_full_size_properties(pair5k):
     assert r4[0]["converged"]
     assert np.abs(r4[0]["T"].astype(np.float64) - Tm).max() < 2e-3
     assert r4[0]["fitness"] < 1e-5
+
+
+# ---------------------------------------------------------------- large clouds (configs C3 / C5)
+
+def test_large_clouds_grid_team_and_chained_knn():
+    """Source and target far beyond the shared-memory staging limit: global-memory grid, the
+    cooperative whole-GPU team (TEAM_GRID), and every other team shape must agree with the oracle."""
+    from riv_slam_b200 import datagen
+    src, tgt, _ = datagen.make_pair(5, 0, n_src=40000, n_tgt=70000, voxel=None)
+    o = _oracle(LAUNCH_PARAMS)
+    o.set_source(src); o.set_target(tgt)
+    rc, T0, conv0, it0 = o.align()
+    assert rc == 0
+    knn_ref = o.knn(0)
+    for team, chain in ((0, 0.0), (1, 0.0), (8, 0.5)):
+        g = _gpu(LAUNCH_PARAMS)
+        g.setOption("team_size", team)
+        g.setOption("knn_chain_ratio", chain)   # the triangle-inequality schedule must give the same sets
+        g.setInputSource(src); g.setInputTarget(tgt)
+        assert np.array_equal(g.getKnn(0), knn_ref)
+        g.align(want_output=False)
+        assert g.hasConverged() == conv0 and g.nr_iterations() == it0
+        _assert_same_transform(g.getFinalTransformation(), T0)
+        assert abs(g.getFitnessScore() - o.fitness()) <= REL_TOL * o.fitness()
+        e, H, b = g.evaluateCost(T0)
+        e0, H0, b0 = o.linearize(T0)
+        assert np.abs(H - H0).max() <= REL_TOL * np.abs(H0).max() and np.abs(b - b0).max() <= REL_TOL * np.abs(b0).max()
+
+
+def test_scan_to_submap_reuses_target():
+    """Config C3: several scans against one large accumulated target; the target is prepared once."""
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import Handle, CloudSet, align_pairs
+    scans, poses = datagen.make_sequence(3, 0, n_scans=6, n_points=3000)
+    # submap = first four scans moved into the frame of scan 0
+    sub = []
+    for t in range(4):
+        Trel = np.linalg.inv(poses[0]) @ poses[t]
+        p = scans[t].copy()
+        p[:, :3] = (scans[t][:, :3].astype(np.float64) @ Trel[:3, :3].T + Trel[:3, 3]).astype(np.float32)
+        sub.append(p)
+    submap = np.concatenate(sub)
+    H = Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+    S = CloudSet(H, scans[4:6])
+    T = CloudSet(H, [submap])
+    guesses = np.stack([(np.linalg.inv(poses[0]) @ poses[3]).astype(np.float32)] * 2)   # last known pose as the guess (SMO:461-465)
+    res = align_pairs(H, S, T, tgt_idx=np.zeros(2, dtype=np.int32), guesses=guesses)
+    for j in range(2):
+        o = _oracle(LAUNCH_PARAMS)
+        o.set_source(scans[4 + j]); o.set_target(submap)
+        rc, T0, conv0, it0 = o.align(guesses[j])
+        assert bool(res[j]["converged"]) == conv0 and res[j]["iterations"] == it0
+        _assert_same_transform(res[j]["T"], T0)
+        # sanity only: with the launch-file epsilon (0.1 m) the loop stops as soon as a step is below 10 cm
+        gt = np.linalg.inv(poses[0]) @ poses[4 + j]
+        assert np.abs(res[j]["T"][:3, 3] - gt[:3, 3]).max() < 1.5

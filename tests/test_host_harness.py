@@ -25,6 +25,8 @@ def hh():
     L = C.CDLL(out)
     L.hh_knn.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _ip, _fp]
     L.hh_nn1.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_float, _ip, _fp]
+    L.hh_knn_chained.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _fp]
+    L.hh_nn1_seeded.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, _ip, C.c_float, _ip, _fp]
     L.hh_sym_eig3.argtypes = [_dp, _dp, _dp]
     L.hh_ldlt6.argtypes = [_dp, _dp, _dp]
     L.hh_so3_exp.argtypes = [_dp, _dp]
@@ -78,6 +80,41 @@ def test_bounded_nn1(hh, small_pair):
         ok = d0[:, 0] < limit2
         assert np.array_equal(idx[ok], i0[ok, 0]) and np.array_equal(d2[ok], d0[ok, 0])
         assert not (d2[~ok] < limit2).any()   # nothing inside the gate is ever invented
+
+
+@pytest.mark.parametrize("cap,chunk", [(1, 7), (2000, 1), (5000, 10), (5000, 64), (40000, 5)])
+def test_chained_ball_knn_is_exact(hh, small_pair, cap, chunk):
+    """The kNN kernel's schedule: ring search for the first query of a chunk, triangle-inequality ball for the rest."""
+    _, tgt, _ = small_pair
+    lat = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(5), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    lat = lat[np.random.default_rng(0).permutation(len(lat))]
+    for cloud in (tgt, lat):
+        c = np.ascontiguousarray(cloud[:, :3], np.float32)
+        for k in (10, 20):
+            idx = np.zeros((len(c), k), np.int32)
+            d2 = np.zeros((len(c), k), np.float32)
+            hh.hh_knn_chained(c.ctypes.data_as(_fp), len(c), cap, chunk, k, idx.ctypes.data_as(_ip), d2.ctypes.data_as(_fp))
+            i0, d0 = knn_bruteforce(cloud, cloud, k)
+            assert np.array_equal(i0, idx) and np.array_equal(d0, d2)
+
+
+def test_seeded_ball_nn1_is_exact(hh, small_pair):
+    src, tgt, _ = small_pair
+    c = np.ascontiguousarray(tgt[:, :3])
+    q = np.ascontiguousarray(src[:, :3])
+    i0, d0 = knn_bruteforce(tgt, src, 1)
+    rng = np.random.default_rng(5)
+    for limit2 in (4.0, np.inf):
+        # seeds: the true neighbour, a random point, or none
+        seed = np.where(rng.uniform(size=len(q)) < 0.4, i0[:, 0], rng.integers(0, len(c), len(q))).astype(np.int32)
+        seed[rng.uniform(size=len(q)) < 0.2] = -1
+        idx = np.zeros(len(q), np.int32)
+        d2 = np.zeros(len(q), np.float32)
+        hh.hh_nn1_seeded(c.ctypes.data_as(_fp), len(c), 6000, q.ctypes.data_as(_fp), len(q), seed.ctypes.data_as(_ip), limit2,
+                         idx.ctypes.data_as(_ip), d2.ctypes.data_as(_fp))
+        ok = (seed >= 0) | (d0[:, 0] <= limit2)
+        assert np.array_equal(idx[ok], i0[ok, 0]) and np.array_equal(d2[ok], d0[ok, 0])
+        assert (idx[~ok] == -1).all()
 
 
 def test_small_solvers(hh):
