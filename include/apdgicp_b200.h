@@ -162,8 +162,7 @@ int apd_synchronize(apd_handle h);
  *   "cells_per_point"  voxel-grid cell budget per point (default 4)
  *   "team_size"        CTAs cooperating on one pair: 0 = automatic, 1 = one CTA, 2..16 = cluster
  *   "force_unstaged"   1 = never stage the target grid in shared memory
- *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit)
- *   "knn_chain_ratio"  kNN: reuse the previous query's radius when |step| <= ratio * r_k (0 = never) */
+ *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit) */
 int apd_set_option(apd_handle h, const char* name, double value);
 
 /* ---- introspection for benchmarks ---- */

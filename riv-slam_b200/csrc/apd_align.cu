@@ -176,6 +176,8 @@ template <typename CellT>
 struct TargetView {
   GridView<CellT> G;
   const double2 *cov0, *cov1, *cov2;  // global, sorted target order
+  const int* inv0;                    // original index -> sorted position (this cloud)
+  int cloud;                          // index in B.tgt (for the coarse pyramid levels)
 };
 
 // update_correspondences for the calling thread's points (fast_apdgicp_impl.hpp:146-193)
@@ -203,8 +205,13 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const A
       grid_ball_search(T.G, qx, qy, qz, fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2), v);
     } else if (prev == -1 && B.prm.corr_limit2 < 3.0e38f) {
       grid_ball_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);
+    } else if (B.prm.corr_limit2 < 3.0e38f) {
+      grid_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);  // the gate bounds the number of rings
     } else {
-      grid_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);
+      // no gate (constructor default FLT_MAX): unbounded search through the pyramid; a hit on a coarse
+      // level is mapped back to its position in the fine order
+      if (pyramid_search<CellT, Top1, false>(T.G, B.tgt, T.cloud, qx, qy, qz, B.prm.corr_limit2, v) > 0 && v.pos >= 0)
+        v.pos = T.inv0[(unsigned)(v.key & 0xFFFFFFFFull)];
     }
     const float d2 = v.bound2();
     const bool ok = v.pos >= 0 && (double)d2 < B.prm.corr_thr2;
@@ -288,7 +295,7 @@ __device__ __forceinline__ void fitness_pass(const AlignBatch& B, const AlignSha
       const float4 t = T.G.spts[prev];
       grid_ball_search(T.G, qx, qy, qz, sqdist_rn(qx, qy, qz, t.x, t.y, t.z), v);
     } else {
-      grid_search(T.G, qx, qy, qz, __int_as_float(0x7f800000), v);
+      pyramid_search<CellT, Top1, false>(T.G, B.tgt, T.cloud, qx, qy, qz, __int_as_float(0x7f800000), v);  // only the distance is used
     }
     if (v.pos >= 0 && (double)v.bound2() <= B.max_range) {
       acc[0] += (double)v.bound2();
@@ -340,6 +347,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     T.G.g = B.tgt.grid[t];
     T.G.n = nt;
     T.cov0 = B.tgt.cov0 + tb; T.cov1 = B.tgt.cov1 + tb; T.cov2 = B.tgt.cov2 + tb;
+    T.inv0 = B.tgt.inv0 + tb;
+    T.cloud = t;
     if (STAGED) {
       float4* s_pts = reinterpret_cast<float4*>(smem_raw);
       uint16_t* s_cells = reinterpret_cast<uint16_t*>(smem_raw + sizeof(float4) * (size_t)nt);
@@ -640,7 +649,7 @@ __global__ void __launch_bounds__(256) fitness_kernel(CloudSetView src, int s, C
       const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
       Top1 v;
       v.init();
-      grid_search(G, qx, qy, qz, __int_as_float(0x7f800000), v);
+      pyramid_search<unsigned, Top1, false>(G, tgt, t, qx, qy, qz, __int_as_float(0x7f800000), v);
       if (v.pos >= 0 && (double)v.bound2() <= max_range) {
         sum += (double)v.bound2();
         cnt += 1.0;

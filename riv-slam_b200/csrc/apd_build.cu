@@ -167,26 +167,90 @@ __global__ void __launch_bounds__(kTileThreads) scatter_kernel(CloudSetView cs, 
   }
 }
 
-// One thread per cell: order the cell's run by original index (runs are a handful of points).
+// Order every cell's run by original index (the scatter's arrival order depends on atomic timing).
+// A warp inspects 32 cells at a time and sorts the ones holding two or more points cooperatively by
+// rank counting: every element counts the smaller keys of its cell, all reads happen before any
+// write, so there is no dependent chain of global-memory round trips (the first version's per-thread
+// insertion sort cost 180 us on one 5000-point cloud because of it).
 __global__ void cell_sort_kernel(CloudSetView cs, int cloud_begin) {
   const int c = cloud_begin + blockIdx.y;
   if (c >= cs.n_clouds) return;
   const int ncells = cs.grid[c].ncells;
   const unsigned* cells = cs.cells + cs.cell_off[c];
   float4* sp = cs.spts + cs.pt_off[c];
-  for (int cell = blockIdx.x * blockDim.x + threadIdx.x; cell < ncells; cell += gridDim.x * blockDim.x) {
-    const int s = (int)cells[cell], e = (int)cells[cell + 1];
-    for (int i = s + 1; i < e; i++) {
-      const float4 v = sp[i];
-      const unsigned key = __float_as_uint(v.w);
-      int j = i - 1;
-      while (j >= s && __float_as_uint(sp[j].w) > key) {
-        sp[j + 1] = sp[j];
-        j--;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  for (int cell0 = warp * 32; cell0 < ncells; cell0 += n_warps * 32) {
+    const int cell = cell0 + lane;
+    int s = 0, m = 0;
+    if (cell < ncells) {
+      s = (int)cells[cell];
+      m = (int)cells[cell + 1] - s;
+    }
+    unsigned todo = __ballot_sync(0xFFFFFFFFu, m >= 2);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int cs0 = __shfl_sync(0xFFFFFFFFu, s, src), cm = __shfl_sync(0xFFFFFFFFu, m, src);
+      if (cm <= 32) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned key = 0xFFFFFFFFu;
+        if (lane < cm) {
+          v = sp[cs0 + lane];
+          key = __float_as_uint(v.w);
+        }
+        int rank = 0;
+        for (int j = 0; j < cm; j++) rank += (__shfl_sync(0xFFFFFFFFu, key, j) < key) ? 1 : 0;
+        __syncwarp();
+        if (lane < cm) sp[cs0 + rank] = v;
+      } else if (cm <= 256) {
+        float4 v[8];
+        int rank[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          rank[t] = 0;
+          v[t] = (lane + 32 * t < cm) ? sp[cs0 + lane + 32 * t] : make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
+        }
+        for (int j = 0; j < cm; j++) {
+          const unsigned kj = __float_as_uint(sp[cs0 + j].w);  // nothing has been written yet
+#pragma unroll
+          for (int t = 0; t < 8; t++) rank[t] += (kj < __float_as_uint(v[t].w)) ? 1 : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+          if (lane + 32 * t < cm) sp[cs0 + rank[t]] = v[t];
+      } else if (lane == 0) {  // a pathological cell (hundreds of points): plain insertion sort
+        for (int i = cs0 + 1; i < cs0 + cm; i++) {
+          const float4 v = sp[i];
+          const unsigned key = __float_as_uint(v.w);
+          int j = i - 1;
+          while (j >= cs0 && __float_as_uint(sp[j].w) > key) {
+            sp[j + 1] = sp[j];
+            j--;
+          }
+          sp[j + 1] = v;
+        }
       }
-      sp[j + 1] = v;
+      __syncwarp();
     }
   }
+}
+
+// original index -> position in the cell-sorted order (needed when a coarse pyramid level finds a
+// neighbour and the caller wants its level-0 position)
+__global__ void inverse_order_kernel(CloudSetView cs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cs.total_points) return;
+  // binary search of the cloud that owns sorted slot i
+  int lo = 0, hi = cs.n_clouds - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (cs.pt_off[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  const int base = cs.pt_off[lo];
+  cs.inv0[base + __float_as_uint(cs.spts[i].w)] = i - base;
 }
 
 __global__ void pack_points_kernel(const float* __restrict__ xyz, int stride_floats, long long n, float4* __restrict__ out) {
@@ -267,8 +331,7 @@ __global__ void corr_export_kernel(AlignBatch b, int slot, int s, int t, int* __
   } while (0)
 
 cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, const int4* tiles, int n_tiles, const int* cell_cap, long long total_cells,
-                              int max_cloud_points, cudaStream_t stream, LaunchStats* st) {
-  (void)max_cloud_points;
+                              bool finest_level, cudaStream_t stream, LaunchStats* st) {
   if (cs.n_clouds == 0 || n_tiles == 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(cs.cells, 0, sizeof(unsigned) * (size_t)total_cells, stream);
   if (e != cudaSuccess) return e;
@@ -284,6 +347,9 @@ cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, 
   APD_LAUNCH_CHECK();
   scatter_kernel<<<n_tiles, kTileThreads, 0, stream>>>(cs, tiles, ws.cellid, ws.cursor);
   APD_LAUNCH_CHECK();
+  // Only the finest level fixes the order in which the align kernel sums its partials; coarse levels
+  // are searched through (d2, index) keys alone, so their in-cell order is irrelevant.
+  if (!finest_level) return cudaSuccess;
   for (int c0 = 0; c0 < cs.n_clouds; c0 += 32768) {
     const int ny = min(cs.n_clouds - c0, 32768);
     // enough threads to cover the largest per-cloud table once for batches; grid-stride otherwise
@@ -293,6 +359,8 @@ cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, 
     cell_sort_kernel<<<dim3(bx, ny), 256, 0, stream>>>(cs, c0);
     APD_LAUNCH_CHECK();
   }
+  inverse_order_kernel<<<(cs.total_points + 255) / 256, 256, 0, stream>>>(cs);
+  APD_LAUNCH_CHECK();
   return cudaSuccess;
 }
 

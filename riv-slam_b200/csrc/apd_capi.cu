@@ -99,14 +99,28 @@ struct apd_cloudset_s {
   int max_n = 0, min_n = 0;
   long long total_cells = 0;
   std::vector<int> h_off;
-  DevBuf pt_off, cell_off, pts, spts, cells, grid, cov0, cov1, cov2, cell_cap, tiles_build, tiles_knn;
+  DevBuf pt_off, cell_off, pts, spts, cells, grid, cov0, cov1, cov2, cell_cap, tiles_build, tiles_knn, inv0;
+  // coarse pyramid levels (cell budget / 64 and / 4096): own sorted copy, cell table and grid parameters
+  DevBuf c_spts[kCoarseLevels], c_cells[kCoarseLevels], c_grid[kCoarseLevels], c_cell_off[kCoarseLevels], c_cell_cap[kCoarseLevels];
+  long long c_total_cells[kCoarseLevels] = {0, 0};
   int n_tiles_build = 0, n_tiles_knn = 0;
   bool grid_built = false, cov_valid = false;
   int cov_k = -1, cov_reg = -1;
   bool staged = false;      // every cloud's grid fits the shared-memory staging area
   size_t staged_smem = 0;   // bytes needed for the largest cloud
   explicit apd_cloudset_s(const std::shared_ptr<Pool>& pool) {
-    for (DevBuf* b : {&pt_off, &cell_off, &pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &cell_cap, &tiles_build, &tiles_knn}) b->pool = pool;
+    for (DevBuf* b : {&pt_off, &cell_off, &pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &cell_cap, &tiles_build, &tiles_knn, &inv0}) b->pool = pool;
+    for (int l = 0; l < kCoarseLevels; l++)
+      for (DevBuf* b : {&c_spts[l], &c_cells[l], &c_grid[l], &c_cell_off[l], &c_cell_cap[l]}) b->pool = pool;
+  }
+  // the view the build kernels use to construct coarse level l (same points, that level's tables)
+  CloudSetView level_view(int l) const {
+    CloudSetView v = view();
+    v.spts = c_spts[l].as<float4>();
+    v.cells = c_cells[l].as<unsigned>();
+    v.grid = c_grid[l].as<GridParams>();
+    v.cell_off = c_cell_off[l].as<long long>();
+    return v;
   }
   CloudSetView view() const {
     CloudSetView v;
@@ -121,6 +135,13 @@ struct apd_cloudset_s {
     v.cov0 = cov0.as<double2>();
     v.cov1 = cov1.as<double2>();
     v.cov2 = cov2.as<double2>();
+    v.inv0 = inv0.as<int>();
+    for (int l = 0; l < kCoarseLevels; l++) {
+      v.coarse[l].spts = c_spts[l].as<float4>();
+      v.coarse[l].cells = c_cells[l].as<unsigned>();
+      v.coarse[l].grid = c_grid[l].as<GridParams>();
+      v.coarse[l].cell_off = c_cell_off[l].as<long long>();
+    }
     return v;
   }
 };
@@ -141,7 +162,6 @@ struct apd_context {
   int team_size = 0;      // 0 = automatic
   int force_unstaged = 0;
   int max_teams_opt = 0;  // 0 = as many as fit
-  double chain_ratio2 = 0.0;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
       counters, grid_partials, misc, knn_tmp, cov_tmp;
@@ -183,9 +203,8 @@ struct DeviceGuard {
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-DeviceParams device_params(const apd_params& p, float chain_ratio2 = 0.0f) {
+DeviceParams device_params(const apd_params& p) {
   DeviceParams d;
-  d.chain_ratio2 = chain_ratio2;
   d.k = p.k_correspondences;
   d.regularization = p.regularization;
   d.max_iterations = p.max_iterations;
@@ -206,7 +225,9 @@ DeviceParams device_params(const apd_params& p, float chain_ratio2 = 0.0f) {
   return d;
 }
 
-size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem() - 512; }
+// shared memory a staged grid may take: the opt-in maximum minus the align kernel's static state and
+// minus room for the kNN kernel's candidate queues (at least 16 two-byte entries per thread)
+size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem() - 512 - 16 * sizeof(uint16_t) * kKnnThreads; }
 
 // Build the device-side description of a ragged batch: offsets, per-cloud cell budgets, tile lists.
 int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
@@ -253,6 +274,23 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   }
   cell_off[nc] = off;
   cs->total_cells = off;
+  // coarse pyramid levels: 64x and 4096x fewer cells than the (unclamped) fine budget
+  std::vector<int> ccap[kCoarseLevels];
+  std::vector<long long> ccell_off[kCoarseLevels];
+  for (int l = 0; l < kCoarseLevels; l++) {
+    ccap[l].resize(nc);
+    ccell_off[l].resize(nc + 1);
+    long long o = 0;
+    for (int c = 0; c < nc; c++) {
+      const int n = cs->h_off[c + 1] - cs->h_off[c];
+      const long long fine = std::min<long long>(std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n)), 1ll << 28);
+      ccap[l][c] = (int)std::max<long long>(8, fine >> (6 * (l + 1)));
+      ccell_off[l][c] = o;
+      o += (long long)ccap[l][c] + 1;
+    }
+    ccell_off[l][nc] = o;
+    cs->c_total_cells[l] = o;
+  }
 
   // tiles for the per-point build kernels: 1024 points per CTA
   std::vector<int4> tb;
@@ -291,6 +329,16 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   if (nc) CK(cudaMemcpyAsync(cs->cell_cap.p, cap.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, h->stream));
   if (!tb.empty()) CK(cudaMemcpyAsync(cs->tiles_build.p, tb.data(), sizeof(int4) * tb.size(), cudaMemcpyHostToDevice, h->stream));
   if (!tk.empty()) CK(cudaMemcpyAsync(cs->tiles_knn.p, tk.data(), sizeof(int4) * tk.size(), cudaMemcpyHostToDevice, h->stream));
+  CK(cs->inv0.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
+  for (int l = 0; l < kCoarseLevels; l++) {
+    CK(cs->c_spts[l].reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
+    CK(cs->c_cells[l].reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->c_total_cells[l], 1)));
+    CK(cs->c_grid[l].reserve(sizeof(GridParams) * std::max(nc, 1)));
+    CK(cs->c_cell_off[l].reserve(sizeof(long long) * (nc + 1)));
+    CK(cs->c_cell_cap[l].reserve(sizeof(int) * std::max(nc, 1)));
+    CK(cudaMemcpyAsync(cs->c_cell_off[l].p, ccell_off[l].data(), sizeof(long long) * (nc + 1), cudaMemcpyHostToDevice, h->stream));
+    if (nc) CK(cudaMemcpyAsync(cs->c_cell_cap[l].p, ccap[l].data(), sizeof(int) * nc, cudaMemcpyHostToDevice, h->stream));
+  }
   CK(cudaStreamSynchronize(h->stream));
   return APD_OK;
 }
@@ -319,7 +367,10 @@ int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
   CK(h->ws_cellid.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
   CK(h->ws_cursor.reserve(sizeof(unsigned) * (size_t)cs->total_cells));
   BuildWorkspace ws{h->ws_bbox.as<unsigned>(), h->ws_cellid.as<int>(), h->ws_cursor.as<unsigned>()};
-  CK(launch_grid_build(cs->view(), ws, cs->tiles_build.as<int4>(), cs->n_tiles_build, cs->cell_cap.as<int>(), cs->total_cells, cs->max_n, h->stream, &h->stats));
+  CK(launch_grid_build(cs->view(), ws, cs->tiles_build.as<int4>(), cs->n_tiles_build, cs->cell_cap.as<int>(), cs->total_cells, true, h->stream, &h->stats));
+  for (int l = 0; l < kCoarseLevels; l++)
+    CK(launch_grid_build(cs->level_view(l), ws, cs->tiles_build.as<int4>(), cs->n_tiles_build, cs->c_cell_cap[l].as<int>(), cs->c_total_cells[l], false, h->stream,
+                         &h->stats));
   cs->grid_built = true;
   return APD_OK;
 }
@@ -332,7 +383,7 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
   if (rc) return rc;
   if (cs->cov_valid && cs->cov_k == k && cs->cov_reg == h->prm.regularization && !knn_out) return APD_OK;
   if (cs->cov_valid && cs->cov_k < 0 && !knn_out) return APD_OK;  // covariances injected by the caller (setSource/TargetCovariances)
-  const DeviceParams dp = device_params(h->prm, (float)h->chain_ratio2);
+  const DeviceParams dp = device_params(h->prm);
   CK(launch_knn_cov(cs->view(), cs->tiles_knn.as<int4>(), cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
@@ -660,7 +711,6 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "team_size") h->team_size = (int)value;
   else if (n == "force_unstaged") h->force_unstaged = value != 0;
   else if (n == "max_teams") h->max_teams_opt = (int)value;
-  else if (n == "knn_chain_ratio") h->chain_ratio2 = value * value;
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
 }

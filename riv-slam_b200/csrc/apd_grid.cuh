@@ -100,8 +100,12 @@ APD_HD void visit_run(const GridView<CellT>& G, int c0, int c1, float qx, float 
 // provably farther than both the visitor's current bound and limit2, the search stops. Pass
 // +inf for an unbounded search. NaN query coordinates fall into cell 0 and produce NaN distances,
 // which never beat a key (the visitor stays empty), like a kd-tree that finds nothing.
+// `max_ring` caps the expansion: the function returns true when the search is COMPLETE (stopping rule
+// met or the whole grid covered) and false when it gave up after ring max_ring, in which case the
+// caller restarts on a coarser level of the grid pyramid (a sparse neighbourhood would otherwise walk
+// (2r+1)^2 mostly empty rows per ring).
 template <typename CellT, typename Visitor>
-APD_HD void grid_search(const GridView<CellT>& G, float qx, float qy, float qz, float limit2, Visitor& vis) {
+APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, float limit2, Visitor& vis, int max_ring = 0x7fffffff) {
   const GridParams& g = G.g;
   const int cx = cell_coord(qx, g.lox, g.inv_h, g.nx);
   const int cy = cell_coord(qy, g.loy, g.inv_h, g.ny);
@@ -149,13 +153,15 @@ APD_HD void grid_search(const GridView<CellT>& G, float qx, float qy, float qz, 
     if (cy + r < g.ny - 1) reach = fminf(reach, (g.loy + (float)(cy + r + 1) * g.h) - qy);
     if (cz - r > 0) reach = fminf(reach, qz - (g.loz + (float)(cz - r) * g.h));
     if (cz + r < g.nz - 1) reach = fminf(reach, (g.loz + (float)(cz + r + 1) * g.h) - qz);
-    if (reach == FLT_MAX) break;  // the cube covers the whole grid
+    if (reach == FLT_MAX) return true;  // the cube covers the whole grid
     reach = reach - g.slack;
     if (reach > 0.f) {
       const float reach2 = reach * reach * 0.99999f;
-      if (reach2 > fminf(vis.bound2(), limit2)) break;
+      if (reach2 > fminf(vis.bound2(), limit2)) return true;
     }
+    if (r >= max_ring) return false;
   }
+  return true;
 }
 
 // Exact search inside a ball whose squared radius `B` is KNOWN to contain the answer (the k-th

@@ -9,6 +9,19 @@
 
 namespace apd {
 
+// Coarser levels of the grid pyramid (cell edge x4 and x16): the same points sorted by a coarser cell
+// id. A search that is not finished after a few rings of the fine grid restarts here instead of
+// walking (2r+1)^2 mostly empty rows per ring through a sparse neighbourhood.
+constexpr int kCoarseLevels = 2;
+constexpr int kFineRings = 3;     // Top1 searches: rings tried on a level before going coarser
+constexpr int kFineRingsKnn = 8;  // kNN: restarting re-inserts every neighbour, so only truly isolated points go coarser
+struct CoarseLevel {
+  float4* spts;
+  unsigned* cells;
+  GridParams* grid;
+  const long long* cell_off;
+};
+
 // Device-side description of a ragged batch of clouds ("cloud set"). All arrays live in HBM.
 struct CloudSetView {
   int n_clouds;
@@ -22,7 +35,36 @@ struct CloudSetView {
   double2* cov0;              // sorted order: (xx, xy)
   double2* cov1;              //               (xz, yy)
   double2* cov2;              //               (yz, zz)
+  int* inv0;                  // original local index -> position in spts
+  CoarseLevel coarse[kCoarseLevels];
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ GridView<unsigned> coarse_view(const CloudSetView& cs, int level, int cloud) {
+  GridView<unsigned> G;
+  const int base = cs.pt_off[cloud];
+  G.spts = cs.coarse[level].spts + base;
+  G.cells = cs.coarse[level].cells + cs.coarse[level].cell_off[cloud];
+  G.g = cs.coarse[level].grid[cloud];
+  G.n = cs.pt_off[cloud + 1] - base;
+  return G;
+}
+
+// Exact unbounded (or gate-bounded) search through the pyramid: fine grid first, then coarser levels.
+// A TopK visitor must be reset between levels (the same points would be offered twice); a Top1
+// visitor keeps its key, which only tightens the bound. Returns the level that completed the search.
+template <typename CellT, typename Visitor, bool RESET, int RINGS = kFineRings>
+__device__ __forceinline__ int pyramid_search(const GridView<CellT>& G0, const CloudSetView& cs, int cloud, float qx, float qy, float qz, float limit2, Visitor& vis) {
+  if (grid_search(G0, qx, qy, qz, limit2, vis, RINGS)) return 0;
+  if (RESET) vis.init();
+  const GridView<unsigned> G1 = coarse_view(cs, 0, cloud);
+  if (grid_search(G1, qx, qy, qz, limit2, vis, RINGS)) return 1;
+  if (RESET) vis.init();
+  const GridView<unsigned> G2 = coarse_view(cs, 1, cloud);
+  grid_search(G2, qx, qy, qz, limit2, vis);
+  return 2;
+}
+#endif
 
 struct DeviceParams {
   int k;
@@ -38,7 +80,6 @@ struct DeviceParams {
   double dist_var;
   double sin_az;            // sin(azimuth_var / 180 * pi)
   double sin_el;            // sin(elevation_var / 180 * pi)
-  float chain_ratio2;       // kNN: chain a query to the previous one only if |step|^2 <= ratio * r_k^2 (tuning, results identical)
 };
 
 // Per concurrent pair slot scratch of the align kernel (sorted-source order).
@@ -90,7 +131,7 @@ struct BuildWorkspace {
 };
 // tiles: device int4 (cloud, first point, count, 0) covering every point of the set
 cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, const int4* tiles, int n_tiles, const int* cell_cap /*device [n_clouds]*/,
-                              long long total_cells, int max_cloud_points, cudaStream_t stream, LaunchStats* st);
+                              long long total_cells, bool finest_level, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,

@@ -42,7 +42,7 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov, int method) {
 
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kKnnThreads, 1)
-knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, float chain_ratio2, int* __restrict__ knn_out) {
+knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int4 tile = tiles[blockIdx.x];
   const int c = tile.x;
@@ -72,27 +72,17 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   const float4* opts = cs.pts + base;  // original order, for the neighbour gather
   const double inv_div = (double)k;
   // Lanes of a warp take ADJACENT cell-sorted queries (stride blockDim per thread): they walk the same
-  // rings at the same time. Measured alternative (round 1): per-thread runs of consecutive queries
-  // chained by the triangle inequality r_k(q') <= r_k(q) + |q - q'| (grid_ball_search) lose 2x to the
-  // loss of that coherence; chain_ratio2 > 0 keeps the experiment reachable ("knn_chain_ratio" option).
-  const bool chained = chain_ratio2 > 0.f;
-  const int per = (tile.z + blockDim.x - 1) / blockDim.x;
-  const int q_begin = chained ? tile.y + threadIdx.x * per : tile.y + threadIdx.x;
-  const int q_end = chained ? min(q_begin + per, tile.y + tile.z) : tile.y + tile.z;
-  const int q_step = chained ? 1 : blockDim.x;
-  float prev_x = 0.f, prev_y = 0.f, prev_z = 0.f, prev_rk2 = -1.f;
-  for (int q = q_begin; q < q_end; q += q_step) {
+  // rings at the same time. Two alternatives were measured in round 1 and rejected (profiles/):
+  // per-thread runs of consecutive queries chained by the triangle inequality (2x slower: the warp
+  // loses its spatial coherence) and per-ring queues drained by the whole warp (1.2x slower: the time
+  // goes to the few lanes whose sparse neighbourhoods need many rings, not to insertion divergence).
+  for (int q = tile.y + threadIdx.x; q < tile.y + tile.z; q += blockDim.x) {
     const float4 p = G.spts[q];
     const unsigned self = __float_as_uint(p.w);
     TopK<K> tk;
     tk.init();
-    const float step2 = sqdist_rn(p.x, p.y, p.z, prev_x, prev_y, prev_z);
-    if (chained && prev_rk2 >= 0.f && step2 <= chain_ratio2 * prev_rk2)
-      grid_ball_search(G, p.x, p.y, p.z, chained_bound2(prev_rk2, step2), tk);
-    else
-      grid_search(G, p.x, p.y, p.z, __int_as_float(0x7f800000), tk);
-    prev_x = p.x; prev_y = p.y; prev_z = p.z;
-    prev_rk2 = tk.bound2();
+    // fine grid for a few rings; a sparse neighbourhood restarts on the coarser pyramid levels
+    pyramid_search<CellT, TopK<K>, true, kFineRingsKnn>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), tk);
 
     // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324)
     double mx = 0.0, my = 0.0, mz = 0.0;
@@ -144,9 +134,9 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
   if (staged) {
     cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, prm.chain_ratio2, knn_out);
+    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
   } else {
-    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, prm.chain_ratio2, knn_out);
+    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
   }
   return cudaGetLastError();
 }

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Wall-clock breakdown of the single-pair (odometry) call sequence through the C ABI."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from riv_slam_b200 import datagen
+from riv_slam_b200.fast_apdgicp import FastAPDGICP
+from bench import LAUNCH_PARAMS, to_pointxyzi
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+opts = [a.split("=") for a in sys.argv[2:]]
+scans, _ = datagen.make_drive(2, 0, n + 1, 5000, workers=8)
+pts, off = to_pointxyzi(scans, np.arange(n + 1))
+clouds = [np.ascontiguousarray(pts[i * 5000:(i + 1) * 5000]) for i in range(n + 1)]
+reg = FastAPDGICP(0)
+reg.handle().set_params(**LAUNCH_PARAMS)
+for k, v in opts:
+    reg.setOption(k, float(v))
+H = reg.handle()
+rows = []
+for i in range(n):
+    t = [time.perf_counter()]
+    reg.setInputTarget(clouds[i], cache_key=i + 1); H.synchronize(); t.append(time.perf_counter())
+    reg.setInputSource(clouds[i + 1], cache_key=i + 2); H.synchronize(); t.append(time.perf_counter())
+    reg.computeCovariances(); t.append(time.perf_counter())
+    reg.align(None, want_output=False); t.append(time.perf_counter())
+    reg.getFitnessScore(); t.append(time.perf_counter())
+    rows.append(np.diff(t))
+r = np.array(rows[3:]) * 1e3
+names = ["setInputTarget(cached)", "setInputSource(upload)", "grid+knn+cov", "align(+fitness)", "getFitnessScore"]
+for nm, m, p in zip(names, np.median(r, 0), np.percentile(r, 95, 0)):
+    print(f"{nm:26s} p50 {m:7.3f} ms   p95 {p:7.3f} ms")
+print(f"{'total':26s} p50 {np.median(r.sum(1)):7.3f} ms   iterations {reg.nr_iterations()} launches/pair {H.launch_count() / n:.1f}")

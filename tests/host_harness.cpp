@@ -108,9 +108,40 @@ void knn_chained_t(const HostGrid& HG, int chunk, int k, int* idx, float* d2) {
   }
 }
 
+// the grid pyramid of apd_internal.h (pyramid_search): fine grid for `rings` rings, then cap/64, then cap/4096
+template <int K>
+int knn_pyramid_t(const HostGrid* L, int rings, const float* q, int nq, int k, int* idx, float* d2) {
+  int coarse_used = 0;
+  for (int i = 0; i < nq; i++) {
+    TopK<K> tk;
+    tk.init();
+    const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    int level = 0;
+    for (; level < 3; level++) {
+      GridView<unsigned> G{L[level].spts.data(), L[level].cells.data(), L[level].g, (int)L[level].spts.size()};
+      if (level) tk.init();
+      if (grid_search(G, qx, qy, qz, INFINITY, tk, level < 2 ? rings : 0x7fffffff)) break;
+    }
+    coarse_used += level > 0;
+    for (int j = 0; j < k; j++) {
+      idx[(size_t)i * k + j] = (int)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
+      d2[(size_t)i * k + j] = u2f((unsigned)(tk.key[j] >> 32));
+    }
+  }
+  return coarse_used;
+}
+
 }  // namespace
 
 extern "C" {
+
+// kNN through the three-level pyramid; returns how many queries needed a coarse level
+int hh_knn_pyramid(const float* cloud_xyz, int n, int cell_cap, int rings, const float* q, int nq, int k, int* idx, float* d2) {
+  const HostGrid L[3] = {build(cloud_xyz, n, cell_cap), build(cloud_xyz, n, std::max(8, cell_cap >> 6)), build(cloud_xyz, n, std::max(8, cell_cap >> 12))};
+  if (k <= 10) return knn_pyramid_t<10>(L, rings, q, nq, k, idx, d2);
+  if (k <= 20) return knn_pyramid_t<20>(L, rings, q, nq, k, idx, d2);
+  return knn_pyramid_t<32>(L, rings, q, nq, k, idx, d2);
+}
 
 // self-kNN of a cloud with the chained-ball schedule; rows in ORIGINAL point order
 void hh_knn_chained(const float* cloud_xyz, int n, int cell_cap, int chunk, int k, int* idx, float* d2) {

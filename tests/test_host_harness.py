@@ -98,6 +98,24 @@ def test_chained_ball_knn_is_exact(hh, small_pair, cap, chunk):
             assert np.array_equal(i0, idx) and np.array_equal(d0, d2)
 
 
+@pytest.mark.parametrize("cap,rings", [(5000, 3), (40000, 1), (40000, 0), (300000, 2)])
+def test_pyramid_knn_is_exact(hh, small_pair, cap, rings):
+    """Fine grid for a few rings, then the coarser pyramid levels (apd_internal.h pyramid_search)."""
+    src, tgt, _ = small_pair
+    hh.hh_knn_pyramid.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _ip, _fp]
+    c = np.ascontiguousarray(tgt[:, :3], np.float32)
+    far = src[:, :3].copy()
+    far[::3, 0] += 300.0
+    for q in (c, np.ascontiguousarray(far, np.float32)):
+        for k in (10, 20):
+            idx = np.zeros((len(q), k), np.int32)
+            d2 = np.zeros((len(q), k), np.float32)
+            used = hh.hh_knn_pyramid(c.ctypes.data_as(_fp), len(c), cap, rings, q.ctypes.data_as(_fp), len(q), k, idx.ctypes.data_as(_ip), d2.ctypes.data_as(_fp))
+            i0, d0 = knn_bruteforce(tgt, q, k)
+            assert np.array_equal(i0, idx) and np.array_equal(d0, d2)
+            assert used > 0   # the coarse levels really are exercised
+
+
 def test_seeded_ball_nn1_is_exact(hh, small_pair):
     src, tgt, _ = small_pair
     c = np.ascontiguousarray(tgt[:, :3])
