@@ -162,7 +162,8 @@ int apd_synchronize(apd_handle h);
  *   "cells_per_point"  voxel-grid cell budget per point (default 4)
  *   "team_size"        CTAs cooperating on one pair: 0 = automatic, 1 = one CTA, 2..16 = cluster
  *   "force_unstaged"   1 = never stage the target grid in shared memory
- *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit) */
+ *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit)
+ *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only */
 int apd_set_option(apd_handle h, const char* name, double value);
 
 /* ---- introspection for benchmarks ---- */

@@ -162,6 +162,7 @@ struct apd_context {
   int team_size = 0;      // 0 = automatic
   int force_unstaged = 0;
   int max_teams_opt = 0;  // 0 = as many as fit
+  int knn_packed = 1;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
       counters, grid_partials, misc, knn_tmp, cov_tmp;
@@ -222,6 +223,7 @@ DeviceParams device_params(const apd_params& p) {
   d.dist_var = p.dist_var;
   d.sin_az = std::sin(p.azimuth_var / 180 * M_PI);
   d.sin_el = std::sin(p.elevation_var / 180 * M_PI);
+  d.knn_packed = 1;
   return d;
 }
 
@@ -383,7 +385,8 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
   if (rc) return rc;
   if (cs->cov_valid && cs->cov_k == k && cs->cov_reg == h->prm.regularization && !knn_out) return APD_OK;
   if (cs->cov_valid && cs->cov_k < 0 && !knn_out) return APD_OK;  // covariances injected by the caller (setSource/TargetCovariances)
-  const DeviceParams dp = device_params(h->prm);
+  DeviceParams dp = device_params(h->prm);
+  dp.knn_packed = h->knn_packed;
   CK(launch_knn_cov(cs->view(), cs->tiles_knn.as<int4>(), cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
@@ -711,6 +714,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "team_size") h->team_size = (int)value;
   else if (n == "force_unstaged") h->force_unstaged = value != 0;
   else if (n == "max_teams") h->max_teams_opt = (int)value;
+  else if (n == "knn_packed") h->knn_packed = value != 0;
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
 }

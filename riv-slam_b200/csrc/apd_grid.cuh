@@ -75,6 +75,94 @@ struct TopK {
   }
 };
 
+// ---- packed 32-bit candidate list (fast path of the kNN kernel) ----
+// Inserting into the exact 64-bit list costs ~6 instructions per slot in a dependent chain, and the
+// round-1 profile shows that this insertion is 60-70 % of the kNN kernel. A 32-bit key
+//   (top bits of d2) << kbits | index        kbits = ceil(log2 n)
+// can be inserted with one unsigned min and one max per slot (independent, no predicates, no payload).
+// It orders candidates by a QUANTISED distance, so it is only a filter: the list keeps the M = K + 4
+// smallest packed keys, and afterwards
+//   - complete() tells whether every candidate of the K-th entry's distance bucket is in the list
+//     (the bucket of entry M-1 is strictly larger): then the exact top-K is a subset of the list and
+//     exact_from_packed() recomputes exact 64-bit keys for the M entries and sorts them;
+//   - otherwise (many ties, e.g. lattice data) the caller redoes the query with the exact list.
+// Every candidate that could still belong to the exact top-K passes the gate "not beyond the K-th
+// entry's bucket", so nothing is lost; bound2() is the upper edge of that bucket, a valid (slightly
+// loose) bound for row pruning and for the stopping rule.
+APD_HD unsigned umin32(unsigned a, unsigned b) { return a < b ? a : b; }
+APD_HD unsigned umax32(unsigned a, unsigned b) { return a > b ? a : b; }
+
+template <int K, int M>
+struct TopKPacked {
+  unsigned a[M];
+  int kbits, sh;
+  APD_HD void setup(int n) {
+    int b = 1;
+    while (b < 31 && (1u << b) < (unsigned)n) b++;
+    kbits = b;
+    sh = b - 1;  // 31 significant bits of d2 (it is >= 0) minus the 32 - kbits we keep
+  }
+  APD_HD void init() {
+#pragma unroll
+    for (int i = 0; i < M; i++) a[i] = 0xFFFFFFFFu;
+  }
+  APD_HD float bound2() const {
+    // all-ones (empty slot) decodes to a NaN: comparisons against it are false, i.e. "no bound yet"
+    return u2f(((a[K - 1] >> kbits) << sh) | ((1u << sh) - 1u));
+  }
+  APD_HD void offer(float d2, unsigned idx, int /*pos*/) {
+    if (!(d2 <= FLT_MAX)) return;
+    const unsigned key = ((f2u(d2) >> sh) << kbits) | idx;
+    if (key <= (a[K - 1] | ((1u << kbits) - 1u))) {
+#pragma unroll
+      for (int j = M - 1; j > 0; j--) a[j] = umin32(a[j], umax32(a[j - 1], key));
+      a[0] = umin32(a[0], key);
+    }
+  }
+  APD_HD bool complete() const { return a[K - 1] == 0xFFFFFFFFu || (a[M - 1] >> kbits) > (a[K - 1] >> kbits); }
+};
+
+// Exact (d2, index)-ordered top-K from a complete packed list: recompute the exact keys of its M
+// entries from the points (original order, `opts`) and sort them. The packed order already agrees
+// with the exact one except inside a distance bucket, so an odd-even transposition sort needs one
+// or two passes.
+template <int K, int M>
+APD_HD void exact_from_packed(const TopKPacked<K, M>& ap, float qx, float qy, float qz, const float4* opts, TopK<K>& tk) {
+  unsigned long long k64[M];
+  const unsigned mask = (1u << ap.kbits) - 1u;
+#pragma unroll
+  for (int j = 0; j < M; j++) {
+    k64[j] = APD_KEY_INF;
+    if (ap.a[j] != 0xFFFFFFFFu) {
+      const unsigned idx = ap.a[j] & mask;
+      const float4 t = opts[idx];
+      k64[j] = make_key(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), idx);
+    }
+  }
+  bool swapped = true;
+  while (swapped) {
+    swapped = false;
+#pragma unroll
+    for (int j = 0; j + 1 < M; j += 2) {
+      const unsigned long long x = k64[j], y = k64[j + 1];
+      const bool sw = y < x;
+      k64[j] = sw ? y : x;
+      k64[j + 1] = sw ? x : y;
+      swapped |= sw;
+    }
+#pragma unroll
+    for (int j = 1; j + 1 < M; j += 2) {
+      const unsigned long long x = k64[j], y = k64[j + 1];
+      const bool sw = y < x;
+      k64[j] = sw ? y : x;
+      k64[j + 1] = sw ? x : y;
+      swapped |= sw;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < K; j++) tk.key[j] = k64[j];
+}
+
 struct Top1 {
   unsigned long long key;
   int pos;  // sorted position of the best point

@@ -80,6 +80,7 @@ struct DeviceParams {
   double dist_var;
   double sin_az;            // sin(azimuth_var / 180 * pi)
   double sin_el;            // sin(elevation_var / 180 * pi)
+  int knn_packed;           // kNN: use the packed 32-bit candidate list (tuning; results identical)
 };
 
 // Per concurrent pair slot scratch of the align kernel (sorted-source order).

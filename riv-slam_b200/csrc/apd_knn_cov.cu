@@ -42,7 +42,7 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov, int method) {
 
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kKnnThreads, 1)
-knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out) {
+knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int* __restrict__ knn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int4 tile = tiles[blockIdx.x];
   const int c = tile.x;
@@ -71,6 +71,10 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
 
   const float4* opts = cs.pts + base;  // original order, for the neighbour gather
   const double inv_div = (double)k;
+  // index bits of the packed key; beyond ~1M points the distance part becomes too coarse to filter
+  int kbits = 1;
+  while (kbits < 31 && (1u << kbits) < (unsigned)n) kbits++;
+  const bool use_packed = packed_path && kbits <= 20;
   // Lanes of a warp take ADJACENT cell-sorted queries (stride blockDim per thread): they walk the same
   // rings at the same time. Two alternatives were measured in round 1 and rejected (profiles/):
   // per-thread runs of consecutive queries chained by the triangle inequality (2x slower: the warp
@@ -79,10 +83,29 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   for (int q = tile.y + threadIdx.x; q < tile.y + tile.z; q += blockDim.x) {
     const float4 p = G.spts[q];
     const unsigned self = __float_as_uint(p.w);
+    // Fast path: collect candidates in a packed 32-bit list (min/max insertion, see TopKPacked), then
+    // recompute and sort the exact keys of its K+4 entries. The list proves its own completeness;
+    // when it cannot (a crowded distance bucket: lattice-like ties) the query is redone with the exact
+    // 64-bit list. Either way the result is the exact (d2, index)-ordered top-k.
+    // Both searches go through the grid pyramid: fine grid for a few rings, coarser levels for the
+    // rare isolated point.
     TopK<K> tk;
-    tk.init();
-    // fine grid for a few rings; a sparse neighbourhood restarts on the coarser pyramid levels
-    pyramid_search<CellT, TopK<K>, true, kFineRingsKnn>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), tk);
+    bool done = false;
+    if (use_packed) {
+      TopKPacked<K, K + 4> ap;
+      ap.kbits = kbits;
+      ap.sh = kbits - 1;
+      ap.init();
+      pyramid_search<CellT, TopKPacked<K, K + 4>, true, kFineRingsKnn>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), ap);
+      if (ap.complete()) {
+        exact_from_packed(ap, p.x, p.y, p.z, opts, tk);
+        done = true;
+      }
+    }
+    if (!done) {
+      tk.init();
+      pyramid_search<CellT, TopK<K>, true, kFineRingsKnn>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), tk);
+    }
 
     // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324)
     double mx = 0.0, my = 0.0, mz = 0.0;
@@ -134,9 +157,9 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
   if (staged) {
     cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
+    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, knn_out);
   } else {
-    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
+    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, knn_out);
   }
   return cudaGetLastError();
 }

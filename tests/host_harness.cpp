@@ -131,9 +131,46 @@ int knn_pyramid_t(const HostGrid* L, int rings, const float* q, int nq, int k, i
   return coarse_used;
 }
 
+// the kNN kernel's fast path: packed 32-bit candidate list, completeness check, exact fix-up, else exact redo
+template <int K>
+int knn_packed_t(const HostGrid& HG, const std::vector<float4>& opts, const float* q, int nq, int k, int* idx, float* d2) {
+  GridView<unsigned> G{HG.spts.data(), HG.cells.data(), HG.g, (int)HG.spts.size()};
+  int fallbacks = 0;
+  for (int i = 0; i < nq; i++) {
+    const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    TopKPacked<K, K + 4> ap;
+    ap.setup(G.n);
+    ap.init();
+    grid_search(G, qx, qy, qz, INFINITY, ap);
+    TopK<K> tk;
+    if (ap.complete()) {
+      exact_from_packed(ap, qx, qy, qz, opts.data(), tk);
+    } else {
+      fallbacks++;
+      tk.init();
+      grid_search(G, qx, qy, qz, INFINITY, tk);
+    }
+    for (int j = 0; j < k; j++) {
+      idx[(size_t)i * k + j] = (int)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
+      d2[(size_t)i * k + j] = u2f((unsigned)(tk.key[j] >> 32));
+    }
+  }
+  return fallbacks;
+}
+
 }  // namespace
 
 extern "C" {
+
+// kNN with the packed-key fast path; returns the number of queries that fell back to the exact list
+int hh_knn_packed(const float* cloud_xyz, int n, int cell_cap, const float* q, int nq, int k, int* idx, float* d2) {
+  const HostGrid G = build(cloud_xyz, n, cell_cap);
+  std::vector<float4> opts(n);
+  for (int i = 0; i < n; i++) opts[i] = make_float4(cloud_xyz[3 * i], cloud_xyz[3 * i + 1], cloud_xyz[3 * i + 2], 1.f);
+  if (k == 10) return knn_packed_t<10>(G, opts, q, nq, k, idx, d2);
+  if (k == 20) return knn_packed_t<20>(G, opts, q, nq, k, idx, d2);
+  return -1;
+}
 
 // kNN through the three-level pyramid; returns how many queries needed a coarse level
 int hh_knn_pyramid(const float* cloud_xyz, int n, int cell_cap, int rings, const float* q, int nq, int k, int* idx, float* d2) {

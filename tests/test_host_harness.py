@@ -116,6 +116,28 @@ def test_pyramid_knn_is_exact(hh, small_pair, cap, rings):
             assert used > 0   # the coarse levels really are exercised
 
 
+def test_packed_key_fast_path_is_exact(hh, small_pair):
+    """32-bit packed candidate list + completeness check + exact fix-up (or exact redo) == brute force."""
+    src, tgt, _ = small_pair
+    hh.hh_knn_packed.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _ip, _fp]
+    lat = np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(5), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    lat = lat[np.random.default_rng(0).permutation(len(lat))]
+    dup = np.concatenate([tgt[:300], tgt[:300], tgt[:300]])          # exact duplicates: ties everywhere
+    for cloud, queries, expect_fallbacks in ((tgt, tgt, False), (tgt, src, False), (lat, lat, True), (dup, dup, False)):
+        c = np.ascontiguousarray(cloud[:, :3], np.float32)
+        q = np.ascontiguousarray(queries[:, :3], np.float32)
+        for k in (10, 20):
+            idx = np.zeros((len(q), k), np.int32)
+            d2 = np.zeros((len(q), k), np.float32)
+            fb = hh.hh_knn_packed(c.ctypes.data_as(_fp), len(c), 4 * len(c), q.ctypes.data_as(_fp), len(q), k, idx.ctypes.data_as(_ip), d2.ctypes.data_as(_fp))
+            i0, d0 = knn_bruteforce(cloud, queries, k)
+            assert np.array_equal(i0, idx) and np.array_equal(d0, d2)
+            if expect_fallbacks:
+                assert fb > 0            # the exact redo path is exercised
+            else:
+                assert fb <= len(q) // 100   # and is rare on radar-like data
+
+
 def test_seeded_ball_nn1_is_exact(hh, small_pair):
     src, tgt, _ = small_pair
     c = np.ascontiguousarray(tgt[:, :3])
