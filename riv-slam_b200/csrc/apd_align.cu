@@ -211,7 +211,7 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const A
       // no gate (constructor default FLT_MAX): unbounded search through the pyramid; a hit on a coarse
       // level is mapped back to its position in the fine order
       if (pyramid_search<CellT, Top1, false>(T.G, B.tgt, T.cloud, qx, qy, qz, B.prm.corr_limit2, v) > 0 && v.pos >= 0)
-        v.pos = T.inv0[(unsigned)(v.key & 0xFFFFFFFFull)];
+        v.pos = T.inv0[v.idx];
     }
     const float d2 = v.bound2();
     const bool ok = v.pos >= 0 && (double)d2 < B.prm.corr_thr2;

@@ -164,13 +164,16 @@ APD_HD void exact_from_packed(const TopKPacked<K, M>& ap, float qx, float qy, fl
 }
 
 struct Top1 {
-  unsigned long long key;
-  int pos;  // sorted position of the best point
-  APD_HD void init() { key = APD_KEY_INF; pos = -1; }
-  APD_HD float bound2() const { return u2f((unsigned)(key >> 32)); }
-  APD_HD void offer(float d2, unsigned idx, int p) {
-    const unsigned long long k = make_key(d2, idx);
-    if (k < key) { key = k; pos = p; }
+  float d2;      // best squared distance so far (+inf: none)
+  unsigned idx;  // its original index (tie-break)
+  int pos;       // its position in the searched (sorted) order
+  APD_HD void init() { d2 = u2f(0x7f800000u); idx = 0xFFFFFFFFu; pos = -1; }
+  APD_HD float bound2() const { return d2; }
+  // (d2, index) lexicographic minimum; the float compare alone settles almost every candidate
+  APD_HD void offer(float d, unsigned i, int p) {
+    if (d <= d2) {
+      if (d < d2 || i < idx) { d2 = d; idx = i; pos = p; }
+    }
   }
 };
 
@@ -218,6 +221,8 @@ APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, 
         dy = fmaxf(dy - g.slack, 0.f);
         // whole row out of reach (strictly farther than the current bound): skip. 0.99999 absorbs the
         // rounding of this bound itself; the bound is re-read per row so it tightens inside a ring.
+        // (Trimming the row to the chord of the bounding ball was measured in round 1: the extra sqrt and
+        // two cell lookups per row cost more than the candidates they save.)
         if ((dz * dz + dy * dy) * 0.99999f > fminf(vis.bound2(), limit2)) continue;
         const bool face = zface || (y == cy - r) || (y == cy + r);
         const int rowbase = (z * g.ny + y) * g.nx;
