@@ -290,10 +290,34 @@ def main():
     clocks = sampler.stop(t0, t1) if sampler else None
     lin, err, _ = H.work_counters()   # of the last step (all steps do identical work)
 
-    # ---- end to end: pinned host PointXYZI buffers in, host results out ----
-    timed(host, F.MEM_HOST, True, 1)
-    e_tot, _, _, e_wall = timed(host, F.MEM_HOST, True, args.steps)
-    results = np.frombuffer(res_host.numpy().tobytes(), dtype=F.RESULT_DTYPE)
+    # ---- end to end: pinned host PointXYZI buffers in, host results out, through the public call a user makes ----
+    # apd_odometry_align uploads every scan from (pinned) host memory, builds grids + covariances, aligns
+    # all pairs and writes the 96-byte records to host memory; it pipelines chunks over two streams.
+    res_np = np.zeros(P, dtype=F.RESULT_DTYPE)
+    res_pin = torch.from_numpy(res_np.view(np.uint8).reshape(-1)).pin_memory()
+    res_view = np.frombuffer(memoryview(res_pin.numpy()), dtype=F.RESULT_DTYPE)
+
+    def e2e_step():
+        H.check(L.apd_odometry_align(H.h, C.c_void_p(host.data_ptr()), off.ctypes.data_as(ip), P + 1, 32, None, C.c_void_p(res_pin.data_ptr())))
+
+    def e2e_timed(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                e2e_step()          # returns when the results are in host memory
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, res_dev)
+            e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0
+
+    e2e_timed(1)
+    e_tot, e_wall = e2e_timed(args.steps)
+    e_tot = max(e_tot, e_wall)    # the helper stream's work is not on `stream`: the host clock bounds the region
+    results = res_view.copy()
 
     def allmax(x):
         if world == 1:
@@ -302,7 +326,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    tot_m, e_m, align_m, prep_m = allmax(tot), allmax(max(e_tot, 0.0)), allmax(align), allmax(prep)
+    tot_m, e_m, align_m, prep_m = allmax(tot), allmax(e_tot), allmax(align), allmax(prep)
     # e2e uses the larger of the device-event time and the host wall clock around the same region
     e_m = max(e_m, 0.0)
     e_wall_m = allmax(e_wall)

@@ -166,6 +166,13 @@ int apd_synchronize(apd_handle h);
  *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only */
 int apd_set_option(apd_handle h, const char* name, double value);
 
+/* Scan-to-scan odometry over one host array of n_scans scans (config C2; the call pattern of
+ * radar_graph_slam/apps/scan_matching_odometry_nodelet.cpp:449-468,584-592 replayed over a recorded drive): pair i registers scan
+ * i+1 onto scan i, every scan is uploaded, gridded and given covariances once, out receives n_scans-1 records. guesses: (n_scans-1)*16
+ * floats or NULL = identity. Like apd_batch_align it pipelines chunks over two streams so uploads overlap compute. */
+int apd_odometry_align(apd_handle h, const float* pts, const int32_t* offsets /* host, n_scans+1 */, int n_scans, int stride_bytes,
+                       const float* guesses, apd_result* out);
+
 /* ---- introspection for benchmarks ---- */
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches claim). */
 int apd_get_launch_count(apd_handle h, int64_t* n);

@@ -174,6 +174,8 @@ struct apd_context {
   std::vector<double> lm_trace;
   bool last_lin_valid = false;  // scratch slot 0 holds correspondences of the current src/tgt
   long long work_lin = 0, work_err = 0, work_pairs = 0;
+  apd_handle helper = nullptr;   // second stream/pool for pipelined batches (pipelined_align)
+  long long helper_launches_seen = 0;
 };
 
 namespace {
@@ -675,6 +677,7 @@ int apd_destroy(apd_handle h) {
   cudaStreamSynchronize(h->stream);
   h->src.reset();
   h->tgt.reset();
+  if (h->helper) apd_destroy(h->helper);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return APD_OK;
@@ -1067,27 +1070,126 @@ int apd_align_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int3
   return fetch_counters(h, n_pairs);
 }
 
+// ---- pipelined host-to-host batches ----
+// A large batch is cut into chunks that alternate between the handle and a lazily created helper
+// handle (same device, own stream and allocation pool): while one chunk's kernels run, the next
+// chunk's points cross PCIe on the other stream. Results are bitwise identical to one big launch:
+// pairs are independent and every pair is processed by the same team shape.
+namespace {
+
+constexpr int kChunkPairs = 256;  // pairs per chunk; the last scan of an odometry chunk is repeated in the next
+
+struct ChunkSlot {
+  apd_handle h = nullptr;
+  std::shared_ptr<apd_cloudset_s> a, b;  // kept alive until the slot's stream has drained
+  int pairs = 0;
+};
+
+int helper_of(apd_handle h, apd_handle* out) {
+  if (!h->helper) {
+    apd_handle x = nullptr;
+    int rc = apd_create(h->device, &x);
+    if (rc) return fail(h, rc, "could not create the pipeline helper handle");
+    h->helper = x;
+  }
+  apd_handle x = h->helper;
+  x->prm = h->prm;
+  x->cells_per_point = h->cells_per_point;
+  x->team_size = h->team_size;
+  x->force_unstaged = h->force_unstaged;
+  x->max_teams_opt = h->max_teams_opt;
+  x->knn_packed = h->knn_packed;
+  *out = x;
+  return APD_OK;
+}
+
+// wait for a slot's previous chunk, collect its counters, release its clouds
+int retire(apd_handle owner, ChunkSlot& s, long long* lin, long long* err) {
+  if (!s.h || s.pairs == 0) return APD_OK;
+  int rc = fetch_counters(s.h, s.pairs);
+  if (rc) return s.h == owner ? rc : fail(owner, rc, s.h->err);
+  *lin += s.h->work_lin;
+  *err += s.h->work_err;
+  s.a.reset();
+  s.b.reset();
+  s.pairs = 0;
+  return APD_OK;
+}
+
+// odometry == true: one ragged array of n_pairs + 1 scans, pair i = scan i+1 -> scan i
+int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, const float* pts_tgt, const int32_t* off_tgt, int stride_bytes, const float* guesses,
+                    int n_pairs, apd_result* out, bool odometry) {
+  ChunkSlot slots[2];
+  slots[0].h = h;
+  if (n_pairs > kChunkPairs) {
+    int rc = helper_of(h, &slots[1].h);
+    if (rc) return rc;
+  }
+  long long lin = 0, err = 0;
+  std::vector<int32_t> idx_s, idx_t;
+  int chunk = 0;
+  for (int p0 = 0; p0 < n_pairs; p0 += kChunkPairs, chunk++) {
+    const int np = std::min(kChunkPairs, n_pairs - p0);
+    ChunkSlot& s = slots[slots[1].h ? (chunk & 1) : 0];
+    int rc = retire(h, s, &lin, &err);
+    if (rc) return rc;
+    apd_handle hc = s.h;
+    AlignCall c;
+    if (odometry) {
+      rc = make_cloudset(hc, pts_src, stride_bytes, off_src + p0, np + 1, APD_MEM_HOST, &s.a);
+      if (rc) return hc == h ? rc : fail(h, rc, hc->err);
+      idx_s.resize(np);
+      idx_t.resize(np);
+      for (int i = 0; i < np; i++) { idx_s[i] = i + 1; idx_t[i] = i; }
+      c.src = c.tgt = s.a.get();
+      c.src_idx = idx_s.data();
+      c.tgt_idx = idx_t.data();
+    } else {
+      rc = make_cloudset(hc, pts_src, stride_bytes, off_src + p0, np, APD_MEM_HOST, &s.a);
+      if (rc) return hc == h ? rc : fail(h, rc, hc->err);
+      rc = make_cloudset(hc, pts_tgt, stride_bytes, off_tgt + p0, np, APD_MEM_HOST, &s.b);
+      if (rc) return hc == h ? rc : fail(h, rc, hc->err);
+      c.src = s.a.get();
+      c.tgt = s.b.get();
+    }
+    c.guesses = guesses ? guesses + (size_t)p0 * 16 : nullptr;
+    c.n_pairs = np;
+    c.min_points = h->prm.k_correspondences;
+    rc = run_align(hc, c);
+    if (rc) return hc == h ? rc : fail(h, rc, hc->err);
+    if (cudaMemcpyAsync(out + p0, hc->results.p, sizeof(apd_result) * np, cudaMemcpyDeviceToHost, hc->stream) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, APD_ERR_CUDA, "result copy failed");
+    }
+    s.pairs = np;
+  }
+  for (ChunkSlot& s : slots) {
+    int rc = retire(h, s, &lin, &err);
+    if (rc) return rc;
+  }
+  h->work_lin = lin;
+  h->work_err = err;
+  h->work_pairs = n_pairs;
+  h->last_lin_valid = false;
+  if (slots[1].h) h->stats.launches += slots[1].h->stats.launches - h->helper_launches_seen, h->helper_launches_seen = slots[1].h->stats.launches;
+  return APD_OK;
+}
+
+}  // namespace
+
 int apd_batch_align(apd_handle h, const float* pts_src, const int32_t* off_src, const float* pts_tgt, const int32_t* off_tgt, int stride_bytes,
                     const float* guesses, int n_pairs, apd_result* out) {
-  if (!h || !out || n_pairs < 0) return APD_ERR_INVALID;
+  if (!h || !out || n_pairs < 0 || !off_src || !off_tgt) return APD_ERR_INVALID;
   DeviceGuard guard(h->device);
   if (n_pairs == 0) return APD_OK;
-  std::shared_ptr<apd_cloudset_s> s, t;
-  int rc = make_cloudset(h, pts_src, stride_bytes, off_src, n_pairs, APD_MEM_HOST, &s);
-  if (rc) return rc;
-  rc = make_cloudset(h, pts_tgt, stride_bytes, off_tgt, n_pairs, APD_MEM_HOST, &t);
-  if (rc) return rc;
-  AlignCall c;
-  c.src = s.get();
-  c.tgt = t.get();
-  c.guesses = guesses;
-  c.n_pairs = n_pairs;
-  c.min_points = h->prm.k_correspondences;
-  rc = run_align(h, c);
-  if (rc) return rc;
-  h->last_lin_valid = false;
-  CK(cudaMemcpyAsync(out, h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToHost, h->stream));
-  return fetch_counters(h, n_pairs);
+  return pipelined_align(h, pts_src, off_src, pts_tgt, off_tgt, stride_bytes, guesses, n_pairs, out, false);
+}
+
+int apd_odometry_align(apd_handle h, const float* pts, const int32_t* offsets, int n_scans, int stride_bytes, const float* guesses, apd_result* out) {
+  if (!h || !out || n_scans < 0 || !offsets) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (n_scans < 2) return APD_OK;
+  return pipelined_align(h, pts, offsets, nullptr, nullptr, stride_bytes, guesses, n_scans - 1, out, true);
 }
 
 int apd_synchronize(apd_handle h) {

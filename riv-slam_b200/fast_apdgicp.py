@@ -96,6 +96,7 @@ _PROTOTYPES = {
     "apd_cloudset_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "apd_align_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip, _fp, C.c_int, C.c_void_p, C.c_int]),
     "apd_batch_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_void_p, _ip, C.c_int, _fp, C.c_int, C.c_void_p]),
+    "apd_odometry_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_int, _fp, C.c_void_p]),
     "apd_synchronize": (C.c_int, [C.c_void_p]),
     "apd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "apd_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -524,4 +525,19 @@ def batch_align(handle: Handle, sources, targets, guesses=None):
     handle.check(handle.L.apd_batch_align(handle.h, C.c_void_p(ps.ctypes.data), os_.ctypes.data_as(_ip), C.c_void_p(pt.ctypes.data),
                                           ot.ctypes.data_as(_ip), ps.shape[1] * 4, None if g is None else g.ctypes.data_as(_fp), n,
                                           C.c_void_p(res.ctypes.data)))
+    return res
+
+
+def odometry_align(handle: Handle, scans, guesses=None, out=None):
+    """apd_odometry_align: pair i registers scan i+1 onto scan i. ``scans`` is a list of (n_i, c) host arrays
+    or a (points, offsets) tuple (points may be a pinned torch tensor); returns RESULT_DTYPE[n_scans - 1]."""
+    pts, off = _ragged(scans)
+    n = len(off) - 1
+    keep, ptr, stride, _, mem = _cloud_arg(pts)
+    if mem != MEM_HOST:
+        raise ValueError("odometry_align takes host memory; use CloudSet + align_pairs for device tensors")
+    g = None if guesses is None else np.ascontiguousarray(guesses, dtype=np.float32).reshape(max(n - 1, 0), 16)
+    res = np.zeros(max(n - 1, 0), dtype=RESULT_DTYPE) if out is None else out
+    optr = C.c_void_p(res.data_ptr()) if _is_torch(res) else C.c_void_p(res.ctypes.data)
+    handle.check(handle.L.apd_odometry_align(handle.h, ptr, off.ctypes.data_as(_ip), n, stride, None if g is None else g.ctypes.data_as(_fp), optr))
     return res

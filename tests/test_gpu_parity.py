@@ -443,3 +443,35 @@ def test_scan_to_submap_reuses_target():
         # sanity only: with the launch-file epsilon (0.1 m) the loop stops as soon as a step is below 10 cm
         gt = np.linalg.inv(poses[0]) @ poses[4 + j]
         assert np.abs(res[j]["T"][:3, 3] - gt[:3, 3]).max() < 1.5
+
+
+def test_pipelined_host_batches_equal_one_launch():
+    """apd_odometry_align / apd_batch_align cut big host batches into chunks over two streams; the records
+    must equal those of a single apd_align_pairs launch bit for bit."""
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import Handle, CloudSet, align_pairs, batch_align, odometry_align
+    base, _ = datagen.make_drive(2, 3, 24, 700, workers=0)
+    order = []
+    t, d = 0, 1
+    for _ in range(601):                       # 600 pairs > 2 chunks of 256
+        order.append(t)
+        if t + d < 0 or t + d >= len(base):
+            d = -d
+        t += d
+    scans = [base[i] for i in order]
+    H = Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+    S = CloudSet(H, scans)
+    n = len(scans) - 1
+    ref = align_pairs(H, S, S, src_idx=np.arange(1, n + 1), tgt_idx=np.arange(0, n))
+    got = odometry_align(H, scans)
+    assert got.tobytes() == ref.tobytes()
+    lin, err, pairs = H.work_counters()
+    assert pairs == n and lin >= n
+    got2 = batch_align(H, scans[1:], scans[:-1])
+    assert got2.tobytes() == ref.tobytes()
+    # guesses are routed per chunk
+    g = np.stack([ref[i]["T"] for i in range(n)])
+    got3 = odometry_align(H, scans, guesses=g)
+    ref3 = align_pairs(H, S, S, src_idx=np.arange(1, n + 1), tgt_idx=np.arange(0, n), guesses=g)
+    assert got3.tobytes() == ref3.tobytes()
