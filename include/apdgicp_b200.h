@@ -118,6 +118,11 @@ int apd_clear_target(apd_handle h);           /* fast_apdgicp_impl.hpp:84-87 */
 int apd_align(apd_handle h, const float guess[16], apd_result* out);
 /* pcl::Registration::getFitnessScore(max_range) on the last alignment. */
 int apd_fitness(apd_handle h, double max_range, double* score);
+/* "Next" row SURVEY.md §8(f)-1: InformationMatrixCalculator::calc_fitness_score(cloud1, cloud2, relpose, max_range)
+ * (radar_graph_slam/src/radar_graph_slam/information_matrix_calculator.cpp:55-86; callers radar_graph_slam_nodelet.cpp:419,704,
+ * loop_detector.cpp:315): mean squared 1-NN distance of T * cloud2 in cloud1, counting pairs with d2 <= max_range; DBL_MAX if none.
+ * cloud1 is the handle's target, cloud2 its source; T == NULL is identity; n_used (may be NULL) receives the pair count. */
+int apd_fitness_score(apd_handle h, const float T[16], double max_range, double* score, int64_t* n_used);
 /* pcl::transformPointCloud(*input_, output, T) (lsq_registration_impl.hpp:79): writes x,y,z every
  * out_stride_bytes; T == NULL uses the last final transformation. */
 int apd_transform_source(apd_handle h, const float T[16], float* out_xyz, int out_stride_bytes, int mem);
@@ -165,6 +170,11 @@ int apd_synchronize(apd_handle h);
  *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit)
  *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only */
 int apd_set_option(apd_handle h, const char* name, double value);
+
+/* Batched calc_fitness_score over cloud sets (one launch for a sliding window of keyframe pairs): scores[i] for cloud src_idx[i]
+ * of `src` (cloud2) against cloud tgt_idx[i] of `tgt` (cloud1) at poses[i] (n_pairs*16 floats, NULL = identity). */
+int apd_fitness_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int32_t* src_idx, const int32_t* tgt_idx, const float* poses,
+                      int n_pairs, double max_range, double* scores);
 
 /* Scan-to-scan odometry over one host array of n_scans scans (config C2; the call pattern of
  * radar_graph_slam/apps/scan_matching_odometry_nodelet.cpp:449-468,584-592 replayed over a recorded drive): pair i registers scan

@@ -66,6 +66,8 @@ def lib():
         L.oracle_align.restype = C.c_int
         L.oracle_fitness.argtypes = [C.c_void_p, C.c_double]
         L.oracle_fitness.restype = C.c_double
+        L.oracle_fitness_score.argtypes = [C.c_void_p, fp, C.c_double]
+        L.oracle_fitness_score.restype = C.c_double
         L.oracle_compute_covariances.argtypes = [C.c_void_p]
         L.oracle_linearize.argtypes = [C.c_void_p, fp, dp, dp]
         L.oracle_linearize.restype = C.c_double
@@ -146,6 +148,11 @@ class Oracle:
 
     def fitness(self, max_range=float(np.finfo(np.float64).max)):
         return self.L.oracle_fitness(self.h, max_range)
+
+    def fitness_score(self, T, max_range=float(np.finfo(np.float64).max)):
+        """calc_fitness_score(target=cloud1, source=cloud2, relpose=T, max_range)"""
+        g = _f32(T).reshape(16)
+        return self.L.oracle_fitness_score(self.h, _ptr(g, C.c_float), max_range)
 
     def compute_covariances(self):
         return self.L.oracle_compute_covariances(self.h)

@@ -79,6 +79,17 @@ int oracle_align(void* h, const float* guess16, float* T16, int* converged, int*
   return rc;
 }
 
+// InformationMatrixCalculator::calc_fitness_score (information_matrix_calculator.cpp:55-86): same pass with an explicit pose
+double oracle_fitness_score(void* h, const float* T16, double max_range) {
+  auto* o = static_cast<FastAPDGICP*>(h);
+  float saved[16];
+  std::memcpy(saved, o->final_T_, sizeof(saved));
+  std::memcpy(o->final_T_, T16, sizeof(saved));
+  const double f = o->getFitnessScore(max_range);
+  std::memcpy(o->final_T_, saved, sizeof(saved));
+  return f;
+}
+
 double oracle_fitness(void* h, double max_range) { return static_cast<FastAPDGICP*>(h)->getFitnessScore(max_range); }
 
 int oracle_compute_covariances(void* h) { return static_cast<FastAPDGICP*>(h)->ensure_covariances() ? 0 : -2; }

@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       status = APD_ERR_TOO_FEW_POINTS;
     }
 
-    for (int it = 0; have_input && it < (B.mode == 1 ? 1 : P.max_iterations); it++) {
+    for (int it = 0; have_input && it < (B.mode == 1 ? 1 : (B.mode == 2 ? 0 : P.max_iterations)); it++) {
       iterations = it;
       // ---- linearize(x0) ----
       correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     // ---- final_transformation_ = x0.cast<float>() (:78) and getFitnessScore ----
 #pragma unroll
     for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-    if (have_input && B.mode == 0) fitness_pass(B, S, T, sspts, begin, end, sbase, P.max_iterations > 0, acc);
+    if (have_input && B.mode != 1) fitness_pass(B, S, T, sspts, begin, end, sbase, B.mode == 0 && P.max_iterations > 0, acc);
     team_reduce<TEAM, 2>(acc, S, tc);
     if (leader) {
       apd_result r;

@@ -502,10 +502,11 @@ struct AlignCall {
 
 // Enqueue the align kernel for a batch; results land in h->results (device).
 int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, TeamPlan* used_plan = nullptr) {
-  int rc = cloudset_prepare(h, c.src);
+  // mode 2 (fitness score only) needs the grids but no covariances
+  int rc = c.mode == 2 ? cloudset_build_grid(h, c.src) : cloudset_prepare(h, c.src);
   if (rc) return rc;
   if (c.tgt != c.src) {
-    rc = cloudset_prepare(h, c.tgt);
+    rc = c.mode == 2 ? cloudset_build_grid(h, c.tgt) : cloudset_prepare(h, c.tgt);
     if (rc) return rc;
   }
   const int np = c.n_pairs;
@@ -848,6 +849,66 @@ int apd_fitness(apd_handle h, double max_range, double* score) {
   CK(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   *score = r[0];
+  return APD_OK;
+}
+
+// InformationMatrixCalculator::calc_fitness_score (radar_graph_slam/src/radar_graph_slam/information_matrix_calculator.cpp:55-86):
+// target slot = cloud1 (the kd-tree side), source slot = cloud2, T = relpose.cast<float>()
+int apd_fitness_score(apd_handle h, const float T[16], double max_range, double* score, int64_t* n_used) {
+  if (!h || !score) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (!h->src || !h->tgt || h->src->total == 0 || h->tgt->total == 0) return fail(h, APD_ERR_NO_INPUT, "source or target cloud not set");
+  int rc = cloudset_build_grid(h, h->src.get());
+  if (rc) return rc;
+  rc = cloudset_build_grid(h, h->tgt.get());
+  if (rc) return rc;
+  float Th[16];
+  if (T) memcpy(Th, T, sizeof(Th));
+  else for (int i = 0; i < 16; i++) Th[i] = (i % 5 == 0) ? 1.f : 0.f;
+  const int blocks = std::max(1, std::min(2 * h->sm_count, (int)((h->src->total + 255) / 256)));
+  CK(h->misc.reserve(sizeof(double) * (2 * blocks + 2) + sizeof(float) * 16));
+  double* partials = h->misc.as<double>();
+  double* res = partials + 2 * blocks;
+  float* dT = reinterpret_cast<float*>(res + 2);
+  CK(cudaMemcpyAsync(dT, Th, sizeof(Th), cudaMemcpyHostToDevice, h->stream));
+  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, max_range, partials, blocks, res, h->stream, &h->stats));
+  double r[2];
+  CK(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *score = r[0];
+  if (n_used) *n_used = (int64_t)r[1];
+  return APD_OK;
+}
+
+// Batched calc_fitness_score: pair i scores cloud src_idx[i] of `src` (cloud2) against cloud tgt_idx[i] of `tgt`
+// (cloud1) at poses[i]; one launch for a whole sliding window of keyframe pairs.
+int apd_fitness_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int32_t* src_idx, const int32_t* tgt_idx, const float* poses, int n_pairs,
+                      double max_range, double* scores) {
+  if (!h || !src || !tgt || !scores || n_pairs < 0) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (n_pairs == 0) return APD_OK;
+  apd_cloudset_s* s = reinterpret_cast<std::shared_ptr<apd_cloudset_s>*>(src)->get();
+  apd_cloudset_s* t = reinterpret_cast<std::shared_ptr<apd_cloudset_s>*>(tgt)->get();
+  for (int i = 0; i < n_pairs; i++) {
+    const int si = src_idx ? src_idx[i] : i, ti = tgt_idx ? tgt_idx[i] : i;
+    if (si < 0 || si >= s->n_clouds || ti < 0 || ti >= t->n_clouds) return fail(h, APD_ERR_INVALID, "pair index out of range");
+  }
+  AlignCall c;
+  c.src = s;
+  c.tgt = t;
+  c.src_idx = src_idx;
+  c.tgt_idx = tgt_idx;
+  c.guesses = poses;
+  c.n_pairs = n_pairs;
+  c.mode = 2;
+  c.max_range = max_range;
+  int rc = run_align(h, c);
+  if (rc) return rc;
+  std::vector<apd_result> r(n_pairs);
+  CK(cudaMemcpyAsync(r.data(), h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_pairs; i++) scores[i] = r[i].fitness;
+  h->last_lin_valid = false;
   return APD_OK;
 }
 

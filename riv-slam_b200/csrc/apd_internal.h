@@ -116,7 +116,8 @@ struct AlignBatch {
   AlignScratch scratch;
   DeviceParams prm;
   int min_points;          // pairs with a cloud smaller than this report APD_ERR_TOO_FEW_POINTS (k; 0 = no check)
-  int mode;                // 0 = align, 1 = linearize only (evaluateCost): out->error, final_hessian, lin_b
+  int mode;                // 0 = align, 1 = linearize only (evaluateCost): out->error, final_hessian, lin_b,
+                           // 2 = fitness score only at the given pose (calc_fitness_score): out->fitness, out->T = pose
   double max_range;        // fitness gate (getFitnessScore max_range)
 };
 

@@ -96,6 +96,8 @@ _PROTOTYPES = {
     "apd_cloudset_prepare": (C.c_int, [C.c_void_p, C.c_void_p]),
     "apd_align_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip, _fp, C.c_int, C.c_void_p, C.c_int]),
     "apd_batch_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_void_p, _ip, C.c_int, _fp, C.c_int, C.c_void_p]),
+    "apd_fitness_score": (C.c_int, [C.c_void_p, _fp, C.c_double, _dp, C.POINTER(C.c_int64)]),
+    "apd_fitness_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip, _fp, C.c_int, C.c_double, _dp]),
     "apd_odometry_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_int, _fp, C.c_void_p]),
     "apd_synchronize": (C.c_int, [C.c_void_p]),
     "apd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
@@ -541,3 +543,16 @@ def odometry_align(handle: Handle, scans, guesses=None, out=None):
     optr = C.c_void_p(res.data_ptr()) if _is_torch(res) else C.c_void_p(res.ctypes.data)
     handle.check(handle.L.apd_odometry_align(handle.h, ptr, off.ctypes.data_as(_ip), n, stride, None if g is None else g.ctypes.data_as(_fp), optr))
     return res
+
+
+def fitness_pairs(handle: Handle, src: CloudSet, tgt: CloudSet, src_idx=None, tgt_idx=None, poses=None, max_range: float = DBL_MAX, n_pairs=None):
+    """apd_fitness_pairs: batched calc_fitness_score; returns float64[n_pairs]."""
+    si = None if src_idx is None else np.ascontiguousarray(src_idx, dtype=np.int32)
+    ti = None if tgt_idx is None else np.ascontiguousarray(tgt_idx, dtype=np.int32)
+    if n_pairs is None:
+        n_pairs = len(si) if si is not None else (len(ti) if ti is not None else min(src.n_clouds, tgt.n_clouds))
+    g = None if poses is None else np.ascontiguousarray(poses, dtype=np.float32).reshape(n_pairs, 16)
+    out = np.zeros(n_pairs)
+    handle.check(handle.L.apd_fitness_pairs(handle.h, src.cs, tgt.cs, None if si is None else si.ctypes.data_as(_ip), None if ti is None else ti.ctypes.data_as(_ip),
+                                            None if g is None else g.ctypes.data_as(_fp), n_pairs, float(max_range), out.ctypes.data_as(_dp)))
+    return out

@@ -475,3 +475,30 @@ def test_pipelined_host_batches_equal_one_launch():
     got3 = odometry_align(H, scans, guesses=g)
     ref3 = align_pairs(H, S, S, src_idx=np.arange(1, n + 1), tgt_idx=np.arange(0, n), guesses=g)
     assert got3.tobytes() == ref3.tobytes()
+
+
+def test_information_matrix_fitness_score(small_pair):
+    """SURVEY §8(f)-1: InformationMatrixCalculator::calc_fitness_score / calc_information_matrix."""
+    from riv_slam_b200.information_matrix import InformationMatrixCalculator
+    from riv_slam_b200.fast_apdgicp import Handle, CloudSet, fitness_pairs
+    src, tgt, T_gt = small_pair
+    calc = InformationMatrixCalculator()
+    o = _oracle()
+    o.set_source(src); o.set_target(tgt)
+    for pose, rng in ((np.eye(4), 1e300), (T_gt, 1e300), (T_gt, 1.0), (T_gt, 1e-9)):
+        f = calc.calc_fitness_score(tgt, src, pose, max_range=rng)
+        f0 = o.fitness_score(pose, rng)
+        assert abs(f - f0) <= REL_TOL * abs(f0)
+    assert calc.calc_fitness_score(tgt, src, T_gt, max_range=-1.0) == np.finfo(np.float64).max   # nothing in range
+    inf = calc.calc_information_matrix(tgt, src, T_gt)
+    f0 = o.fitness_score(T_gt)
+    w = lambda lo, hi: np.float32(1e-8 * (lo ** 2 + (hi ** 2 - lo ** 2) * (1 - np.exp(-20.0 * f0)) / (1 - np.exp(-20.0 * 2.5))))
+    assert np.allclose(np.diag(inf)[:3], 1.0 / float(w(0.1, 5.0)), rtol=1e-5) and np.allclose(np.diag(inf)[3:], 1.0 / float(w(0.05, 0.2)), rtol=1e-5)
+    # batched over cloud sets
+    H = Handle(0)
+    S, T = CloudSet(H, [src, src[:700]]), CloudSet(H, [tgt])
+    poses = np.stack([T_gt, np.eye(4)]).astype(np.float32)
+    sc = fitness_pairs(H, S, T, tgt_idx=[0, 0], poses=poses, max_range=4.0)
+    o2 = _oracle()
+    o2.set_source(src[:700]); o2.set_target(tgt)
+    assert abs(sc[0] - o.fitness_score(T_gt, 4.0)) <= REL_TOL * sc[0] and abs(sc[1] - o2.fitness_score(np.eye(4), 4.0)) <= REL_TOL * sc[1]
