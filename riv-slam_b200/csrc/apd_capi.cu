@@ -1138,7 +1138,7 @@ int apd_align_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int3
 // pairs are independent and every pair is processed by the same team shape.
 namespace {
 
-constexpr int kChunkPairs = 256;  // pairs per chunk; the last scan of an odometry chunk is repeated in the next
+constexpr int kMinChunkPairs = 256;  // smallest chunk worth a launch sequence of its own
 
 struct ChunkSlot {
   apd_handle h = nullptr;
@@ -1180,6 +1180,10 @@ int retire(apd_handle owner, ChunkSlot& s, long long* lin, long long* err) {
 // odometry == true: one ragged array of n_pairs + 1 scans, pair i = scan i+1 -> scan i
 int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, const float* pts_tgt, const int32_t* off_tgt, int stride_bytes, const float* guesses,
                     int n_pairs, apd_result* out, bool odometry) {
+  // about four chunks per call, each a whole number of waves of one-pair-per-SM teams: enough to hide
+  // all but the first upload, few enough that launch tails and per-chunk host work stay small
+  int kChunkPairs = std::max(kMinChunkPairs, (n_pairs + 3) / 4);
+  kChunkPairs = (kChunkPairs + h->sm_count - 1) / h->sm_count * h->sm_count;
   ChunkSlot slots[2];
   slots[0].h = h;
   if (n_pairs > kChunkPairs) {

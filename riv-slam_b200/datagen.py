@@ -91,6 +91,8 @@ def pose_matrix(t, rpy_deg) -> np.ndarray:
 
 def _cast(scene: Scene, origin: np.ndarray, dirs: np.ndarray, rmax: float) -> np.ndarray:
     """First-hit range along unit rays (n,3) from origin (3,); inf where nothing is hit."""
+    if dirs.shape[0] > 65536:  # bound the (rays x obstacles) temporaries of the million-point configs
+        return np.concatenate([_cast(scene, origin, dirs[i:i + 65536], rmax) for i in range(0, dirs.shape[0], 65536)])
     n = dirs.shape[0]
     best = np.full(n, np.inf)
     eps = 1e-12

@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""Measurements for the BASELINE.json configs that bench.py's headline line does not cover
+(C3 scan-to-submap, C4 batched loop-closure verification, C5 large-cloud sweep) and for the
+"next" row 8(f)-1 (fitness scoring), each with the CPU oracle timed beside it on a bounded sample.
+One JSON line per measurement on stdout; run on the GPU box:
+
+    python scripts/bench_configs.py [c3] [c4] [c5] [fit]  > gpurun_out/configs.jsonl
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from bench import LAUNCH_PARAMS  # noqa: E402
+from riv_slam_b200 import datagen  # noqa: E402
+from riv_slam_b200 import fast_apdgicp as F  # noqa: E402
+
+PEAK = 6545.6
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def gpu_time(H, fn, reps=3):
+    """best-of wall clock around a synchronised call (the calls themselves end with a stream sync)"""
+    best = 1e30
+    for _ in range(reps):
+        H.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        H.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def oracle(**kw):
+    from oracle.oracle import Oracle
+    p = dict(LAUNCH_PARAMS)
+    p.update(kw)
+    return Oracle(**p)
+
+
+def c3():
+    """5k-point scans against a ~100k-point accumulated submap, target prepared once and reused."""
+    n_scans, per = 24, 5000
+    scans, poses = datagen.make_drive(3, 0, n_scans + 20, per, workers=min(16, os.cpu_count() or 1))
+    sub = []
+    for t in range(20):  # 20 scans accumulated in the frame of scan 0 (SMO:606-617 keeps the last keyframes)
+        Trel = np.linalg.inv(poses[0]) @ poses[t]
+        p = scans[t].copy()
+        p[:, :3] = (scans[t][:, :3].astype(np.float64) @ Trel[:3, :3].T + Trel[:3, 3]).astype(np.float32)
+        sub.append(p)
+    submap = np.concatenate(sub)
+    queries = scans[20:20 + n_scans]
+    guesses = np.stack([(np.linalg.inv(poses[0]) @ poses[19]).astype(np.float32)] * n_scans)
+    H = F.Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+    T = F.CloudSet(H, [submap])
+    t_prep = gpu_time(H, lambda: (setattr(T, "_x", 0), T.prepare())[1], reps=1)
+    S = F.CloudSet(H, queries)
+    S.prepare()
+    H.synchronize()
+    res = None
+
+    def run():
+        nonlocal res
+        res = F.align_pairs(H, S, T, tgt_idx=np.zeros(n_scans, np.int32), guesses=guesses)
+    t_batch = gpu_time(H, run)
+    # one scan at a time through the reference-shaped object (target cached by key)
+    reg = F.FastAPDGICP(0)
+    reg.handle().set_params(**LAUNCH_PARAMS)
+    reg.setInputTarget(submap, cache_key=1)
+    lat = []
+    for i, q in enumerate(queries):
+        t0 = time.perf_counter()
+        reg.setInputTarget(submap, cache_key=1)
+        reg.setInputSource(q, cache_key=100 + i)
+        reg.align(guesses[i], want_output=False)
+        reg.getFitnessScore()
+        lat.append(time.perf_counter() - t0)
+    o = oracle()
+    t0 = time.perf_counter()
+    o.set_target(submap)
+    o.set_source(queries[0])
+    o.compute_covariances()
+    t_cpu_prep = time.perf_counter() - t0
+    cpu = []
+    for i in range(min(8, n_scans)):
+        t0 = time.perf_counter()
+        o.set_source(queries[i])
+        rc, Tc, conv, it = o.align(guesses[i])
+        o.fitness()
+        cpu.append(time.perf_counter() - t0)
+        assert np.abs(Tc - res[i]["T"]).max() < 1e-3
+    emit(config="C3 scan-to-submap", n_src=per, n_tgt=int(submap.shape[0]), target_prepare_ms=t_prep * 1e3, batch_reg_per_s=n_scans / t_batch,
+         single_p50_latency_ms=float(np.median(lat[2:]) * 1e3), cpu_target_prepare_ms=t_cpu_prep * 1e3, cpu_p50_latency_ms=float(np.median(cpu) * 1e3),
+         cpu_reg_per_s=len(cpu) / sum(cpu), converged=int(res["converged"].sum()), mean_iterations=float(res["iterations"].mean()))
+
+
+def c4():
+    """4096 independent 5k-point pairs, identity guess (loop-closure candidate verification)."""
+    n_pairs, uniq = 4096, 64
+    base = [datagen.make_pair(4, i, n_src=5000) for i in range(uniq)]
+    srcs = [base[i % uniq][0] for i in range(n_pairs)]
+    tgts = [base[i % uniq][1] for i in range(n_pairs)]
+    H = F.Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+    ps, os_ = F._ragged(srcs)
+    pt, ot = F._ragged(tgts)
+    res = None
+
+    def e2e():
+        nonlocal res
+        res = F.batch_align(H, (ps, os_), (pt, ot))
+    e2e()
+    t_e2e = gpu_time(H, e2e, reps=2)
+    lin, err, _ = H.work_counters()
+    S, T = F.CloudSet(H, (ps, os_)), F.CloudSet(H, (pt, ot))
+    t_prep = gpu_time(H, lambda: (S.prepare(), T.prepare()), reps=1)
+    t_align = gpu_time(H, lambda: F.align_pairs(H, S, T), reps=2)
+    o = oracle()
+    cpu = []
+    for i in range(40):
+        sec, Tc, conv, it, fit = o.timed_registration(srcs[i], tgts[i])
+        cpu.append(sec)
+        assert np.abs(Tc - res[i]["T"]).max() < 1e-3 and bool(res[i]["converged"]) == conv
+    bytes_align = 5000 * (148 * lin + 84 * err + 32 * n_pairs)
+    emit(config="C4 batched loop-closure verification", n_pairs=n_pairs, unique_pairs=uniq, e2e_reg_per_s=n_pairs / t_e2e, e2e_ms=t_e2e * 1e3,
+         prepare_ms=t_prep * 1e3, align_ms=t_align * 1e3, device_reg_per_s=n_pairs / (t_prep + t_align), align_algorithmic_GBps=bytes_align / t_align / 1e9,
+         align_frac_of_measured_hbm=bytes_align / t_align / 1e9 / PEAK, cpu_reg_per_s=len(cpu) / sum(cpu), cpu_sample="first 40 pairs, all host cores",
+         converged_frac=float(res["converged"].mean()), mean_iterations=float(res["iterations"].mean()))
+
+
+def c5():
+    """200k-point source vs 1M-point target (scene scaled x4, no voxel filter), k in {10, 15, 20}."""
+    src, tgt, T_gt = datagen.make_pair(5, 0, n_src=200000, n_tgt=1000000, scale=4.0, voxel=None)
+    for k in (10, 15, 20):
+        reg = F.FastAPDGICP(0)
+        reg.handle().set_params(**dict(LAUNCH_PARAMS, k_correspondences=k))
+        H = reg.handle()
+        reg.setInputTarget(tgt)
+        reg.setInputSource(src)
+        H.synchronize()
+        t_cov = gpu_time(H, reg.computeCovariances, reps=1)       # grid + kNN + covariances of both clouds (1.2M points)
+        t_lin = gpu_time(H, lambda: reg.evaluateCost(np.eye(4)), reps=3)
+        t_align = gpu_time(H, lambda: reg.align(None, want_output=False), reps=2)
+        lin, err, _ = H.work_counters()
+        n_all = src.shape[0] + tgt.shape[0]
+        row = dict(config="C5 large-cloud sweep", k=k, n_src=int(src.shape[0]), n_tgt=int(tgt.shape[0]), grid_knn_cov_ms=t_cov * 1e3,
+                   knn_cov_points_per_s=n_all / t_cov, knn_cov_algorithmic_GBps=n_all * 84 / t_cov / 1e9, linearize_ms=t_lin * 1e3,
+                   linearize_algorithmic_GBps=src.shape[0] * 148 / t_lin / 1e9, linearize_frac_of_measured_hbm=src.shape[0] * 148 / t_lin / 1e9 / PEAK,
+                   align_ms=t_align * 1e3, linearize_passes=int(lin), error_passes=int(err), converged=bool(reg.hasConverged()), iterations=reg.nr_iterations())
+        if k == 20:
+            o = oracle(k_correspondences=k)
+            o.set_target(tgt)
+            o.set_source(src)
+            t0 = time.perf_counter()
+            o.compute_covariances()
+            row["cpu_knn_cov_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            e0, H0, b0 = o.linearize(np.eye(4))
+            row["cpu_linearize_ms"] = (time.perf_counter() - t0) * 1e3
+            e, Hg, bg = reg.evaluateCost(np.eye(4))
+            row["H_rel_err_vs_oracle"] = float(np.abs(Hg - H0).max() / np.abs(H0).max())
+            t0 = time.perf_counter()
+            rc, Tc, conv, it = o.align()
+            row["cpu_align_ms"] = (time.perf_counter() - t0) * 1e3
+            reg.align(None, want_output=False)
+            row["T_abs_err_vs_oracle"] = float(np.abs(Tc - reg.getFinalTransformation()).max())
+        emit(**row)
+
+
+def fit():
+    """8(f)-1: fitness scoring of a sliding window of keyframe pairs in one launch vs one by one on the CPU."""
+    n, per = 256, 5000
+    scans, poses = datagen.make_drive(2, 7, 33, per, workers=min(16, os.cpu_count() or 1))
+    idx_a = np.arange(n) % 32
+    idx_b = idx_a + 1
+    rel = np.stack([(np.linalg.inv(poses[a]) @ poses[b]).astype(np.float32) for a, b in zip(idx_a, idx_b)])
+    H = F.Handle(0)
+    S = F.CloudSet(H, scans)
+    sc = None
+
+    def run():
+        nonlocal sc
+        sc = F.fitness_pairs(H, S, S, src_idx=idx_b, tgt_idx=idx_a, poses=rel, max_range=1e300)
+    run()
+    t = gpu_time(H, run)
+    o = oracle()
+    cpu = []
+    for i in range(16):
+        t0 = time.perf_counter()
+        o.set_target(scans[idx_a[i]])
+        o.set_source(scans[idx_b[i]])
+        f0 = o.fitness_score(rel[i])
+        cpu.append(time.perf_counter() - t0)
+        assert abs(f0 - sc[i]) <= 1e-5 * f0
+    emit(config="8(f)-1 fitness scoring (calc_fitness_score)", n_pairs=n, points=per, gpu_scores_per_s=n / t, gpu_ms=t * 1e3,
+         algorithmic_GBps=n * per * 32 / t / 1e9, cpu_scores_per_s=len(cpu) / sum(cpu), cpu_note="kd-tree build + single-threaded queries, as the reference")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c3", "c4", "fit", "c5"]
+    for w in which:
+        {"c3": c3, "c4": c4, "c5": c5, "fit": fit}[w]()
