@@ -168,7 +168,8 @@ int apd_synchronize(apd_handle h);
  *   "team_size"        CTAs cooperating on one pair: 0 = automatic, 1 = one CTA, 2..16 = cluster
  *   "force_unstaged"   1 = never stage the target grid in shared memory
  *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit)
- *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only */
+ *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only
+ *   "knn_fine_rings"   kNN: rings searched on one level of the grid pyramid before restarting on the next coarser one */
 int apd_set_option(apd_handle h, const char* name, double value);
 
 /* Batched calc_fitness_score over cloud sets (one launch for a sliding window of keyframe pairs): scores[i] for cloud src_idx[i]

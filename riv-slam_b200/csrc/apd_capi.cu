@@ -163,6 +163,7 @@ struct apd_context {
   int force_unstaged = 0;
   int max_teams_opt = 0;  // 0 = as many as fit
   int knn_packed = 1;
+  int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
       counters, grid_partials, misc, knn_tmp, cov_tmp;
@@ -226,6 +227,7 @@ DeviceParams device_params(const apd_params& p) {
   d.sin_az = std::sin(p.azimuth_var / 180 * M_PI);
   d.sin_el = std::sin(p.elevation_var / 180 * M_PI);
   d.knn_packed = 1;
+  d.knn_fine_rings = kFineRingsKnn;
   return d;
 }
 
@@ -306,8 +308,8 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   // split so that about two waves of CTAs exist
   std::vector<int4> tk;
   const long long target_ctas = 2ll * h->sm_count;
-  long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 128);
-  tile_q = std::max<long long>(tile_q, 1);
+  long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 32);
+  tile_q = (std::max<long long>(tile_q, 1) + 31) / 32 * 32;  // whole warps
   for (int c = 0; c < nc; c++) {
     const int n = cs->h_off[c + 1] - cs->h_off[c];
     for (long long s = 0; s < n; s += tile_q) tk.push_back(int4{c, (int)s, (int)std::min<long long>(tile_q, n - s), 0});
@@ -389,6 +391,7 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
   if (cs->cov_valid && cs->cov_k < 0 && !knn_out) return APD_OK;  // covariances injected by the caller (setSource/TargetCovariances)
   DeviceParams dp = device_params(h->prm);
   dp.knn_packed = h->knn_packed;
+  dp.knn_fine_rings = h->knn_fine_rings;
   CK(launch_knn_cov(cs->view(), cs->tiles_knn.as<int4>(), cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
@@ -719,6 +722,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "force_unstaged") h->force_unstaged = value != 0;
   else if (n == "max_teams") h->max_teams_opt = (int)value;
   else if (n == "knn_packed") h->knn_packed = value != 0;
+  else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
 }
@@ -1160,6 +1164,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->force_unstaged = h->force_unstaged;
   x->max_teams_opt = h->max_teams_opt;
   x->knn_packed = h->knn_packed;
+  x->knn_fine_rings = h->knn_fine_rings;
   *out = x;
   return APD_OK;
 }

@@ -14,7 +14,7 @@ namespace apd {
 // walking (2r+1)^2 mostly empty rows per ring through a sparse neighbourhood.
 constexpr int kCoarseLevels = 2;
 constexpr int kFineRings = 3;     // Top1 searches: rings tried on a level before going coarser
-constexpr int kFineRingsKnn = 8;  // kNN: restarting re-inserts every neighbour, so only truly isolated points go coarser
+constexpr int kFineRingsKnn = 5;  // kNN: measured optimum (profiles/): coarse cells hold many points, so only sparse neighbourhoods go coarser
 struct CoarseLevel {
   float4* spts;
   unsigned* cells;
@@ -53,8 +53,9 @@ __device__ __forceinline__ GridView<unsigned> coarse_view(const CloudSetView& cs
 // Exact unbounded (or gate-bounded) search through the pyramid: fine grid first, then coarser levels.
 // A TopK visitor must be reset between levels (the same points would be offered twice); a Top1
 // visitor keeps its key, which only tightens the bound. Returns the level that completed the search.
-template <typename CellT, typename Visitor, bool RESET, int RINGS = kFineRings>
-__device__ __forceinline__ int pyramid_search(const GridView<CellT>& G0, const CloudSetView& cs, int cloud, float qx, float qy, float qz, float limit2, Visitor& vis) {
+template <typename CellT, typename Visitor, bool RESET>
+__device__ __forceinline__ int pyramid_search(const GridView<CellT>& G0, const CloudSetView& cs, int cloud, float qx, float qy, float qz, float limit2, Visitor& vis,
+                                              int RINGS = kFineRings) {
   if (grid_search(G0, qx, qy, qz, limit2, vis, RINGS)) return 0;
   if (RESET) vis.init();
   const GridView<unsigned> G1 = coarse_view(cs, 0, cloud);
@@ -81,6 +82,7 @@ struct DeviceParams {
   double sin_az;            // sin(azimuth_var / 180 * pi)
   double sin_el;            // sin(elevation_var / 180 * pi)
   int knn_packed;           // kNN: use the packed 32-bit candidate list (tuning; results identical)
+  int knn_fine_rings;       // kNN: rings tried on a pyramid level before restarting on the next coarser one
 };
 
 // Per concurrent pair slot scratch of the align kernel (sorted-source order).

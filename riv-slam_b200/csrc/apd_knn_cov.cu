@@ -42,7 +42,7 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov, int method) {
 
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kKnnThreads, 1)
-knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int* __restrict__ knn_out) {
+knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int fine_rings, int* __restrict__ knn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int4 tile = tiles[blockIdx.x];
   const int c = tile.x;
@@ -96,7 +96,7 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
       ap.kbits = kbits;
       ap.sh = kbits - 1;
       ap.init();
-      pyramid_search<CellT, TopKPacked<K, K + 4>, true, kFineRingsKnn>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), ap);
+      pyramid_search<CellT, TopKPacked<K, K + 4>, true>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), ap, fine_rings);
       if (ap.complete()) {
         exact_from_packed(ap, p.x, p.y, p.z, opts, tk);
         done = true;
@@ -104,7 +104,7 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
     }
     if (!done) {
       tk.init();
-      pyramid_search<CellT, TopK<K>, true, kFineRingsKnn>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), tk);
+      pyramid_search<CellT, TopK<K>, true>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), tk, fine_rings);
     }
 
     // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324)
@@ -157,9 +157,9 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
   if (staged) {
     cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, knn_out);
+    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, knn_out);
   } else {
-    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, knn_out);
+    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, knn_out);
   }
   return cudaGetLastError();
 }
