@@ -355,8 +355,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       if (S.staged_target != t) {  // consecutive pairs on the same target (scan-to-submap) reuse the staged grid
         const float4* gp = B.tgt.spts + tb;
         const unsigned* gc = B.tgt.cells + B.tgt.cell_off[t];
-        for (int i = threadIdx.x; i < nt; i += blockDim.x) s_pts[i] = gp[i];
-        for (int i = threadIdx.x; i <= T.G.g.ncells; i += blockDim.x) s_cells[i] = (uint16_t)gc[i];
+        stage_grid(s_pts, s_cells, gp, gc, nt, T.G.g.ncells);
         __syncthreads();
         if (threadIdx.x == 0) S.staged_target = t;
       }

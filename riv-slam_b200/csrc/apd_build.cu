@@ -57,18 +57,10 @@ __global__ void __launch_bounds__(kTileThreads) bbox_kernel(CloudSetView cs, con
   }
 }
 
-// One thread per cloud: bounding box -> cell edge h and grid dimensions with nx*ny*nz <= cell_cap.
-__global__ void grid_params_kernel(CloudSetView cs, const unsigned* __restrict__ bbox, const int* __restrict__ cell_cap) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cs.n_clouds) return;
-  float lo[3], hi[3];
-  for (int a = 0; a < 3; a++) {
-    const unsigned l = bbox[c * 6 + a], h = bbox[c * 6 + 3 + a];
-    if (l > h) { lo[a] = 0.f; hi[a] = 0.f; }  // no finite point
-    else { lo[a] = dec_f(l); hi[a] = dec_f(h); }
-  }
+// Bounding box -> cell edge h and grid dimensions with nx*ny*nz <= cap.
+__device__ __forceinline__ GridParams make_grid_params(const float lo[3], const float hi[3], long long cap) {
   const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-  const long long cap = max(cell_cap[c], 1);
+  if (cap < 1) cap = 1;
   // start from the edge that spends the whole budget on the box volume, then grow until it fits
   const float emax = fmaxf(fmaxf(ex, ey), ez);
   const float floor_h = fmaxf(emax * 1e-4f, 1e-6f);
@@ -93,7 +85,20 @@ __global__ void grid_params_kernel(CloudSetView cs, const unsigned* __restrict__
   float amax = 0.f;
   for (int a = 0; a < 3; a++) amax = fmaxf(amax, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
   g.slack = 4e-6f * (amax + emax + h) + 1e-30f;
-  cs.grid[c] = g;
+  return g;
+}
+
+// One thread per cloud.
+__global__ void grid_params_kernel(CloudSetView cs, const unsigned* __restrict__ bbox, const int* __restrict__ cell_cap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cs.n_clouds) return;
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; a++) {
+    const unsigned l = bbox[c * 6 + a], h = bbox[c * 6 + 3 + a];
+    if (l > h) { lo[a] = 0.f; hi[a] = 0.f; }  // no finite point
+    else { lo[a] = dec_f(l); hi[a] = dec_f(h); }
+  }
+  cs.grid[c] = make_grid_params(lo, hi, cell_cap[c]);
 }
 
 __global__ void __launch_bounds__(kTileThreads) count_kernel(CloudSetView cs, const int4* __restrict__ tiles, int* __restrict__ cellid) {
@@ -172,15 +177,8 @@ __global__ void __launch_bounds__(kTileThreads) scatter_kernel(CloudSetView cs, 
 // rank counting: every element counts the smaller keys of its cell, all reads happen before any
 // write, so there is no dependent chain of global-memory round trips (the first version's per-thread
 // insertion sort cost 180 us on one 5000-point cloud because of it).
-__global__ void cell_sort_kernel(CloudSetView cs, int cloud_begin) {
-  const int c = cloud_begin + blockIdx.y;
-  if (c >= cs.n_clouds) return;
-  const int ncells = cs.grid[c].ncells;
-  const unsigned* cells = cs.cells + cs.cell_off[c];
-  float4* sp = cs.spts + cs.pt_off[c];
+__device__ __forceinline__ void warp_sort_cells(const unsigned* __restrict__ cells, float4* __restrict__ sp, int ncells, int warp, int n_warps) {
   const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int n_warps = gridDim.x * (blockDim.x >> 5);
   for (int cell0 = warp * 32; cell0 < ncells; cell0 += n_warps * 32) {
     const int cell = cell0 + lane;
     int s = 0, m = 0;
@@ -236,6 +234,135 @@ __global__ void cell_sort_kernel(CloudSetView cs, int cloud_begin) {
       __syncwarp();
     }
   }
+}
+
+__global__ void cell_sort_kernel(CloudSetView cs, int cloud_begin) {
+  const int c = cloud_begin + blockIdx.y;
+  if (c >= cs.n_clouds) return;
+  warp_sort_cells(cs.cells + cs.cell_off[c], cs.spts + cs.pt_off[c], cs.grid[c].ncells, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5),
+                  gridDim.x * (blockDim.x >> 5));
+}
+
+// ---- fused build for small clouds: ONE CTA builds one pyramid level of one cloud ----
+// bbox -> grid parameters -> count -> scan -> scatter -> (finest level) cell sort + inverse order, with
+// block barriers instead of kernel boundaries. Replaces ~23 launches per cloud set by one; on a single
+// 5000-point scan that is the difference between ~130 us and ~20 us of the align latency.
+struct FusedLevels {
+  const int* cap[1 + kCoarseLevels];      // per-cloud cell budgets of each level
+  int* cellid[1 + kCoarseLevels];         // per-point cell ids (workspace, one array per level)
+  unsigned* cursor[1 + kCoarseLevels];    // scatter cursors (workspace, laid out like the level's cell table)
+};
+
+__global__ void __launch_bounds__(1024) build_fused_kernel(CloudSetView cs, FusedLevels L) {
+  __shared__ unsigned s_box[32][6];
+  __shared__ GridParams s_g;
+  __shared__ unsigned s_warp[32];
+  const int c = blockIdx.x, level = blockIdx.y;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int base = cs.pt_off[c];
+  const int n = cs.pt_off[c + 1] - base;
+  const float4* pts = cs.pts + base;
+  float4* spts = (level == 0 ? cs.spts : cs.coarse[level - 1].spts) + base;
+  const long long coff = level == 0 ? cs.cell_off[c] : cs.coarse[level - 1].cell_off[c];
+  unsigned* cells = (level == 0 ? cs.cells : cs.coarse[level - 1].cells) + coff;
+  unsigned* cursor = L.cursor[level] + coff;
+  int* cellid = L.cellid[level] + base;
+
+  // 1. bounding box of the finite points
+  unsigned mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  for (int i = tid; i < n; i += T) {
+    const float4 p = pts[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const unsigned e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        mn[a] = min(mn[a], e[a]);
+        mx[a] = max(mx[a], e[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
+    mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { s_box[warp][a] = mn[a]; s_box[warp][3 + a] = mx[a]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+      unsigned l = 0xFFFFFFFFu, h = 0u;
+      for (int w = 0; w < (T >> 5); w++) { l = min(l, s_box[w][a]); h = max(h, s_box[w][3 + a]); }
+      if (l > h) { lo[a] = 0.f; hi[a] = 0.f; }
+      else { lo[a] = dec_f(l); hi[a] = dec_f(h); }
+    }
+    s_g = make_grid_params(lo, hi, L.cap[level][c]);
+    (level == 0 ? cs.grid : cs.coarse[level - 1].grid)[c] = s_g;
+  }
+  __syncthreads();
+  const GridParams g = s_g;
+  const int total = g.ncells + 1;
+
+  // 2. zero the counters, 3. count
+  for (int j = tid; j < total; j += T) cells[j] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const float4 p = pts[i];
+    const int cell = cell_index(g, p.x, p.y, p.z);
+    cellid[i] = cell;
+    atomicAdd(&cells[cell], 1u);
+  }
+  __syncthreads();
+
+  // 4. exclusive scan: every thread owns a contiguous segment, the segment totals are scanned by the block
+  const int seg = (total + T - 1) / T;
+  const int j0 = min(tid * seg, total), j1 = min(j0 + seg, total);
+  unsigned sum = 0;
+  for (int j = j0; j < j1; j++) sum += cells[j];
+  unsigned incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    const unsigned w = tid < (T >> 5) ? s_warp[tid] : 0u;
+    unsigned wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+      if (tid >= d) wi += t;
+    }
+    s_warp[tid] = wi - w;
+  }
+  __syncthreads();
+  unsigned run = s_warp[warp] + incl - sum;
+  for (int j = j0; j < j1; j++) {
+    const unsigned v = cells[j];
+    cells[j] = run;
+    cursor[j] = run;
+    run += v;
+  }
+  __syncthreads();
+
+  // 5. scatter
+  for (int i = tid; i < n; i += T) {
+    const float4 p = pts[i];
+    const unsigned pos = atomicAdd(&cursor[cellid[i]], 1u);
+    spts[pos] = make_float4(p.x, p.y, p.z, __uint_as_float((unsigned)i));
+  }
+  if (level != 0) return;
+  __syncthreads();
+
+  // 6. deterministic order inside every cell, then the inverse permutation
+  warp_sort_cells(cells, spts, g.ncells, warp, T >> 5);
+  __syncthreads();
+  for (int i = tid; i < n; i += T) cs.inv0[base + __float_as_uint(spts[i].w)] = i;
 }
 
 // original index -> position in the cell-sorted order (needed when a coarse pyramid level finds a
@@ -360,6 +487,16 @@ cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, 
     APD_LAUNCH_CHECK();
   }
   inverse_order_kernel<<<(cs.total_points + 255) / 256, 256, 0, stream>>>(cs);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap[1 + kCoarseLevels], int* const cellid[1 + kCoarseLevels],
+                                    unsigned* const cursor[1 + kCoarseLevels], cudaStream_t stream, LaunchStats* st) {
+  if (cs.n_clouds == 0) return cudaSuccess;
+  FusedLevels L;
+  for (int l = 0; l <= kCoarseLevels; l++) { L.cap[l] = cap[l]; L.cellid[l] = cellid[l]; L.cursor[l] = cursor[l]; }
+  build_fused_kernel<<<dim3(cs.n_clouds, 1 + kCoarseLevels), 1024, 0, stream>>>(cs, L);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

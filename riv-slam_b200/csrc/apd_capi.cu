@@ -163,6 +163,7 @@ struct apd_context {
   int force_unstaged = 0;
   int max_teams_opt = 0;  // 0 = as many as fit
   int knn_packed = 1;
+  int no_fused_build = 0;
   int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
@@ -276,7 +277,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   long long off = 0;
   for (int c = 0; c < nc; c++) {
     cell_off[c] = off;
-    off += (long long)cap[c] + 1;
+    off += ((long long)cap[c] + 1 + 3) & ~3ll;  // 16-byte aligned tables (stage_grid reads them as uint4)
   }
   cell_off[nc] = off;
   cs->total_cells = off;
@@ -307,7 +308,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   // tiles for kNN + covariance: whole clouds per CTA when the batch alone fills the GPU, otherwise
   // split so that about two waves of CTAs exist
   std::vector<int4> tk;
-  const long long target_ctas = 2ll * h->sm_count;
+  const long long target_ctas = h->sm_count;  // one CTA per SM fits (shared memory): a single wave
   long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 32);
   tile_q = (std::max<long long>(tile_q, 1) + 31) / 32 * 32;  // whole warps
   for (int c = 0; c < nc; c++) {
@@ -367,8 +368,34 @@ int cloudset_fill(apd_handle h, apd_cloudset_s* cs, const float* xyz, int stride
   return APD_OK;
 }
 
+constexpr int kFusedBuildMaxPoints = 16384;  // clouds up to this size are built by one CTA per pyramid level
+
 int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
   if (cs->grid_built || cs->n_clouds == 0) { cs->grid_built = true; return APD_OK; }
+  if (cs->max_n <= kFusedBuildMaxPoints && !h->no_fused_build) {
+    // one launch for every level of every cloud
+    const size_t np = (size_t)std::max<long long>(cs->total, 1);
+    CK(h->ws_cellid.reserve(sizeof(int) * np * (1 + kCoarseLevels)));
+    size_t cur_total = (size_t)cs->total_cells;
+    for (int l = 0; l < kCoarseLevels; l++) cur_total += (size_t)cs->c_total_cells[l];
+    CK(h->ws_cursor.reserve(sizeof(unsigned) * cur_total));
+    const int* cap[1 + kCoarseLevels];
+    int* cellid[1 + kCoarseLevels];
+    unsigned* cursor[1 + kCoarseLevels];
+    cap[0] = cs->cell_cap.as<int>();
+    cellid[0] = h->ws_cellid.as<int>();
+    cursor[0] = h->ws_cursor.as<unsigned>();
+    size_t off = (size_t)cs->total_cells;
+    for (int l = 0; l < kCoarseLevels; l++) {
+      cap[l + 1] = cs->c_cell_cap[l].as<int>();
+      cellid[l + 1] = h->ws_cellid.as<int>() + np * (l + 1);
+      cursor[l + 1] = h->ws_cursor.as<unsigned>() + off;
+      off += (size_t)cs->c_total_cells[l];
+    }
+    CK(launch_grid_build_fused(cs->view(), cap, cellid, cursor, h->stream, &h->stats));
+    cs->grid_built = true;
+    return APD_OK;
+  }
   CK(h->ws_bbox.reserve(sizeof(unsigned) * 6 * cs->n_clouds));
   CK(h->ws_cellid.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
   CK(h->ws_cursor.reserve(sizeof(unsigned) * (size_t)cs->total_cells));
@@ -443,14 +470,16 @@ struct TeamPlan {
 
 // Pick the launch shape for n_pairs pairs: one CTA per pair when the batch fills the GPU, clusters
 // (or the whole cooperative grid for very large sources) when few pairs must be made fast.
-int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tgt, int n_pairs, TeamPlan* plan) {
+// plan_for_pairs: the batch size the team shape is chosen for (a pipelined call plans once for the whole
+// batch so that every chunk sums in the same order and the records do not depend on the chunking)
+int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tgt, int n_pairs, int plan_for_pairs, TeamPlan* plan) {
   TeamPlan p;
   p.staged = tgt->staged;
   p.smem = p.staged ? tgt->staged_smem : 0;
   int size = h->team_size;
   if (size <= 0) {
     size = 1;
-    while (size < 8 && (long long)n_pairs * size * 2 <= h->sm_count) size *= 2;
+    while (size < 8 && (long long)std::max(n_pairs, plan_for_pairs) * size * 2 <= h->sm_count) size *= 2;
     // a CTA pass handles kAlignThreads points at a time: no point in more CTAs than that
     while (size > 1 && (long long)src->max_n < (long long)(size / 2) * kAlignThreads) size /= 2;
   }
@@ -498,6 +527,7 @@ struct AlignCall {
   int n_pairs = 0;
   int mode = 0;
   int min_points = 0;
+  int plan_for_pairs = 0;
   double max_range = DBL_MAX;
   bool want_trace = false;
   bool want_hessian = false;
@@ -514,7 +544,7 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   }
   const int np = c.n_pairs;
   TeamPlan plan;
-  rc = plan_teams(h, c.src, c.tgt, np, &plan);
+  rc = plan_teams(h, c.src, c.tgt, np, c.plan_for_pairs, &plan);
   if (rc) return rc;
   rc = ensure_align_scratch(h, plan.kind == TEAM_GRID ? 1 : plan.teams, std::max(c.src->max_n, 1));
   if (rc) return rc;
@@ -722,6 +752,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "force_unstaged") h->force_unstaged = value != 0;
   else if (n == "max_teams") h->max_teams_opt = (int)value;
   else if (n == "knn_packed") h->knn_packed = value != 0;
+  else if (n == "fused_build") h->no_fused_build = value == 0;
   else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
@@ -1164,6 +1195,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->force_unstaged = h->force_unstaged;
   x->max_teams_opt = h->max_teams_opt;
   x->knn_packed = h->knn_packed;
+  x->no_fused_build = h->no_fused_build;
   x->knn_fine_rings = h->knn_fine_rings;
   *out = x;
   return APD_OK;
@@ -1224,6 +1256,7 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
     }
     c.guesses = guesses ? guesses + (size_t)p0 * 16 : nullptr;
     c.n_pairs = np;
+    c.plan_for_pairs = n_pairs;
     c.min_points = h->prm.k_correspondences;
     rc = run_align(hc, c);
     if (rc) return hc == h ? rc : fail(h, rc, hc->err);

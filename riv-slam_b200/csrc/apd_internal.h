@@ -50,6 +50,38 @@ __device__ __forceinline__ GridView<unsigned> coarse_view(const CloudSetView& cs
   return G;
 }
 
+// Stage one cloud's fine grid in shared memory: sorted points (16 B each) and the cell table narrowed to
+// 16-bit entries. Loads are issued in independent batches (4 x 16 B per thread for the points, 8 x 16 B
+// for the table, whose per-cloud offset is a multiple of four entries) so the copy is bandwidth- rather
+// than latency-bound: on a single scan it is on the critical path of every CTA.
+__device__ __forceinline__ void stage_grid(float4* __restrict__ s_pts, uint16_t* __restrict__ s_cells, const float4* __restrict__ gp,
+                                           const unsigned* __restrict__ gc, int n, int ncells) {
+  const int T = blockDim.x, t = threadIdx.x;
+  for (int i = t; i < n; i += 4 * T) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i + u * T < n) v[u] = gp[i + u * T];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (i + u * T < n) s_pts[i + u * T] = v[u];
+  }
+  const int total = ncells + 1;
+  const int quads = total >> 2;
+  const uint4* gc4 = reinterpret_cast<const uint4*>(gc);
+  uint2* sc2 = reinterpret_cast<uint2*>(s_cells);
+  for (int i = t; i < quads; i += 8 * T) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (i + u * T < quads) v[u] = gc4[i + u * T];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (i + u * T < quads) sc2[i + u * T] = make_uint2(v[u].x | (v[u].y << 16), v[u].z | (v[u].w << 16));
+  }
+  for (int i = (quads << 2) + t; i < total; i += T) s_cells[i] = (uint16_t)gc[i];
+}
+
 // Exact unbounded (or gate-bounded) search through the pyramid: fine grid first, then coarser levels.
 // A TopK visitor must be reset between levels (the same points would be offered twice); a Top1
 // visitor keeps its key, which only tightens the bound. Returns the level that completed the search.
@@ -136,6 +168,9 @@ struct BuildWorkspace {
 // tiles: device int4 (cloud, first point, count, 0) covering every point of the set
 cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, const int4* tiles, int n_tiles, const int* cell_cap /*device [n_clouds]*/,
                               long long total_cells, bool finest_level, cudaStream_t stream, LaunchStats* st);
+// all pyramid levels of every cloud in ONE launch (clouds small enough for one CTA per cloud and level)
+cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap[1 + kCoarseLevels], int* const cellid[1 + kCoarseLevels],
+                                    unsigned* const cursor[1 + kCoarseLevels], cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,

@@ -59,8 +59,7 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   if (STAGED) {
     float4* s_pts = reinterpret_cast<float4*>(smem_raw);
     uint16_t* s_cells = reinterpret_cast<uint16_t*>(smem_raw + sizeof(float4) * (size_t)n);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_pts[i] = gspts[i];
-    for (int i = threadIdx.x; i <= g.ncells; i += blockDim.x) s_cells[i] = (uint16_t)gcells[i];
+    stage_grid(s_pts, s_cells, gspts, gcells, n, g.ncells);
     __syncthreads();
     G.spts = s_pts;
     G.cells = reinterpret_cast<const CellT*>(s_cells);

@@ -502,3 +502,16 @@ def test_information_matrix_fitness_score(small_pair):
     o2 = _oracle()
     o2.set_source(src[:700]); o2.set_target(tgt)
     assert abs(sc[0] - o.fitness_score(T_gt, 4.0)) <= REL_TOL * sc[0] and abs(sc[1] - o2.fitness_score(np.eye(4), 4.0)) <= REL_TOL * sc[1]
+
+
+def test_fused_and_multikernel_grid_builds_agree(pair5k):
+    """The one-launch build for small clouds and the multi-kernel pipeline must give identical registrations."""
+    from riv_slam_b200.fast_apdgicp import Handle, CloudSet, align_pairs
+    src, tgt, _ = pair5k
+    out = []
+    for fused in (1, 0):
+        H = Handle(0)
+        H.set_params(**TIGHT_PARAMS)
+        H.set_option("fused_build", fused)
+        out.append(align_pairs(H, CloudSet(H, [src, src[:3000]]), CloudSet(H, [tgt, tgt[:2500]])).tobytes())
+    assert out[0] == out[1]
