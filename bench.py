@@ -364,6 +364,12 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback"
     achieved = align_bytes / align_s / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one align launch at this shape, from the committed ncu capture
+    try:
+        if P == 1000:
+            traffic = int(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))["align_kernel"]["dram_bytes_per_launch"])
+    except Exception:
+        traffic = None
     prep_bytes = (P + 1) * N_POINTS * B_PREPARE
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -378,7 +384,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "align_kernel<TEAM_CTA,staged>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(align_bytes), "launch_ms": 1e3 * align_s,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(align_bytes), "launch_ms": 1e3 * align_s,
                      "linearize_passes": int(lin), "error_passes": int(err)},
         "phases_ms_per_step": {"upload_or_copy+grid+knn_cov": 1e3 * prep_m / args.steps, "align+fitness": 1e3 * align_m / args.steps,
                                "prepare_algorithmic_GBps": prep_bytes / (prep_m / args.steps) / 1e9},

@@ -169,6 +169,7 @@ int apd_synchronize(apd_handle h);
  *   "force_unstaged"   1 = never stage the target grid in shared memory
  *   "max_teams"        cap on concurrently processed pairs (0 = as many as fit)
  *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only
+ *   "fitness_max_range" max_range of the getFitnessScore the batched calls fill into apd_result.fitness (default DBL_MAX)
  *   "fused_build"      1 = small clouds are gridded by one launch for all levels (default), 0 = the multi-kernel pipeline
  *   "knn_fine_rings"   kNN: rings searched on one level of the grid pyramid before restarting on the next coarser one */
 int apd_set_option(apd_handle h, const char* name, double value);

@@ -164,6 +164,7 @@ struct apd_context {
   int max_teams_opt = 0;  // 0 = as many as fit
   int knn_packed = 1;
   int no_fused_build = 0;
+  double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
@@ -753,6 +754,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "max_teams") h->max_teams_opt = (int)value;
   else if (n == "knn_packed") h->knn_packed = value != 0;
   else if (n == "fused_build") h->no_fused_build = value == 0;
+  else if (n == "fitness_max_range") h->fitness_max_range = value;
   else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
@@ -1154,6 +1156,7 @@ int apd_align_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int3
   c.guesses = guesses;
   c.n_pairs = n_pairs;
   c.min_points = h->prm.k_correspondences;
+  c.max_range = h->fitness_max_range;
   int rc = run_align(h, c);
   if (rc) return rc;
   h->last_lin_valid = false;
@@ -1196,6 +1199,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->max_teams_opt = h->max_teams_opt;
   x->knn_packed = h->knn_packed;
   x->no_fused_build = h->no_fused_build;
+  x->fitness_max_range = h->fitness_max_range;
   x->knn_fine_rings = h->knn_fine_rings;
   *out = x;
   return APD_OK;
@@ -1257,6 +1261,7 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
     c.guesses = guesses ? guesses + (size_t)p0 * 16 : nullptr;
     c.n_pairs = np;
     c.plan_for_pairs = n_pairs;
+    c.max_range = h->fitness_max_range;
     c.min_points = h->prm.k_correspondences;
     rc = run_align(hc, c);
     if (rc) return hc == h ? rc : fail(h, rc, hc->err);

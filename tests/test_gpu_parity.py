@@ -515,3 +515,35 @@ def test_fused_and_multikernel_grid_builds_agree(pair5k):
         H.set_option("fused_build", fused)
         out.append(align_pairs(H, CloudSet(H, [src, src[:3000]]), CloudSet(H, [tgt, tgt[:2500]])).tobytes())
     assert out[0] == out[1]
+
+
+def test_batched_loop_candidate_matching():
+    """SURVEY §8(f)-3: LoopDetector::matching (loop_detector.cpp:379-441) over all candidates in one launch."""
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import Handle
+    from riv_slam_b200.loop_matching import matching, relative_guess
+    scans, poses = datagen.make_sequence(4, 5, n_scans=7, n_points=1500)
+    new_kf, new_pose = scans[3], poses[3]
+    cands = [scans[i] for i in (0, 1, 2, 4, 5, 6)]
+    cand_poses = [poses[i] for i in (0, 1, 2, 4, 5, 6)]
+    guesses = np.stack([relative_guess(new_pose, p) for p in cand_poses])
+    H = Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+    best, rel, score, res = matching(H, cands, new_kf, guesses, fitness_score_max_range=4.0, fitness_score_thresh=6.0)
+    # the reference's sequential loop on the CPU oracle
+    best0, score0, rel0 = None, np.finfo(np.float64).max, None
+    for i, c in enumerate(cands):
+        o = _oracle(LAUNCH_PARAMS)
+        o.set_target(new_kf); o.set_source(c)
+        rc, T0, conv0, it0 = o.align(guesses[i])
+        s0 = o.fitness(4.0)
+        assert bool(res[i]["converged"]) == conv0 and res[i]["iterations"] == it0
+        assert abs(res[i]["fitness"] - s0) <= REL_TOL * s0
+        if not conv0 or s0 > score0:
+            continue
+        best0, score0, rel0 = i, s0, T0
+    assert best == best0 and abs(score - score0) <= REL_TOL * score0
+    _assert_same_transform(rel, rel0)
+    # a threshold below the best score rejects the loop
+    assert matching(H, cands, new_kf, guesses, 4.0, fitness_score_thresh=score0 * 0.5)[0] is None
+    assert matching(H, [], new_kf)[0] is None
