@@ -267,24 +267,25 @@ def _drive_poses(n_scans: int, speed: float, rng: np.random.Generator):
 
 
 def _drive_scan(args):
-    config, seq_index, t, n_scans, n_points, speed, voxel = args
+    config, seq_index, t, n_scans, n_points, speed, voxel, resample = args
     rng0 = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
     length = speed * n_scans * 1.15 + 140.0
     scene = make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False, clear_lane=(-1.0, 3.0))
     poses = _drive_poses(n_scans, speed, rng0)
-    rng = np.random.Generator(np.random.PCG64([pair_seed(config, seq_index), t + 1]))
+    rng = np.random.Generator(np.random.PCG64([pair_seed(config, seq_index), t + 1 + 1000003 * resample]))
     return scan(scene, poses[t], n_points, rng, voxel=voxel)
 
 
 def make_drive(config: int, seq_index: int, n_scans: int, n_points: int = 5000, speed: float = 0.5,
-               voxel: float | None = 0.1, workers: int = 0):
+               voxel: float | None = 0.1, workers: int = 0, resample: int = 0):
     """Like :func:`make_sequence` but scan t draws from its own stream PCG64([seed, t+1]), so the scans
     can be generated by a process pool. Returns (scans, poses)."""
     rng0 = np.random.Generator(np.random.PCG64(pair_seed(config, seq_index)))
     length = speed * n_scans * 1.15 + 140.0
     make_scene(rng0, x_min=-20.0, x_max=length, far_wall=False, clear_lane=(-1.0, 3.0))  # advance the stream exactly as the workers do
     poses = _drive_poses(n_scans, speed, rng0)
-    jobs = [(config, seq_index, t, n_scans, n_points, speed, voxel) for t in range(n_scans)]
+    # resample > 0 re-draws every scan (same scene, same poses, independent rays and noise)
+    jobs = [(config, seq_index, t, n_scans, n_points, speed, voxel, resample) for t in range(n_scans)]
     if workers and workers > 1 and n_scans > 1:
         import multiprocessing as mp
         with mp.get_context("fork").Pool(min(workers, n_scans)) as pool:
@@ -292,3 +293,29 @@ def make_drive(config: int, seq_index: int, n_scans: int, n_points: int = 5000, 
     else:
         scans = [_drive_scan(j) for j in jobs]
     return scans, poses
+
+
+def voxel_keep_one(points: np.ndarray, voxel: float) -> np.ndarray:
+    """Keep the first point of every voxel (the generator's stand-in for the 0.1 m down-sampling of launch:56-57)."""
+    kv = np.floor(points[:, :3].astype(np.float64) / voxel).astype(np.int64) + (1 << 20)
+    keys = (kv[:, 0] << 42) | (kv[:, 1] << 21) | kv[:, 2]
+    _, first = np.unique(keys, return_index=True)
+    return points[np.sort(first)]
+
+
+def make_map(config: int, seq_index: int, n_scans: int, n_points: int = 5000, frame: int = 0, first: int = 0, stride: int = 1,
+             voxel: float = 0.1, workers: int = 0, speed: float = 0.5, total_scans: int | None = None, resample: int = 0):
+    """An accumulated, voxel-filtered map: scans first, first+stride, ... of a drive moved into the frame of
+    pose `frame` and de-duplicated per voxel — the kind of cloud a keyframe map holds (bounded density,
+    unlike a raw million-point scan). Returns (cloud float32 (m,4), pose of `frame`)."""
+    total = total_scans or (first + stride * n_scans + 1)
+    scans, poses = make_drive(config, seq_index, total, n_points, speed=speed, workers=workers, resample=resample)
+    inv = np.linalg.inv(poses[frame])
+    parts = []
+    for j in range(n_scans):
+        t = first + stride * j
+        Trel = inv @ poses[t]
+        p = scans[t].copy()
+        p[:, :3] = (scans[t][:, :3].astype(np.float64) @ Trel[:3, :3].T + Trel[:3, 3]).astype(np.float32)
+        parts.append(p)
+    return voxel_keep_one(np.concatenate(parts), voxel), poses[frame]

@@ -144,8 +144,16 @@ def c4():
 
 
 def c5():
-    """200k-point source vs 1M-point target (scene scaled x4, no voxel filter), k in {10, 15, 20}."""
-    src, tgt, T_gt = datagen.make_pair(5, 0, n_src=200000, n_tgt=1000000, scale=4.0, voxel=None)
+    """200k-point source vs 1M-point target, k in {10, 15, 20}. Both are accumulated keyframe maps of one
+    drive (330 resp. 80 scans of 5000 points moved into one frame, 0.1 m voxel de-duplication as in the
+    reference pipeline, launch:56-57), independently sampled, 0.8 m / 1 deg apart."""
+    w = min(16, os.cpu_count() or 1)
+    tgt, pose_t = datagen.make_map(5, 0, 330, 5000, frame=150, workers=w, total_scans=340, speed=1.0)
+    src, pose_s = datagen.make_map(5, 0, 80, 5000, frame=151, first=112, workers=w, total_scans=340, speed=1.0, resample=1)
+    rng = np.random.default_rng(5)
+    tgt = tgt[np.sort(rng.choice(tgt.shape[0], min(1000000, tgt.shape[0]), replace=False))]
+    src = src[np.sort(rng.choice(src.shape[0], min(200000, src.shape[0]), replace=False))]
+    T_gt = np.linalg.inv(pose_t) @ pose_s
     for k in (10, 15, 20):
         reg = F.FastAPDGICP(0)
         reg.handle().set_params(**dict(LAUNCH_PARAMS, k_correspondences=k))
