@@ -85,7 +85,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -287,7 +287,6 @@ def main():
     tot, prep, align, wall = timed(dev_pts, F.MEM_DEVICE, False, args.steps)
     t1 = time.perf_counter()
     launches = H.launch_count() - launches0
-    clocks = sampler.stop(t0, t1) if sampler else None
     lin, err, _ = H.work_counters()   # of the last step (all steps do identical work)
 
     # ---- end to end: pinned host PointXYZI buffers in, host results out, through the public call a user makes ----
@@ -314,8 +313,10 @@ def main():
         barrier()
         return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0
 
-    e2e_timed(1)
+    e2e_timed(max(args.warmup, 1))
     e_tot, e_wall = e2e_timed(args.steps)
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None   # samples cover both timed regions (device-resident and end to end)
     e_tot = max(e_tot, e_wall)    # the helper stream's work is not on `stream`: the host clock bounds the region
     results = res_view.copy()
 
