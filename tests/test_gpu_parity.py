@@ -547,3 +547,50 @@ def test_batched_loop_candidate_matching():
     # a threshold below the best score rejects the loop
     assert matching(H, cands, new_kf, guesses, 4.0, fitness_score_thresh=score0 * 0.5)[0] is None
     assert matching(H, [], new_kf)[0] is None
+
+
+def _degenerate_clouds():
+    rng = np.random.default_rng(11)
+    n = 400
+    yield "planar_z0", np.c_[rng.uniform(-20, 20, (n, 2)), np.zeros(n)].astype(np.float32)
+    yield "collinear", np.c_[np.linspace(0, 50, n), np.full(n, 3.0), np.full(n, -1.0)].astype(np.float32)
+    yield "all_identical", np.tile(np.array([[1.5, -2.0, 0.25]], np.float32), (n, 1))
+    yield "duplicates", np.repeat(rng.uniform(-5, 5, (n // 4, 3)).astype(np.float32), 4, axis=0)
+    yield "huge_coordinates", (rng.uniform(-1, 1, (n, 3)) + np.array([4.0e5, -3.0e5, 1.0e5])).astype(np.float32)
+    yield "tiny_extent", (rng.uniform(0, 1e-4, (n, 3)) + 7.0).astype(np.float32)
+    yield "two_far_clusters", np.r_[rng.normal(0, 0.2, (n // 2, 3)), rng.normal(0, 0.2, (n // 2, 3)) + 900.0].astype(np.float32)
+    yield "exactly_k_points", rng.uniform(-3, 3, (20, 3)).astype(np.float32)
+    yield "k_plus_one", rng.uniform(-3, 3, (21, 3)).astype(np.float32)
+    yield "one_outlier", np.r_[rng.uniform(-2, 2, (n - 1, 3)), [[5000.0, 5000.0, 5000.0]]].astype(np.float32)
+
+
+@pytest.mark.parametrize("unstaged", [0, 1])
+def test_knn_exact_on_degenerate_clouds(unstaged):
+    """Index sets stay bit-exact where a grid is at its worst: flat, collinear, duplicated, far-apart, tiny."""
+    from oracle.oracle import knn_bruteforce
+    for name, cloud in _degenerate_clouds():
+        for cpp in (4.0, 0.05, 200.0):
+            g = _gpu(k_correspondences=20)
+            g.setOption("cells_per_point", cpp)
+            g.setOption("force_unstaged", unstaged)
+            g.setInputSource(cloud)
+            ref, _ = knn_bruteforce(cloud, cloud, 20)
+            got = g.getKnn(0)
+            assert np.array_equal(got, ref), (name, cpp, unstaged, int((got != ref).any(axis=1).sum()))
+    # and a 1-NN / gate check against the same clouds as targets
+    rng = np.random.default_rng(3)
+    for name, cloud in _degenerate_clouds():
+        q = (cloud[rng.integers(0, len(cloud), 300)] + rng.normal(0, 0.3, (300, 3))).astype(np.float32)
+        g = _gpu(LAUNCH_PARAMS)
+        g.setOption("force_unstaged", unstaged)
+        g.setInputSource(q); g.setInputTarget(cloud)
+        o = _oracle(LAUNCH_PARAMS)
+        o.set_source(q); o.set_target(cloud)
+        if len(cloud) < 20 or len(q) < 20:
+            continue
+        g.evaluateCost(np.eye(4))
+        o.linearize(np.eye(4))
+        corr, sq = g.getCorrespondences()
+        corr0, sq0 = o.correspondences()
+        assert np.array_equal(corr, corr0), name
+        assert np.array_equal(sq[corr0 >= 0], sq0[corr0 >= 0]), name
