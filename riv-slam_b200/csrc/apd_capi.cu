@@ -480,7 +480,7 @@ int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tg
   int size = h->team_size;
   if (size <= 0) {
     size = 1;
-    while (size < 8 && (long long)std::max(n_pairs, plan_for_pairs) * size * 2 <= h->sm_count) size *= 2;
+    while (size < 16 && (long long)std::max(n_pairs, plan_for_pairs) * size * 2 <= h->sm_count) size *= 2;  // 16 = the non-portable cluster maximum
     // a CTA pass handles kAlignThreads points at a time: no point in more CTAs than that
     while (size > 1 && (long long)src->max_n < (long long)(size / 2) * kAlignThreads) size /= 2;
   }

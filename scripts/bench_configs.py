@@ -52,6 +52,36 @@ def oracle(**kw):
     return Oracle(**p)
 
 
+def c1():
+    """Single align of two ~3k-point clouds: the reference-path config (CPU/OpenMP), with the GPU beside it."""
+    src, tgt, T_gt = datagen.make_pair(1, 0, n_src=3000)
+    from oracle.oracle import max_threads
+    rows = {}
+    for name, prm in (("launch", LAUNCH_PARAMS), ("tight", dict(LAUNCH_PARAMS, transformation_epsilon=1e-6, rotation_epsilon=1e-6))):
+        o = oracle(**{k: v for k, v in prm.items() if k not in LAUNCH_PARAMS or prm[k] != LAUNCH_PARAMS[k]})
+        cpu = []
+        for _ in range(7):
+            sec, Tc, conv, it, fit = o.timed_registration(src, tgt)
+            cpu.append(sec)
+        o1 = oracle(num_threads=1, **{k: v for k, v in prm.items() if k not in LAUNCH_PARAMS or prm[k] != LAUNCH_PARAMS[k]})
+        sec1 = min(o1.timed_registration(src, tgt)[0] for _ in range(3))
+        reg = F.FastAPDGICP(0)
+        reg.handle().set_params(**prm)
+        gpu = []
+        for i in range(12):
+            t0 = time.perf_counter()
+            reg.setInputTarget(tgt, cache_key=2 * i + 1)
+            reg.setInputSource(src, cache_key=2 * i + 2)
+            reg.align(None, want_output=False)
+            reg.getFitnessScore()
+            gpu.append(time.perf_counter() - t0)
+        Tg = reg.getFinalTransformation()
+        rows[name] = dict(cpu_ms_all_cores=float(np.median(cpu[2:]) * 1e3), cpu_ms_1_thread=sec1 * 1e3, cpu_cores=max_threads(), gpu_ms=float(np.median(gpu[3:]) * 1e3),
+                          iterations=it, converged=bool(conv), gpu_iterations=reg.nr_iterations(), T_abs_err_vs_oracle=float(np.abs(Tc - Tg).max()),
+                          fitness=fit, gpu_fitness=reg.getFitnessScore())
+    emit(config="C1 single align, N = M = 3000, cold (both clouds new: upload + grid + kNN + covariances + align + fitness)", **{f"{k}_{kk}": vv for k, r in rows.items() for kk, vv in r.items()})
+
+
 def c3():
     """5k-point scans against a ~100k-point accumulated submap, target prepared once and reused."""
     n_scans, per = 24, 5000
@@ -220,6 +250,6 @@ def fit():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c3", "c4", "fit", "c5"]
+    which = sys.argv[1:] or ["c1", "c3", "c4", "fit", "c5"]
     for w in which:
-        {"c3": c3, "c4": c4, "c5": c5, "fit": fit}[w]()
+        {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fit": fit}[w]()

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): single pair in every
+team shape, a ragged batch, the pipelined host call and the fitness entry points."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from riv_slam_b200 import datagen
+from riv_slam_b200 import fast_apdgicp as F
+from bench import LAUNCH_PARAMS
+
+src, tgt, _ = datagen.make_pair(1, 3, n_src=700, n_tgt=800)
+for team in (0, 1, 2, 4):
+    for unstaged in (0, 1):
+        r = F.FastAPDGICP(0)
+        r.handle().set_params(**LAUNCH_PARAMS)
+        r.setOption("team_size", team)
+        r.setOption("force_unstaged", unstaged)
+        r.setInputTarget(tgt); r.setInputSource(src)
+        r.align(want_output=True)
+        r.getFitnessScore(1.0); r.getKnn(0); r.getCorrespondences(); r.evaluateCost(np.eye(4))
+        print("team", team, "unstaged", unstaged, r.hasConverged(), r.nr_iterations())
+H = F.Handle(0)
+H.set_params(**LAUNCH_PARAMS)
+clouds = [src[:300], src, tgt[:500], src[:0], tgt]
+res = F.batch_align(H, clouds, [tgt, tgt[:600], src, tgt, src[:5]])
+print(res["status"], res["converged"])
+print(F.odometry_align(H, [src, tgt, src[:400], tgt[:350]])["iterations"])
+S = F.CloudSet(H, clouds[:3])
+print(F.fitness_pairs(H, S, S, src_idx=[0, 1], tgt_idx=[2, 2], max_range=4.0))
+print("done")
