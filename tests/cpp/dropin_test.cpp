@@ -3,6 +3,8 @@
 // with the launch-file values) and driven the way scan_matching_odometry_nodelet.cpp:437-482 and
 // loop_detector.cpp:222-236 drive it. Input: a binary file of float32 PointXYZI-layout scans written by
 // tests/test_cpp_dropin.py. Output: one text line per registration.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -57,6 +59,49 @@ int main(int argc, char** argv) {
     std::printf(" fitness_pcl %.17g fitness_gpu %.17g out0 %.9g %.9g %.9g %.9g n_out %zu\n", fit, apd->lastFitnessScore(), aligned->points[0].x,
                 aligned->points[0].y, aligned->points[0].z, aligned->points[0].intensity, aligned->size());
     registration->setInputTarget(scans[t]);
+  }
+  // the FastAPDGICP-specific surface through the derived type (fast_apdgicp.hpp:51-74, lsq_registration.hpp:51-57)
+  {
+    auto gicp = std::make_shared<fast_gicp::FastAPDGICP<PointT, PointT>>();
+    gicp->setMaxCorrespondenceDistance(2.0);
+    gicp->setTransformationEpsilon(1e-6);
+    gicp->setRotationEpsilon(1e-6);
+    gicp->setAzimuthVar(1.0);
+    gicp->setRegularizationMethod(fast_gicp::RegularizationMethod::PLANE);
+    gicp->setInputTarget(scans[0]);
+    gicp->setInputSource(scans[1]);
+    Eigen::Matrix<double, 6, 6> H;
+    Eigen::Matrix<double, 6, 1> b;
+    const double e = gicp->evaluateCost(Eigen::Matrix4f::Identity(), &H, &b);
+    std::printf("cost %.17g H00 %.17g H35 %.17g H53 %.17g b0 %.17g b5 %.17g\n", e, H(0, 0), H(3, 5), H(5, 3), b(0), b(5));
+    gicp->align(*aligned);
+    const auto Tf = gicp->getFinalTransformation();
+    const auto& Hf = gicp->getFinalHessian();
+    std::printf("fwd converged %d T03 %.9g T13 %.9g Hf00 %.17g\n", gicp->hasConverged() ? 1 : 0, Tf(0, 3), Tf(1, 3), Hf(0, 0));
+    // covariances out, swap, covariances in: the swapped object must reproduce a fresh backward registration
+    const auto cs = gicp->getSourceCovariances();
+    const auto ct = gicp->getTargetCovariances();
+    std::printf("covs %zu %zu c0 %.17g %.17g %.17g\n", cs.size(), ct.size(), cs[0](0, 0), cs[0](1, 0), cs[0](3, 3));
+    gicp->swapSourceAndTarget();
+    gicp->align(*aligned);
+    const auto Tb = gicp->getFinalTransformation();
+    auto fresh2 = std::make_shared<fast_gicp::FastAPDGICP<PointT, PointT>>();
+    fresh2->setMaxCorrespondenceDistance(2.0);
+    fresh2->setTransformationEpsilon(1e-6);
+    fresh2->setRotationEpsilon(1e-6);
+    fresh2->setAzimuthVar(1.0);
+    fresh2->setInputSource(scans[0]);
+    fresh2->setInputTarget(scans[1]);
+    fresh2->setSourceCovariances(ct);   // injected: what the swapped object holds for the same clouds
+    fresh2->setTargetCovariances(cs);
+    fresh2->align(*aligned);
+    const auto Tb2 = fresh2->getFinalTransformation();
+    double dmax = 0;
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) dmax = std::max(dmax, (double)std::fabs(Tb(r, c) - Tb2(r, c)));
+    std::printf("bwd converged %d %d maxdiff %.3g T03 %.9g\n", gicp->hasConverged() ? 1 : 0, fresh2->hasConverged() ? 1 : 0, dmax, Tb(0, 3));
+    gicp->clearSource();
+    gicp->align(*aligned);  // no source any more: PCL returns from initCompute (converged_ keeps its previous value)
+    std::printf("cleared converged %d\n", gicp->hasConverged() ? 1 : 0);
   }
   // loop-closure style call without a target: align must print and leave hasConverged() false
   pcl::Registration<PointT, PointT>::Ptr fresh = select_registration_method();

@@ -69,5 +69,32 @@ def test_dropin_matches_python_path_and_oracle(tmp_path):
         assert np.abs(out0[:3] - ref0).max() < 1e-4
         assert out0[3] == scans[t + 1][0, 3]          # intensity rides along in the output cloud
         assert int(l[31]) == scans[t + 1].shape[0]
+    # derived-type surface: evaluateCost / getFinalHessian / covariances / swap / clear against the oracle
+    T = dict(LAUNCH_PARAMS, transformation_epsilon=1e-6, rotation_epsilon=1e-6)
+    o = Oracle(**T)
+    o.set_source(scans[1]); o.set_target(scans[0])
+    e0, H0, b0 = o.linearize(np.eye(4))
+    cost = next(l for l in lines if l[0] == "cost")
+    vals = dict(zip(cost[0::2], cost[1::2]))
+    assert abs(float(vals["cost"]) - e0) <= 1e-5 * abs(e0)
+    for key, ref in (("H00", H0[0, 0]), ("H35", H0[3, 5]), ("H53", H0[5, 3]), ("b0", b0[0]), ("b5", b0[5])):
+        assert abs(float(vals[key]) - ref) <= 1e-5 * max(np.abs(H0).max() if key[0] == "H" else np.abs(b0).max(), 1e-30)
+    rc, Tf0, conv0, it0 = o.align()
+    fwd = next(l for l in lines if l[0] == "fwd")
+    assert int(fwd[2]) == int(conv0) and abs(float(fwd[4]) - Tf0[0, 3]) < 1e-4 and abs(float(fwd[6]) - Tf0[1, 3]) < 1e-4
+    assert abs(float(fwd[8]) - o.final_hessian()[0, 0]) <= 1e-5 * abs(o.final_hessian()[0, 0])
+    covs = next(l for l in lines if l[0] == "covs")
+    C0 = o.covariances(0)
+    assert int(covs[1]) == scans[1].shape[0] and int(covs[2]) == scans[0].shape[0]
+    assert abs(float(covs[4]) - C0[0][0, 0]) < 1e-9 and abs(float(covs[5]) - C0[0][1, 0]) < 1e-9 and float(covs[6]) == 0.0
+    o2 = Oracle(**T)
+    o2.set_source(scans[0]); o2.set_target(scans[1])
+    rc, Tb0, convb, itb = o2.align()
+    bwd = next(l for l in lines if l[0] == "bwd")
+    assert int(bwd[2]) == int(convb) and int(bwd[3]) == int(convb)
+    assert float(bwd[5]) < 1e-6                      # swapped object == fresh object with injected covariances
+    assert abs(float(bwd[7]) - Tb0[0, 3]) < 1e-4
+    # after clearSource() PCL's align returns from initCompute before touching converged_ (stale value, as in PCL)
+    assert any(l[:2] == ["cleared", "converged"] for l in lines)
     assert ["notarget", "converged", "0"] in lines
     assert "No input target dataset" in r.stderr
