@@ -200,13 +200,30 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const A
     // from the new query bounds the nearest neighbour, so one pass over the rows of that ball is
     // exact (grid_ball_search); a point that had none searches the ball of the gate radius.
     const int prev = seeded ? B.scratch.corr[sbase + i] : -2;
+    bool full_ring = false;
+    float unexplored = 0.f;
     if (prev >= 0) {
       const float4 t = T.G.spts[prev];
       grid_ball_search(T.G, qx, qy, qz, fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2), v);
     } else if (prev == -1 && B.prm.corr_limit2 < 3.0e38f) {
+      // A point that had no correspondence keeps an ANCHOR: where it was searched and how far every
+      // target point is from there at least. If it has moved by less than the slack between that
+      // bound and the gate, nothing can have come inside the gate: no search at all (clutter and
+      // non-overlapping regions, a quarter of a radar scan, otherwise pay the widest search every iteration).
+      const float4 an = B.scratch.anchor[sbase + i];
+      const float moved = sqrtf(sqdist_rn(qx, qy, qz, an.x, an.y, an.z));
+      if (an.w * 0.99999f - moved * 1.00001f - 1e-3f > sqrtf(B.prm.corr_limit2) * 1.00001f) {
+        B.scratch.sqd[sbase + i] = __int_as_float(0x7f800000);
+        continue;  // corr stays -1, the anchor stays valid
+      }
       grid_ball_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);
+      unexplored = sqrtf(B.prm.corr_limit2);  // everything inside the gate radius was visited
+      full_ring = true;
     } else if (B.prm.corr_limit2 < 3.0e38f) {
-      grid_search(T.G, qx, qy, qz, B.prm.corr_limit2, v);  // the gate bounds the number of rings
+      // searched a little beyond the gate so that a point without correspondence learns how far the target
+      // really is (its anchor); the gate itself is applied below
+      grid_search(T.G, qx, qy, qz, B.prm.corr_wide2, v, 0x7fffffff, &unexplored);
+      full_ring = true;
     } else {
       // no gate (constructor default FLT_MAX): unbounded search through the pyramid; a hit on a coarse
       // level is mapped back to its position in the fine order
@@ -217,7 +234,13 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const A
     const bool ok = v.pos >= 0 && (double)d2 < B.prm.corr_thr2;
     B.scratch.corr[sbase + i] = ok ? v.pos : -1;
     B.scratch.sqd[sbase + i] = d2;
-    if (!ok) continue;
+    if (!ok) {
+      // anchor: every target point is at least min(nearest visited, distance to the unexplored region) away;
+      // after a seeded ball search that lost its correspondence nothing is known (bound 0: always search)
+      const float lb = full_ring ? fminf(v.pos >= 0 ? sqrtf(d2) : FLT_MAX, unexplored) : 0.f;
+      B.scratch.anchor[sbase + i] = make_float4(qx, qy, qz, lb);
+      continue;
+    }
     const double2 a0 = c0[i], a1 = c1[i], a2 = c2[i];
     const double2 b0 = T.cov0[v.pos], b1 = T.cov1[v.pos], b2 = T.cov2[v.pos];
     const Sym3 Cd = apd_cov(qx, qy, qz, B.prm);

@@ -167,7 +167,7 @@ struct apd_context {
   double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
-  DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
+  DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
       counters, grid_partials, misc, knn_tmp, cov_tmp;
   int scratch_slots = 0, scratch_max_src = 0;
   // last single-pair alignment
@@ -222,6 +222,7 @@ DeviceParams device_params(const apd_params& p) {
   if (!(d.corr_thr2 < 3.0e38)) f = INFINITY;
   else if ((double)f < d.corr_thr2) f = std::nextafterf(f, INFINITY);
   d.corr_limit2 = f;
+  d.corr_wide2 = f < 3.0e38f ? f * 1.96f : f;
   d.rotation_epsilon = p.rotation_epsilon;
   d.transformation_epsilon = p.transformation_epsilon;
   d.lm_init_lambda_factor = p.lm_init_lambda_factor;
@@ -458,6 +459,7 @@ int ensure_align_scratch(apd_handle h, int slots, int max_src) {
   CK(h->sc_m0.reserve(sizeof(double2) * n));
   CK(h->sc_m1.reserve(sizeof(double2) * n));
   CK(h->sc_m2.reserve(sizeof(double2) * n));
+  CK(h->sc_anchor.reserve(sizeof(float4) * n));
   h->scratch_slots = slots;
   h->scratch_max_src = max_src;
   return APD_OK;
@@ -600,6 +602,7 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   b.scratch.m0 = h->sc_m0.as<double2>();
   b.scratch.m1 = h->sc_m1.as<double2>();
   b.scratch.m2 = h->sc_m2.as<double2>();
+  b.scratch.anchor = h->sc_anchor.as<float4>();
   b.prm = device_params(h->prm);
   b.mode = c.mode;
   b.min_points = c.min_points;

@@ -196,7 +196,13 @@ APD_HD void visit_run(const GridView<CellT>& G, int c0, int c1, float qx, float 
 // caller restarts on a coarser level of the grid pyramid (a sparse neighbourhood would otherwise walk
 // (2r+1)^2 mostly empty rows per ring).
 template <typename CellT, typename Visitor>
-APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, float limit2, Visitor& vis, int max_ring = 0x7fffffff) {
+APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, float limit2, Visitor& vis, int max_ring = 0x7fffffff,
+                        float* unexplored = nullptr) {
+  // *unexplored: on a complete search, a lower bound of the distance from the query to every point that
+  // was NOT offered to the visitor: points beyond the explored cube and points of rows that were skipped
+  // (+inf when every point was offered)
+  if (unexplored) *unexplored = 0.f;
+  float skipped2 = FLT_MAX;  // smallest lower bound (squared) among the skipped rows
   const GridParams& g = G.g;
   const int cx = cell_coord(qx, g.lox, g.inv_h, g.nx);
   const int cy = cell_coord(qy, g.loy, g.inv_h, g.ny);
@@ -223,7 +229,11 @@ APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, 
         // rounding of this bound itself; the bound is re-read per row so it tightens inside a ring.
         // (Trimming the row to the chord of the bounding ball was measured in round 1: the extra sqrt and
         // two cell lookups per row cost more than the candidates they save.)
-        if ((dz * dz + dy * dy) * 0.99999f > fminf(vis.bound2(), limit2)) continue;
+        const float row_lb2 = (dz * dz + dy * dy) * 0.99999f;
+        if (row_lb2 > fminf(vis.bound2(), limit2)) {
+          skipped2 = fminf(skipped2, row_lb2);
+          continue;
+        }
         const bool face = zface || (y == cy - r) || (y == cy + r);
         const int rowbase = (z * g.ny + y) * g.nx;
         if (face) {
@@ -246,14 +256,21 @@ APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, 
     if (cy + r < g.ny - 1) reach = fminf(reach, (g.loy + (float)(cy + r + 1) * g.h) - qy);
     if (cz - r > 0) reach = fminf(reach, qz - (g.loz + (float)(cz - r) * g.h));
     if (cz + r < g.nz - 1) reach = fminf(reach, (g.loz + (float)(cz + r + 1) * g.h) - qz);
-    if (reach == FLT_MAX) return true;  // the cube covers the whole grid
+    if (reach == FLT_MAX) {  // the cube covers the whole grid
+      if (unexplored) *unexplored = sqrtf(skipped2) * 0.999995f;
+      return true;
+    }
     reach = reach - g.slack;
     if (reach > 0.f) {
       const float reach2 = reach * reach * 0.99999f;
-      if (reach2 > fminf(vis.bound2(), limit2)) return true;
+      if (reach2 > fminf(vis.bound2(), limit2)) {
+        if (unexplored) *unexplored = fminf(reach, sqrtf(skipped2)) * 0.999995f;
+        return true;
+      }
     }
     if (r >= max_ring) return false;
   }
+  if (unexplored) *unexplored = sqrtf(skipped2) * 0.999995f;
   return true;
 }
 

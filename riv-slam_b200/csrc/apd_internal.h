@@ -106,6 +106,7 @@ struct DeviceParams {
   int optimizer;
   int lm_max_iterations;
   float corr_limit2;        // float upper bound of max_corr_dist^2 for search pruning
+  float corr_wide2;         // (1.4 * max_corr_dist)^2: radius of the first, anchoring search (see apd_align.cu)
   double corr_thr2;         // max_corr_dist^2 (double product, fast_apdgicp_impl.hpp:156)
   double rotation_epsilon;
   double transformation_epsilon;
@@ -125,6 +126,7 @@ struct AlignScratch {
   double2* m0;        // Mahalanobis (xx, xy)
   double2* m1;        //             (xz, yy)
   double2* m2;        //             (yz, zz)
+  float4* anchor;     // unmatched points: (query position, lower bound of the distance to ANY target point) of their last full search
 };
 
 enum TeamKind { TEAM_CTA = 0, TEAM_CLUSTER = 1, TEAM_GRID = 2 };
