@@ -179,6 +179,34 @@ int apd_set_option(apd_handle h, const char* name, double value);
 int apd_fitness_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int32_t* src_idx, const int32_t* tgt_idx, const float* poses,
                       int n_pairs, double max_range, double* scores);
 
+/* ---- "next" rows SURVEY.md §8(f)-4 and §8(f)-2: the filters in front of the scan matcher and the submap behind it ----
+ * Parameters of PreprocessingNodelet (radar_graph_slam/apps/preprocessing_nodelet.cpp:137-205; apd_default_preprocess_params gives
+ * the code defaults, the launch file overrides several: radar_graph_slam/launch/radar_graph_slam.launch:50-63). */
+typedef struct apd_preprocess_params {
+  int32_t use_distance_filter;      /* preprocessing_nodelet.cpp:201 (true)                                   */
+  int32_t outlier_removal;          /* 0 = NONE, 1 = RADIUS (pcl::RadiusOutlierRemoval); STATISTICAL is not implemented */
+  int32_t radius_min_neighbors;     /* :178 (2)                                                                */
+  int32_t reserved;
+  double distance_near_thresh;      /* :202 (1.0)   */
+  double distance_far_thresh;       /* :203 (100.0) */
+  double z_low_thresh;              /* :204 (-5.0)  */
+  double z_high_thresh;             /* :205 (20.0)  */
+  double downsample_resolution;     /* :138 (0.1); <= 0 = downsample_method NONE; otherwise pcl::VoxelGrid with this leaf */
+  double radius_radius;             /* :177 (0.8)   */
+} apd_preprocess_params;
+int apd_default_preprocess_params(apd_preprocess_params* p);
+/* distance_filter -> downsample -> outlier_removal (preprocessing_nodelet.cpp:812-815) of one cloud on the GPU.
+ * Points are read as x,y,z at the start of every stride_bytes record and the intensity at intensity_offset_bytes inside it
+ * (pcl::PointXYZI: stride 32, intensity offset 16; packed xyzi: stride 16, offset 12); the output uses the same record layout.
+ * out must hold n records; *n_out receives the number of points kept. */
+int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int intensity_offset_bytes, int n, const apd_preprocess_params* p, float* out, int* n_out);
+/* Submap accumulation (radar_graph_slam/apps/scan_matching_odometry_nodelet.cpp:606-616): clouds which[0..n_sel) of a cloud set, each moved by
+ * its rel_pose (row-major double[16], pcl::transformPointCloud in double), concatenated, then pcl::VoxelGrid if downsample_resolution > 0.
+ * The result becomes the handle's TARGET without leaving the device (setInputTarget(keyframe_cloud_s2m), :615); out_xyzi (host, packed
+ * x y z intensity, capacity out_capacity points, may be NULL) receives a copy. The 4th float of the set's points is taken as intensity. */
+int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which, int n_sel, const double* rel_poses, double downsample_resolution,
+                     uint64_t cache_key, float* out_xyzi, int out_capacity, int* n_out);
+
 /* Scan-to-scan odometry over one host array of n_scans scans (config C2; the call pattern of
  * radar_graph_slam/apps/scan_matching_odometry_nodelet.cpp:449-468,584-592 replayed over a recorded drive): pair i registers scan
  * i+1 onto scan i, every scan is uploaded, gridded and given covariances once, out receives n_scans-1 records. guesses: (n_scans-1)*16

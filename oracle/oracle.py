@@ -84,6 +84,10 @@ def lib():
         L.oracle_timed_registration.argtypes = [C.c_void_p, fp, C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, fp, ip, ip, dp]
         L.oracle_timed_registration.restype = C.c_double
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_distance_filter.argtypes = [fp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, fp]
+        L.oracle_voxel_grid.argtypes = [fp, C.c_int, C.c_float, fp]
+        L.oracle_radius_outlier_removal.argtypes = [fp, C.c_int, C.c_double, C.c_int, fp]
+        L.oracle_accumulate_submap.argtypes = [fp, ip, C.c_int, dp, C.c_float, fp]
         _lib = L
     return _lib
 
@@ -243,3 +247,42 @@ def knn_kdtree(cloud, queries, k):
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+# ---- preprocessing filters and submap accumulation (oracle/preprocess_oracle.hpp); clouds are (n, 4) x y z intensity ----
+
+def _xyzi(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4
+    return a
+
+
+def distance_filter(cloud, near_thresh, far_thresh, z_low, z_high):
+    a = _xyzi(cloud)
+    out = np.zeros_like(a)
+    n = lib().oracle_distance_filter(_ptr(a, C.c_float), a.shape[0], near_thresh, far_thresh, z_low, z_high, _ptr(out, C.c_float))
+    return out[:n]
+
+
+def voxel_grid(cloud, leaf):
+    a = _xyzi(cloud)
+    out = np.zeros_like(a)
+    n = lib().oracle_voxel_grid(_ptr(a, C.c_float), a.shape[0], leaf, _ptr(out, C.c_float))
+    return out[:n]
+
+
+def radius_outlier_removal(cloud, radius, min_pts):
+    a = _xyzi(cloud)
+    out = np.zeros_like(a)
+    n = lib().oracle_radius_outlier_removal(_ptr(a, C.c_float), a.shape[0], radius, min_pts, _ptr(out, C.c_float))
+    return out[:n]
+
+
+def accumulate_submap(clouds, rel_poses, leaf=0.0):
+    off = np.zeros(len(clouds) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([c.shape[0] for c in clouds])
+    a = _xyzi(np.concatenate(clouds))
+    P = np.ascontiguousarray(rel_poses, dtype=np.float64).reshape(len(clouds), 16)
+    out = np.zeros_like(a)
+    n = lib().oracle_accumulate_submap(_ptr(a, C.c_float), _ptr(off, C.c_int), len(clouds), _ptr(P, C.c_double), leaf, _ptr(out, C.c_float))
+    return out[:n]

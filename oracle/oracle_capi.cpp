@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "apd_oracle.hpp"
+#include "preprocess_oracle.hpp"
 
 using apd_oracle::FastAPDGICP;
 using apd_oracle::Mat3;
@@ -203,6 +204,46 @@ double oracle_timed_registration(void* h, const float* src_xyz, int ns, const fl
   if (fitness) *fitness = f;
   const auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- "next" rows 8(f)-2 / 8(f)-4: preprocessing filters and submap accumulation (preprocess_oracle.hpp) ----
+// clouds are (n, 4) float arrays x, y, z, intensity; outputs are written to `out` (capacity n_in) and the count returned
+static std::vector<apd_oracle::PointI> to_pts(const float* xyzi, int n) {
+  std::vector<apd_oracle::PointI> v(n);
+  std::memcpy(v.data(), xyzi, sizeof(apd_oracle::PointI) * n);
+  return v;
+}
+int oracle_distance_filter(const float* xyzi, int n, double near_thresh, double far_thresh, double z_low, double z_high, float* out) {
+  const auto r = apd_oracle::distance_filter(to_pts(xyzi, n), near_thresh, far_thresh, z_low, z_high);
+  std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
+  return (int)r.size();
+}
+int oracle_voxel_grid(const float* xyzi, int n, float leaf, float* out) {
+  std::vector<apd_oracle::PointI> r;
+  apd_oracle::voxel_grid(to_pts(xyzi, n), leaf, r);
+  std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
+  return (int)r.size();
+}
+int oracle_radius_outlier_removal(const float* xyzi, int n, double radius, int min_pts, float* out) {
+  const auto r = apd_oracle::radius_outlier_removal(to_pts(xyzi, n), radius, min_pts);
+  std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
+  return (int)r.size();
+}
+int oracle_accumulate_submap(const float* xyzi, const int* offsets, int n_clouds, const double* rel_poses16, float leaf, float* out) {
+  std::vector<std::vector<apd_oracle::PointI>> clouds(n_clouds);
+  std::vector<const double*> poses(n_clouds);
+  for (int k = 0; k < n_clouds; k++) {
+    clouds[k] = to_pts(xyzi + (size_t)offsets[k] * 4, offsets[k + 1] - offsets[k]);
+    poses[k] = rel_poses16 + (size_t)k * 16;
+  }
+  auto acc = apd_oracle::accumulate_submap(clouds, poses);
+  if (leaf > 0.f) {
+    std::vector<apd_oracle::PointI> r;
+    apd_oracle::voxel_grid(acc, leaf, r);
+    acc.swap(r);
+  }
+  std::memcpy(out, acc.data(), sizeof(apd_oracle::PointI) * acc.size());
+  return (int)acc.size();
 }
 
 int oracle_max_threads() {

@@ -12,7 +12,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libapdgicp_b200.so")
-SOURCES = ["apd_build.cu", "apd_knn_cov.cu", "apd_align.cu", "apd_capi.cu"]
+SOURCES = ["apd_build.cu", "apd_knn_cov.cu", "apd_align.cu", "apd_preprocess.cu", "apd_capi.cu"]
 HEADERS = ["apd_internal.h", "apd_grid.cuh", "apd_math.cuh", os.path.join("..", "..", "include", "apdgicp_b200.h")]
 
 NVCC_FLAGS = [

@@ -384,7 +384,8 @@ __global__ void pack_points_kernel(const float* __restrict__ xyz, int stride_flo
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float* p = xyz + i * stride_floats;
-  out[i] = make_float4(p[0], p[1], p[2], 1.0f);
+  // .w is never read by the matcher; for pcl::PointXYZI records (stride >= 20 bytes) it carries the intensity for apd_build_submap
+  out[i] = make_float4(p[0], p[1], p[2], stride_floats >= 5 ? p[4] : 1.0f);
 }
 
 // pcl::transformPointCloud(*input_, output, T) at lsq_registration_impl.hpp:79 (float arithmetic)

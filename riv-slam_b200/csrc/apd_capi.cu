@@ -168,7 +168,7 @@ struct apd_context {
   int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
-      counters, grid_partials, misc, knn_tmp, cov_tmp;
+      counters, grid_partials, misc, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
   int scratch_slots = 0, scratch_max_src = 0;
   // last single-pair alignment
   bool has_last = false;
@@ -1301,6 +1301,155 @@ int apd_odometry_align(apd_handle h, const float* pts, const int32_t* offsets, i
   DeviceGuard guard(h->device);
   if (n_scans < 2) return APD_OK;
   return pipelined_align(h, pts, offsets, nullptr, nullptr, stride_bytes, guesses, n_scans - 1, out, true);
+}
+
+// ---- "next" rows 8(f)-4 / 8(f)-2: preprocessing filters and submap accumulation ----
+
+int apd_default_preprocess_params(apd_preprocess_params* p) {
+  if (!p) return APD_ERR_INVALID;
+  memset(p, 0, sizeof(*p));
+  p->use_distance_filter = 1;
+  p->outlier_removal = 1;  // launch file: outlier_removal_method RADIUS (radar_graph_slam.launch:59)
+  p->radius_min_neighbors = 2;
+  p->distance_near_thresh = 1.0;
+  p->distance_far_thresh = 100.0;
+  p->z_low_thresh = -5.0;
+  p->z_high_thresh = 20.0;
+  p->downsample_resolution = 0.1;
+  p->radius_radius = 0.8;
+  return APD_OK;
+}
+
+static int preprocess_scratch(apd_handle h, size_t n) {
+  n = std::max<size_t>(n, 1);
+  CK(h->pp_a.reserve(sizeof(float4) * n));
+  CK(h->pp_b.reserve(sizeof(float4) * n));
+  CK(h->pp_flag.reserve(n));
+  CK(h->pp_n.reserve(sizeof(int) * 8));
+  CK(h->pp_ws.reserve(sizeof(unsigned) * 4 * n));
+  CK(h->pp_seg.reserve(sizeof(int) * (n + 1)));
+  return APD_OK;
+}
+
+int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int intensity_offset_bytes, int n, const apd_preprocess_params* p, float* out, int* n_out) {
+  if (!h || !p || !n_out || n < 0) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  *n_out = 0;
+  if (stride_bytes < 16 || stride_bytes % 4) return fail(h, APD_ERR_INVALID, "stride_bytes must be a multiple of 4 and at least 16 (x, y, z, intensity)");
+  if (intensity_offset_bytes < 12 || intensity_offset_bytes % 4 || intensity_offset_bytes + 4 > stride_bytes)
+    return fail(h, APD_ERR_INVALID, "intensity_offset_bytes must address a float inside the record, after x, y, z");
+  if (p->outlier_removal < 0 || p->outlier_removal > 1) return fail(h, APD_ERR_UNSUPPORTED, "outlier_removal must be 0 (NONE) or 1 (RADIUS)");
+  if (p->outlier_removal == 1 && (p->radius_min_neighbors < 0 || !(p->radius_radius > 0))) return fail(h, APD_ERR_INVALID, "bad radius outlier parameters");
+  if (n == 0) return APD_OK;
+  if (!points || !out) return fail(h, APD_ERR_INVALID, "null point pointer");
+  const int sf = stride_bytes / 4, io = intensity_offset_bytes / 4;
+  int rc = preprocess_scratch(h, (size_t)n);
+  if (rc) return rc;
+  const size_t raw_bytes = (size_t)n * stride_bytes;
+  CK(h->raw_upload.reserve(raw_bytes));
+  CK(cudaMemcpyAsync(h->raw_upload.p, points, raw_bytes, cudaMemcpyHostToDevice, h->stream));
+  float4 *A = h->pp_a.as<float4>(), *B = h->pp_b.as<float4>();
+  int* nd = h->pp_n.as<int>();
+  unsigned char* flag = h->pp_flag.as<unsigned char>();
+  CK(launch_pack_xyzi(h->raw_upload.as<float>(), sf, io, n, A, h->stream, &h->stats));
+  // distance_filter (preprocessing_nodelet.cpp:812); without it only the NaN removal of downsample() (:852-856) can drop points
+  const bool voxel = p->downsample_resolution > 0;
+  const int mode = p->use_distance_filter ? 0 : (voxel ? 2 : 1);
+  CK(launch_distance_filter(A, n, p->distance_near_thresh, p->distance_far_thresh, p->z_low_thresh, p->z_high_thresh, mode, flag, B, nd + 0, h->stream, &h->stats));
+  float4 *cur = B, *other = A;
+  int* cur_n = nd + 0;
+  if (voxel) {
+    CK(launch_voxel_grid(cur, cur_n, n, (float)p->downsample_resolution, h->pp_ws.as<unsigned>(), h->pp_seg.as<int>(), other, nd + 1, h->stream, &h->stats));
+    std::swap(cur, other);
+    cur_n = nd + 1;
+  }
+  if (p->outlier_removal == 1) {
+    int m = 0;
+    CK(cudaMemcpyAsync(&m, cur_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (m > 0) {
+      // neighbour counting on the same uniform grid the scan matcher searches
+      const int32_t off[2] = {0, m};
+      std::shared_ptr<apd_cloudset_s> cs;
+      rc = make_cloudset(h, reinterpret_cast<const float*>(cur), 16, off, 1, APD_MEM_DEVICE, &cs);
+      if (rc) return rc;
+      rc = cloudset_build_grid(h, cs.get());
+      if (rc) return rc;
+      CK(launch_radius_flags(cs->view(), m, p->radius_radius, p->radius_min_neighbors, flag, h->stream, &h->stats));
+      CK(launch_compact(cur, flag, cur_n, other, nd + 2, h->stream, &h->stats));
+      std::swap(cur, other);
+      cur_n = nd + 2;
+      CK(cudaStreamSynchronize(h->stream));  // cs (pooled buffers) dies here; its kernels are done
+    }
+  }
+  CK(launch_unpack_xyzi(cur, cur_n, n, sf, io, h->raw_upload.as<float>(), h->stream, &h->stats));
+  int m = 0;
+  CK(cudaMemcpyAsync(&m, cur_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (m > 0) {
+    CK(cudaMemcpyAsync(out, h->raw_upload.p, (size_t)m * stride_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  *n_out = m;
+  return APD_OK;
+}
+
+int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which, int n_sel, const double* rel_poses, double downsample_resolution, uint64_t cache_key,
+                     float* out_xyzi, int out_capacity, int* n_out) {
+  if (!h || !keyframes || !n_out || n_sel < 0 || (n_sel > 0 && (!which || !rel_poses))) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  *n_out = 0;
+  apd_cloudset_s* ks = deref(keyframes);
+  std::vector<int> off(n_sel + 1, 0);
+  for (int i = 0; i < n_sel; i++) {
+    if (which[i] < 0 || which[i] >= ks->n_clouds) return fail(h, APD_ERR_INVALID, "keyframe index out of range");
+    off[i + 1] = off[i] + (ks->h_off[which[i] + 1] - ks->h_off[which[i]]);
+  }
+  const int total = off[n_sel];
+  h->last_lin_valid = false;
+  h->has_last = false;
+  if (total == 0) {  // an empty submap: the target is cleared (PCL would refuse an empty target at align time)
+    h->tgt.reset();
+    h->tgt_key = 0;
+    return APD_OK;
+  }
+  int rc = preprocess_scratch(h, (size_t)total);
+  if (rc) return rc;
+  // selection tables: [which n_sel | out_off n_sel+1] ints, then poses (16 doubles each), 16-byte aligned
+  const size_t ints = (size_t)(2 * n_sel + 1), pose_at = (ints * sizeof(int) + 15) & ~(size_t)15;
+  std::vector<unsigned char> tab(pose_at + sizeof(double) * 16 * n_sel);
+  memcpy(tab.data(), which, sizeof(int) * n_sel);
+  memcpy(tab.data() + sizeof(int) * n_sel, off.data(), sizeof(int) * (n_sel + 1));
+  memcpy(tab.data() + pose_at, rel_poses, sizeof(double) * 16 * n_sel);
+  CK(h->pp_tab.reserve(tab.size()));
+  CK(cudaMemcpyAsync(h->pp_tab.p, tab.data(), tab.size(), cudaMemcpyHostToDevice, h->stream));
+  const int* d_which = h->pp_tab.as<int>();
+  const int* d_off = d_which + n_sel;
+  const double* d_pose = reinterpret_cast<const double*>(h->pp_tab.as<unsigned char>() + pose_at);
+  float4 *A = h->pp_a.as<float4>(), *B = h->pp_b.as<float4>();
+  CK(launch_submap_gather(ks->view(), ks->pts.as<float4>(), d_which, d_off, n_sel, total, d_pose, A, h->stream, &h->stats));
+  float4* cur = A;
+  int m = total;
+  if (downsample_resolution > 0) {
+    int* nd = h->pp_n.as<int>();
+    CK(launch_voxel_grid(A, nullptr, total, (float)downsample_resolution, h->pp_ws.as<unsigned>(), h->pp_seg.as<int>(), B, nd, h->stream, &h->stats));
+    CK(cudaMemcpyAsync(&m, nd, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    cur = B;
+  }
+  CK(cudaStreamSynchronize(h->stream));  // also: the host table `tab` has been consumed
+  // registration_s2m->setInputTarget(keyframe_cloud_s2m), scan_matching_odometry_nodelet.cpp:615, without leaving the device
+  const int32_t one[2] = {0, m};
+  std::shared_ptr<apd_cloudset_s> cs;
+  rc = make_cloudset(h, reinterpret_cast<const float*>(cur), 16, one, 1, APD_MEM_DEVICE, &cs);
+  if (rc) return rc;
+  h->tgt = cs;
+  h->tgt_key = cache_key;
+  if (out_xyzi && out_capacity > 0) {
+    CK(cudaMemcpyAsync(out_xyzi, cur, sizeof(float4) * (size_t)std::min(m, out_capacity), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  *n_out = m;
+  return APD_OK;
 }
 
 int apd_synchronize(apd_handle h) {

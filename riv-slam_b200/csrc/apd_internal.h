@@ -186,6 +186,18 @@ cudaError_t launch_cov_export(const CloudSetView& cs, int cloud, double* out16 /
 cudaError_t launch_cov_import(const CloudSetView& cs, int cloud, const double* in16 /*device n*16*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_corr_export(const AlignBatch& b, int slot, int s /*source cloud*/, int t /*target cloud*/, int* corr_out, float* sqd_out, double* m16_out, cudaStream_t stream, LaunchStats* st);
 
+// ---- preprocessing filters and submap accumulation (apd_preprocess.cu); clouds are float4 x, y, z, intensity ----
+cudaError_t launch_distance_filter(const float4* in, int n, double near_t, double far_t, double z_low, double z_high, int mode, unsigned char* flag, float4* out,
+                                   int* n_out, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_voxel_grid(const float4* in, const int* n_in_dev, int n_in_host, float leaf, unsigned* ws_u32 /*4*n*/, int* seg_start /*n+1*/, float4* out, int* n_out,
+                              cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_radius_flags(const CloudSetView& cs, int n, double radius, int min_pts, unsigned char* flag, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_compact(const float4* in, const unsigned char* flag, const int* n_dev, float4* out, int* n_out, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_submap_gather(const CloudSetView& cs, const float4* xyzi, const int* which, const int* out_off, int n_sel, int total, const double* poses, float4* out,
+                                 cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_pack_xyzi(const float* raw, int stride_floats, int intensity_offset, int n, float4* out, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_unpack_xyzi(const float4* in, const int* n_dev, int n_max, int stride_floats, int intensity_offset, float* raw, cudaStream_t stream, LaunchStats* st);
+
 size_t align_static_smem();
 int align_max_teams(int team_kind, int team_size, bool stage_target, size_t smem_bytes);
 

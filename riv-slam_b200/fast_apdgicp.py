@@ -50,6 +50,15 @@ class ApdResult(C.Structure):
     ]
 
 
+class ApdPreprocessParams(C.Structure):
+    """apd_preprocess_params: the PreprocessingNodelet parameters (preprocessing_nodelet.cpp:137-205)."""
+    _fields_ = [
+        ("use_distance_filter", C.c_int32), ("outlier_removal", C.c_int32), ("radius_min_neighbors", C.c_int32), ("reserved", C.c_int32),
+        ("distance_near_thresh", C.c_double), ("distance_far_thresh", C.c_double), ("z_low_thresh", C.c_double), ("z_high_thresh", C.c_double),
+        ("downsample_resolution", C.c_double), ("radius_radius", C.c_double),
+    ]
+
+
 RESULT_DTYPE = np.dtype([("T", np.float32, (4, 4)), ("fitness", np.float64), ("error", np.float64), ("converged", np.int32),
                          ("iterations", np.int32), ("status", np.int32), ("num_inliers", np.int32)])
 assert RESULT_DTYPE.itemsize == C.sizeof(ApdResult) == 96
@@ -98,6 +107,9 @@ _PROTOTYPES = {
     "apd_batch_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_void_p, _ip, C.c_int, _fp, C.c_int, C.c_void_p]),
     "apd_fitness_score": (C.c_int, [C.c_void_p, _fp, C.c_double, _dp, C.POINTER(C.c_int64)]),
     "apd_fitness_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip, _fp, C.c_int, C.c_double, _dp]),
+    "apd_default_preprocess_params": (C.c_int, [C.POINTER(ApdPreprocessParams)]),
+    "apd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(ApdPreprocessParams), C.c_void_p, _ip]),
+    "apd_build_submap": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, _dp, C.c_double, C.c_uint64, C.c_void_p, C.c_int, _ip]),
     "apd_odometry_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_int, _fp, C.c_void_p]),
     "apd_synchronize": (C.c_int, [C.c_void_p]),
     "apd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
@@ -556,3 +568,46 @@ def fitness_pairs(handle: Handle, src: CloudSet, tgt: CloudSet, src_idx=None, tg
     handle.check(handle.L.apd_fitness_pairs(handle.h, src.cs, tgt.cs, None if si is None else si.ctypes.data_as(_ip), None if ti is None else ti.ctypes.data_as(_ip),
                                             None if g is None else g.ctypes.data_as(_fp), n_pairs, float(max_range), out.ctypes.data_as(_dp)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows SURVEY.md 8(f)-4 / 8(f)-2: the filters in front of the matcher and the submap behind it
+# ---------------------------------------------------------------------------------------------
+
+def preprocess_params(**kw) -> ApdPreprocessParams:
+    """Code defaults of PreprocessingNodelet::initializeParams (preprocessing_nodelet.cpp:137-205) with keyword overrides."""
+    p = ApdPreprocessParams()
+    load_library().apd_default_preprocess_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"unknown preprocessing parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+def preprocess(handle: Handle, cloud, params: ApdPreprocessParams | None = None, **kw) -> np.ndarray:
+    """distance_filter -> downsample -> outlier_removal (preprocessing_nodelet.cpp:812-815) of one host cloud on the GPU.
+
+    ``cloud`` is (n, 4) packed x y z intensity or (n, 8) pcl::PointXYZI memory; the result has the same row layout."""
+    a = np.ascontiguousarray(cloud, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("preprocess takes (n, 4) xyzi or (n, 8) pcl::PointXYZI arrays")
+    p = params if params is not None else preprocess_params(**kw)
+    out = np.zeros_like(a)
+    n_out = C.c_int32(0)
+    handle.check(handle.L.apd_preprocess(handle.h, C.c_void_p(a.ctypes.data), a.shape[1] * 4, 12 if a.shape[1] == 4 else 16, a.shape[0], C.byref(p),
+                                         C.c_void_p(out.ctypes.data), C.byref(n_out)))
+    return out[:n_out.value]
+
+
+def build_submap(handle: Handle, keyframes: CloudSet, which, rel_poses, downsample_resolution: float = 0.1, cache_key: int = 0, want_cloud: bool = True):
+    """apd_build_submap: the keyframe clouds ``which`` moved by ``rel_poses`` (4x4 double each), concatenated and voxel-filtered,
+    become the handle's target (scan_matching_odometry_nodelet.cpp:606-616). Returns the submap as (m, 4) xyzi (or its size)."""
+    w = np.ascontiguousarray(which, dtype=np.int32)
+    P = np.ascontiguousarray(rel_poses, dtype=np.float64).reshape(len(w), 16)
+    cap = int(sum(keyframes.offsets[i + 1] - keyframes.offsets[i] for i in w))
+    out = np.zeros((max(cap, 1), 4), dtype=np.float32) if want_cloud else None
+    n_out = C.c_int32(0)
+    handle.check(handle.L.apd_build_submap(handle.h, keyframes.cs, w.ctypes.data_as(_ip), len(w), P.ctypes.data_as(_dp), float(downsample_resolution),
+                                           C.c_uint64(cache_key), None if out is None else C.c_void_p(out.ctypes.data), cap if want_cloud else 0, C.byref(n_out)))
+    return out[:n_out.value] if want_cloud else n_out.value

@@ -1,0 +1,244 @@
+""""Next" rows SURVEY.md §8(f)-4 (preprocessing filters) and §8(f)-2 (submap accumulation).
+
+CPU part (not gpu): the C++ oracle (oracle/preprocess_oracle.hpp) against an independent numpy /
+pure-Python twin written from the same reference lines (preprocessing_nodelet.cpp:812-815,850-896,
+scan_matching_odometry_nodelet.cpp:606-616) and PCL's published filter behaviour.
+GPU part: apd_preprocess / apd_build_submap through the C ABI against the oracle, bit-exact
+(same points, same order, same float bits).
+"""
+import numpy as np
+import pytest
+
+from conftest import LAUNCH_PARAMS
+
+
+# ---------------------------------------------------------------- inputs
+
+def raw_scan(seed, n=3000, with_bad=True):
+    """A raw radar-like cloud (x y z intensity): several returns per 0.1 m voxel, near/far/z outliers, NaN/inf rows."""
+    from riv_slam_b200 import datagen
+    src, _, _ = datagen.make_pair(9, seed, n_src=n)
+    rng = np.random.default_rng(1234 + seed)
+    base = np.asarray(src[:, :3], dtype=np.float32)
+    reps = [base]
+    for _ in range(2):  # extra returns of the same scatterers -> voxels with 2-3 points
+        keep = rng.random(len(base)) < 0.5
+        reps.append(base[keep] + rng.normal(0, 0.02, (int(keep.sum()), 3)).astype(np.float32))
+    xyz = np.concatenate(reps)
+    lone = rng.uniform([-20, -40, -8], [110, 40, 25], (200, 3)).astype(np.float32)  # isolated clutter, some outside the z band
+    near = rng.normal(0, 0.4, (50, 3)).astype(np.float32)                           # inside distance_near_thresh
+    xyz = np.concatenate([xyz, lone, near])
+    pts = np.concatenate([xyz, rng.uniform(0, 40, (len(xyz), 1)).astype(np.float32)], axis=1)
+    pts = pts[rng.permutation(len(pts))]
+    if with_bad:
+        bad = rng.choice(len(pts), 12, replace=False)
+        pts[bad[:4], 0] = np.nan
+        pts[bad[4:8], 1] = np.inf
+        pts[bad[8:], 2] = -np.inf
+    return np.ascontiguousarray(pts, dtype=np.float32)
+
+
+def oracle_pipeline(cloud, use_distance_filter=1, distance_near_thresh=1.0, distance_far_thresh=100.0, z_low_thresh=-5.0, z_high_thresh=20.0,
+                    downsample_resolution=0.1, outlier_removal=1, radius_radius=0.8, radius_min_neighbors=2):
+    from oracle import oracle as O
+    c = cloud
+    if use_distance_filter:
+        c = O.distance_filter(c, distance_near_thresh, distance_far_thresh, z_low_thresh, z_high_thresh)
+    if downsample_resolution > 0:
+        c = O.voxel_grid(c, downsample_resolution)
+    else:
+        c = c[np.isfinite(c[:, :3]).all(axis=1)]  # pcl::removeNaNFromPointCloud, preprocessing_nodelet.cpp:852-856
+    if outlier_removal == 1:
+        c = O.radius_outlier_removal(c, radius_radius, radius_min_neighbors)
+    return c
+
+
+# ---------------------------------------------------------------- twins (independent of the C++ oracle)
+
+def twin_distance_filter(c, near, far, zlo, zhi):
+    x, y, z = c[:, 0], c[:, 1], c[:, 2]
+    with np.errstate(invalid="ignore", over="ignore"):
+        d = np.sqrt(((x * x).astype(np.float32) + (y * y).astype(np.float32)).astype(np.float32) + (z * z).astype(np.float32), dtype=np.float32).astype(np.float64)
+        keep = (d > near) & (d < far) & (z.astype(np.float64) < zhi) & (z.astype(np.float64) > zlo)
+    return c[keep]
+
+
+def twin_voxel_grid(c, leaf):
+    f32 = np.float32
+    inv = f32(1.0) / f32(leaf)
+    fin = np.isfinite(c[:, :3]).all(axis=1)
+    p = c[fin]
+    mn, mx = p[:, :3].min(axis=0), p[:, :3].max(axis=0)
+    minb = np.floor(mn * inv).astype(np.int64)
+    div = np.floor(mx * inv).astype(np.int64) - minb + 1
+    ijk = (np.floor(p[:, :3] * inv) - minb.astype(f32)).astype(np.int64)
+    key = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    groups = {}
+    for i, k in enumerate(key.tolist()):  # ascending input order inside a voxel
+        groups.setdefault(k, []).append(i)
+    out = []
+    for k in sorted(groups):
+        s = np.zeros(4, dtype=f32)
+        for i in groups[k]:
+            s = (s + p[i]).astype(f32)
+        out.append(s / f32(len(groups[k])))
+    return np.array(out, dtype=f32).reshape(-1, 4)
+
+
+def twin_radius_outlier(c, radius, min_pts):
+    x = c[:, :3]
+    d = (x[:, None, :] - x[None, :, :]).astype(np.float32)
+    d2 = ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32) + (d[..., 2] * d[..., 2]).astype(np.float32)
+    if len(c) < min_pts + 1:
+        return c[:0]
+    kth = np.partition(d2, min_pts, axis=1)[:, min_pts].astype(np.float64)
+    return c[~(radius * radius < kth)]
+
+
+# ---------------------------------------------------------------- CPU: oracle vs twins
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_oracle_distance_filter_matches_twin(seed):
+    from oracle import oracle as O
+    c = raw_scan(seed, 1500)
+    for args in [(1.0, 100.0, -5.0, 20.0), (2.0, 50.0, -2.0, 6.0)]:
+        assert np.array_equal(O.distance_filter(c, *args), twin_distance_filter(c, *args))
+
+
+@pytest.mark.parametrize("leaf", [0.1, 0.5, 2.0])
+def test_oracle_voxel_grid_matches_twin(leaf):
+    from oracle import oracle as O
+    c = raw_scan(2, 1500)
+    got, want = O.voxel_grid(c, leaf), twin_voxel_grid(c, leaf)
+    assert got.shape == want.shape and got.tobytes() == want.tobytes()
+    # every output point is the centroid of a distinct voxel: idempotent up to centroid rounding in count
+    assert len(O.voxel_grid(got, leaf)) == len(got)
+
+
+def test_oracle_voxel_grid_edge_cases():
+    from oracle import oracle as O
+    assert O.voxel_grid(np.zeros((0, 4), np.float32), 0.1).shape == (0, 4)
+    nan = np.full((5, 4), np.nan, np.float32)
+    assert O.voxel_grid(nan, 0.1).shape == (0, 4)
+    one = np.array([[1, 2, 3, 4]], np.float32)
+    assert np.array_equal(O.voxel_grid(one, 0.1), one)
+    # leaf too small for 32-bit voxel indices: PCL warns and returns the input cloud unchanged
+    far = np.array([[0, 0, 0, 1], [9000, 9000, 9000, 2]], np.float32)
+    assert np.array_equal(O.voxel_grid(far, 0.001), far)
+
+
+@pytest.mark.parametrize("radius,min_pts", [(0.8, 2), (0.5, 5), (0.3, 1)])
+def test_oracle_radius_outlier_matches_twin(radius, min_pts):
+    from oracle import oracle as O
+    c = O.voxel_grid(raw_scan(3, 800, with_bad=False), 0.1)
+    got, want = O.radius_outlier_removal(c, radius, min_pts), twin_radius_outlier(c, radius, min_pts)
+    assert np.array_equal(got, want)
+    assert 0 < len(got) < len(c)
+
+
+def test_oracle_submap_matches_twin():
+    from oracle import oracle as O
+    from riv_slam_b200 import datagen
+    clouds = [raw_scan(10 + i, 600, with_bad=False) for i in range(3)]
+    poses = [datagen.pose_matrix([0.4 * i, 0.05 * i, 0.0], [0.0, 0.2 * i, 1.0 * i]) for i in range(3)]
+    got = O.accumulate_submap(clouds, poses, 0.0)
+    want = []
+    for c, T in zip(clouds, poses):
+        x = c[:, :3].astype(np.float64)
+        q = ((T[:3, 0] * x[:, :1] + T[:3, 1] * x[:, 1:2]) + T[:3, 2] * x[:, 2:3]) + T[:3, 3]
+        want.append(np.concatenate([q.astype(np.float32), c[:, 3:4]], axis=1))
+    want = np.concatenate(want)
+    assert got.tobytes() == want.tobytes()
+    assert O.accumulate_submap(clouds, poses, 0.1).tobytes() == twin_voxel_grid(want, 0.1).tobytes()
+
+
+# ---------------------------------------------------------------- GPU: the CUDA path vs the oracle, bit-exact
+
+def _handle():
+    from riv_slam_b200.fast_apdgicp import Handle
+    return Handle(0)
+
+
+CASES = [
+    dict(),                                                         # code defaults + RADIUS (launch file)
+    dict(outlier_removal=0),
+    dict(downsample_resolution=0.0),                                # downsample_method NONE -> NaN removal only
+    dict(use_distance_filter=0, outlier_removal=0),
+    dict(use_distance_filter=0, downsample_resolution=0.0, outlier_removal=0),
+    dict(distance_near_thresh=2.0, distance_far_thresh=60.0, z_low_thresh=-2.0, z_high_thresh=6.0, downsample_resolution=0.25, radius_radius=0.5,
+         radius_min_neighbors=5),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("width", [4, 8])
+def test_preprocess_bit_exact(case, width):
+    from riv_slam_b200.fast_apdgicp import preprocess
+    kw = CASES[case]
+    c = raw_scan(20 + case, 3000)
+    want = oracle_pipeline(c, **kw)
+    cloud = c
+    if width == 8:  # pcl::PointXYZI memory: x y z 1 | intensity pad pad pad
+        cloud = np.zeros((len(c), 8), np.float32)
+        cloud[:, :3], cloud[:, 3], cloud[:, 4] = c[:, :3], 1.0, c[:, 3]
+    got = preprocess(_handle(), cloud, **kw)
+    if width == 8:
+        assert np.all(got[:, 3] == 1.0) and np.all(got[:, 5:] == 0.0)
+        got = np.ascontiguousarray(got[:, [0, 1, 2, 4]])
+    assert got.shape == want.shape
+    assert got.tobytes() == want.tobytes()
+    assert 0 < len(got) < len(c)
+
+
+@pytest.mark.gpu
+def test_preprocess_edge_cases():
+    from riv_slam_b200.fast_apdgicp import preprocess, ApdError
+    H = _handle()
+    assert preprocess(H, np.zeros((0, 4), np.float32)).shape == (0, 4)
+    assert preprocess(H, np.full((7, 4), np.nan, np.float32)).shape == (0, 4)          # everything filtered
+    lone = np.array([[5, 0, 0, 1], [50, 0, 0, 2]], np.float32)
+    assert preprocess(H, lone).shape == (0, 4)                                          # fewer points than min_neighbors + 1
+    assert np.array_equal(preprocess(H, lone, outlier_removal=0), lone)
+    with pytest.raises(ApdError):
+        preprocess(H, lone, outlier_removal=2)                                          # STATISTICAL is not implemented: loud, no fallback
+    # a 20k-point raw scan (several CTA-sized segments per thread)
+    big = np.concatenate([raw_scan(40 + i, 5000) for i in range(3)])
+    assert preprocess(H, big).tobytes() == oracle_pipeline(big).tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("leaf", [0.1, 0.0])
+def test_build_submap_bit_exact_and_becomes_target(leaf):
+    from oracle import oracle as O
+    from oracle.oracle import Oracle
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import CloudSet, FastAPDGICP, build_submap
+    scans, poses = datagen.make_drive(9, 3, 6, n_points=3000)
+    clouds = [np.ascontiguousarray(np.concatenate([s[:, :3], np.full((len(s), 1), 7.0 + i, np.float32)], axis=1)) for i, s in enumerate(scans)]
+    which = [1, 2, 3, 4]
+    last = poses[5]
+    rel = [np.linalg.inv(poses[i]) @ last for i in which]  # scan_matching_odometry_nodelet.cpp:610 (as written in the reference)
+    want = O.accumulate_submap([clouds[i] for i in which], rel, leaf)
+    reg = FastAPDGICP(0)
+    reg.handle().set_params(**LAUNCH_PARAMS)
+    ks = CloudSet(reg.handle(), clouds)
+    got = build_submap(reg.handle(), ks, which, rel, leaf, cache_key=77)
+    assert got.shape == want.shape and got.tobytes() == want.tobytes()
+    # the submap is now the target: aligning against it equals aligning against the same cloud set from the host
+    reg.setInputSource(clouds[5])
+    reg.align(want_output=False)
+    assert reg.hasConverged()
+    Ta = reg.getFinalTransformation().copy()
+    fit_a, it_a = reg.getFitnessScore(), reg.nr_iterations()
+    ref = FastAPDGICP(0)
+    ref.handle().set_params(**LAUNCH_PARAMS)
+    ref.setInputTarget(want)
+    ref.setInputSource(clouds[5])
+    ref.align(want_output=False)
+    assert np.array_equal(Ta, ref.getFinalTransformation()) and fit_a == ref.getFitnessScore() and it_a == ref.nr_iterations()
+    o = Oracle(**LAUNCH_PARAMS)
+    o.set_source(clouds[5]); o.set_target(want)
+    rc, To, conv, it = o.align()
+    assert rc == 0 and conv and it == it_a
+    assert np.abs(Ta.astype(np.float64) - To).max() < 1e-4
