@@ -48,6 +48,7 @@ struct AlignShared {
   int converged;
   int pair;
   int staged_target;  // cloud index currently staged, -1 none
+  int next;           // next unclaimed source point of the running search pass (dynamic chunks)
 };
 
 template <int TEAM>
@@ -100,6 +101,34 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
   }
   tc.buf ^= 1;
   __syncthreads();
+}
+
+// The search passes hand out their points in chunks of adjacent (cell-sorted) points from a shared counter:
+// the cost of a chunk varies a lot (sparse neighbourhoods, anchors that skip the search), and with a static
+// round-robin 14 % of the kernel's samples sat at the next barrier waiting for the slowest warp (round-1 ncu).
+// The passes only write per-point results, so the assignment does not influence any sum. A CTA with fewer
+// points than threads (cluster and grid teams) spreads them thinly over all its warps.
+struct ChunkPlan {
+  int chunk, lane;
+};
+__device__ __forceinline__ ChunkPlan chunk_begin(AlignShared& S, int begin, int end) {
+  __syncthreads();
+  if (threadIdx.x == 0) S.next = begin;
+  __syncthreads();
+  const int n_warps = blockDim.x >> 5;
+  ChunkPlan c;
+  c.chunk = max(1, min(32, (end - begin + n_warps - 1) / n_warps));
+  c.lane = threadIdx.x & 31;
+  return c;
+}
+// returns false when the pass is over; otherwise i is this lane's point or -1 (idle lane of the chunk)
+__device__ __forceinline__ bool chunk_next(AlignShared& S, const ChunkPlan& c, int end, int& i) {
+  int i0 = 0;
+  if (c.lane == 0) i0 = atomicAdd(&S.next, c.chunk);
+  i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
+  if (i0 >= end) return false;
+  i = (c.lane < c.chunk && i0 + c.lane < end) ? i0 + c.lane : -1;
+  return true;
 }
 
 // APD measurement covariance of the transformed source point (fast_apdgicp_impl.hpp:167-184)
@@ -182,14 +211,16 @@ struct TargetView {
 
 // update_correspondences for the calling thread's points (fast_apdgicp_impl.hpp:146-193)
 template <typename CellT>
-__device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts,
+__device__ __forceinline__ void correspondence_pass(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts,
                                                     const double2* __restrict__ c0, const double2* __restrict__ c1, const double2* __restrict__ c2,
                                                     int begin, int end, size_t sbase, bool seeded) {
   const float* Tf = S.Tf;
   const float r00 = Tf[0], r01 = Tf[1], r02 = Tf[2], t0 = Tf[3];
   const float r10 = Tf[4], r11 = Tf[5], r12 = Tf[6], t1 = Tf[7];
   const float r20 = Tf[8], r21 = Tf[9], r22 = Tf[10], t2 = Tf[11];
-  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+  const ChunkPlan cp = chunk_begin(S, begin, end);
+  for (int i; chunk_next(S, cp, end, i);) {
+    if (i < 0) continue;
     const float4 a = sspts[i];
     const float qx = xform_row_rn(r00, r01, r02, t0, a.x, a.y, a.z);
     const float qy = xform_row_rn(r10, r11, r12, t1, a.x, a.y, a.z);
@@ -252,6 +283,7 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, const A
     B.scratch.m1[sbase + i] = make_double2(M.xz, M.yy);
     B.scratch.m2[sbase + i] = make_double2(M.yz, M.zz);
   }
+  __syncthreads();  // the accumulation passes read these records with a different (static) point-to-thread map
 }
 
 // H/b/error accumulation (FULL, fast_apdgicp_impl.hpp:221-258) or error only (:278-296) at pose x
@@ -303,10 +335,12 @@ __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const doubl
 
 // pcl::Registration::getFitnessScore(max_range): mean squared 1-NN distance of the transformed source
 template <typename CellT>
-__device__ __forceinline__ void fitness_pass(const AlignBatch& B, const AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
+__device__ __forceinline__ void fitness_pass(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
                                              size_t sbase, bool seeded, double (&acc)[kNRed]) {
   const float* Tf = S.Tf;
-  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+  const ChunkPlan cp = chunk_begin(S, begin, end);
+  for (int i; chunk_next(S, cp, end, i);) {
+    if (i < 0) continue;
     const float4 a = sspts[i];
     const float qx = xform_row_rn(Tf[0], Tf[1], Tf[2], Tf[3], a.x, a.y, a.z);
     const float qy = xform_row_rn(Tf[4], Tf[5], Tf[6], Tf[7], a.x, a.y, a.z);
@@ -320,8 +354,14 @@ __device__ __forceinline__ void fitness_pass(const AlignBatch& B, const AlignSha
     } else {
       pyramid_search<CellT, Top1, false>(T.G, B.tgt, T.cloud, qx, qy, qz, __int_as_float(0x7f800000), v);  // only the distance is used
     }
-    if (v.pos >= 0 && (double)v.bound2() <= B.max_range) {
-      acc[0] += (double)v.bound2();
+    B.scratch.fit[sbase + i] = v.pos >= 0 ? v.bound2() : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
+  }
+  __syncthreads();
+  // the sum runs in a fixed point-to-thread order, whatever warp searched the point
+  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const float d2 = B.scratch.fit[sbase + i];
+    if ((double)d2 <= B.max_range) {
+      acc[0] += (double)d2;
       acc[1] += 1.0;
     }
   }

@@ -167,7 +167,7 @@ struct apd_context {
   double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
-  DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
+  DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, sc_fit, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
       counters, grid_partials, misc, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
   int scratch_slots = 0, scratch_max_src = 0;
   // last single-pair alignment
@@ -311,8 +311,9 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   // split so that about two waves of CTAs exist
   std::vector<int4> tk;
   const long long target_ctas = h->sm_count;  // one CTA per SM fits (shared memory): a single wave
-  long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 32);
-  tile_q = (std::max<long long>(tile_q, 1) + 31) / 32 * 32;  // whole warps
+  // (a tile smaller than the CTA is spread over all its warps, a few queries per warp: knn_cov_kernel)
+  long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 16);
+  tile_q = std::max<long long>(tile_q, 1);
   for (int c = 0; c < nc; c++) {
     const int n = cs->h_off[c + 1] - cs->h_off[c];
     for (long long s = 0; s < n; s += tile_q) tk.push_back(int4{c, (int)s, (int)std::min<long long>(tile_q, n - s), 0});
@@ -460,6 +461,7 @@ int ensure_align_scratch(apd_handle h, int slots, int max_src) {
   CK(h->sc_m1.reserve(sizeof(double2) * n));
   CK(h->sc_m2.reserve(sizeof(double2) * n));
   CK(h->sc_anchor.reserve(sizeof(float4) * n));
+  CK(h->sc_fit.reserve(sizeof(float) * n));
   h->scratch_slots = slots;
   h->scratch_max_src = max_src;
   return APD_OK;
@@ -603,6 +605,7 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   b.scratch.m1 = h->sc_m1.as<double2>();
   b.scratch.m2 = h->sc_m2.as<double2>();
   b.scratch.anchor = h->sc_anchor.as<float4>();
+  b.scratch.fit = h->sc_fit.as<float>();
   b.prm = device_params(h->prm);
   b.mode = c.mode;
   b.min_points = c.min_points;

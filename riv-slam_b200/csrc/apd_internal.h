@@ -126,6 +126,7 @@ struct AlignScratch {
   double2* m0;        // Mahalanobis (xx, xy)
   double2* m1;        //             (xz, yy)
   double2* m2;        //             (yz, zz)
+  float* fit;         // [slots * max_src] squared 1-NN distance at the final pose (fitness pass)
   float4* anchor;     // unmatched points: (query position, lower bound of the distance to ANY target point) of their last full search
 };
 

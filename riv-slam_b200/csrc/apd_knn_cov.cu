@@ -44,7 +44,9 @@ template <int K, bool STAGED>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int fine_rings, int* __restrict__ knn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_next;  // next unclaimed query of the tile
   const int4 tile = tiles[blockIdx.x];
+  if (threadIdx.x == 0) s_next = tile.y;
   const int c = tile.x;
   const int base = cs.pt_off[c];
   const int n = cs.pt_off[c + 1] - base;
@@ -66,6 +68,7 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   } else {
     G.spts = gspts;
     G.cells = reinterpret_cast<const CellT*>(gcells);
+    __syncthreads();
   }
 
   const float4* opts = cs.pts + base;  // original order, for the neighbour gather
@@ -74,12 +77,26 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   int kbits = 1;
   while (kbits < 31 && (1u << kbits) < (unsigned)n) kbits++;
   const bool use_packed = packed_path && kbits <= 20;
-  // Lanes of a warp take ADJACENT cell-sorted queries (stride blockDim per thread): they walk the same
-  // rings at the same time. Two alternatives were measured in round 1 and rejected (profiles/):
-  // per-thread runs of consecutive queries chained by the triangle inequality (2x slower: the warp
-  // loses its spatial coherence) and per-ring queues drained by the whole warp (1.2x slower: the time
-  // goes to the few lanes whose sparse neighbourhoods need many rings, not to insertion divergence).
-  for (int q = tile.y + threadIdx.x; q < tile.y + tile.z; q += blockDim.x) {
+  // Lanes of a warp take ADJACENT cell-sorted queries: they walk the same rings at the same time. Two
+  // alternatives were measured in round 1 and rejected (profiles/): per-thread runs of consecutive
+  // queries chained by the triangle inequality (2x slower: the warp loses its spatial coherence) and
+  // per-ring queues drained by the whole warp (1.2x slower).
+  // Warps pull chunks of `qpw` adjacent queries from a shared counter: the cost of a chunk varies a lot
+  // (sparse neighbourhoods walk more rings), and with a static round-robin the CTA idled ~20 % of its
+  // warp slots waiting for the slowest warp (ncu sm__warps_active 12.8 of 16). A tile smaller than the
+  // CTA (single-pair latency mode) is spread thinly, few queries per warp, so that every scheduler of
+  // the SM has warps and a warp serialises fewer divergent lanes.
+  const int tile_end = tile.y + tile.z;
+  const int lane = threadIdx.x & 31;
+  const int n_warps = blockDim.x >> 5;
+  const int qpw = imax(1, imin(32, (tile.z + n_warps - 1) / n_warps));
+  for (;;) {
+    int q0 = 0;
+    if (lane == 0) q0 = atomicAdd(&s_next, qpw);
+    q0 = __shfl_sync(0xFFFFFFFFu, q0, 0);
+    if (q0 >= tile_end) break;
+    const int q = q0 + lane;
+    if (lane >= qpw || q >= tile_end) continue;
     const float4 p = G.spts[q];
     const unsigned self = __float_as_uint(p.w);
     // Fast path: collect candidates in a packed 32-bit list (min/max insertion, see TopKPacked), then
