@@ -235,8 +235,8 @@ DeviceParams device_params(const apd_params& p) {
 }
 
 // shared memory a staged grid may take: the opt-in maximum minus the align kernel's static state and
-// minus room for the kNN kernel's candidate queues (at least 16 two-byte entries per thread)
-size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem() - 512 - 16 * sizeof(uint16_t) * kKnnThreads; }
+// minus room for the kNN kernel's per-thread neighbour lists (up to 32 two-byte entries per thread)
+size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem() - 512 - 32 * sizeof(uint16_t) * kKnnThreads; }
 
 // Build the device-side description of a ragged batch: offsets, per-cloud cell budgets, tile lists.
 int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {

@@ -236,13 +236,22 @@ APD_HD bool grid_search(const GridView<CellT>& G, float qx, float qy, float qz, 
         }
         const bool face = zface || (y == cy - r) || (y == cy + r);
         const int rowbase = (z * g.ny + y) * g.nx;
-        if (face) {
-          // the full x-run of this ring belongs to the shell (r == 0: the query's own cell)
-          visit_run(G, rowbase + x0, rowbase + x1 + 1, qx, qy, qz, vis);
-        } else {
-          // interior row: only the two end cells at x = cx-r and cx+r are new
-          if (xa >= 0) visit_run(G, rowbase + xa, rowbase + xa + 1, qx, qy, qz, vis);
-          if (xb <= g.nx - 1) visit_run(G, rowbase + xb, rowbase + xb + 1, qx, qy, qz, vis);
+        // face row: the full x-run of this ring belongs to the shell (r == 0: the query's own cell);
+        // interior row: only the two end cells at x = cx-r and cx+r are new.
+        // Both shapes go through ONE visit site (a rolled two-part loop): the visitor's insertion code is
+        // the bulk of the kernels' instruction footprint, and three inlined copies per search level thrashed
+        // the 32 KB instruction cache (ncu: no_instruction was the top stall of the kNN kernel).
+        int ca0 = rowbase + x0, ca1 = rowbase + x1 + 1, cb0 = 0, cb1 = 0;
+        if (!face) {
+          ca0 = rowbase + xa; ca1 = ca0 + (xa >= 0 ? 1 : 0);
+          cb0 = rowbase + xb; cb1 = cb0 + (xb <= g.nx - 1 ? 1 : 0);
+        }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+        for (int part = 0; part < 2; part++) {
+          const int c0 = part ? cb0 : ca0, c1 = part ? cb1 : ca1;
+          if (c1 > c0) visit_run(G, c0, c1, qx, qy, qz, vis);
         }
       }
     }

@@ -131,8 +131,14 @@ struct AlignScratch {
 };
 
 enum TeamKind { TEAM_CTA = 0, TEAM_CLUSTER = 1, TEAM_GRID = 2 };
-constexpr int kAlignThreads = 512;
-constexpr int kKnnThreads = 512;
+#ifndef APD_ALIGN_THREADS
+#define APD_ALIGN_THREADS 512
+#endif
+constexpr int kAlignThreads = APD_ALIGN_THREADS;
+#ifndef APD_KNN_THREADS
+#define APD_KNN_THREADS 640
+#endif
+constexpr int kKnnThreads = APD_KNN_THREADS;
 constexpr int kNRed = 30;  // doubles per reduction record (see apd_align.cu)
 
 struct AlignBatch {

@@ -40,9 +40,45 @@ __device__ __forceinline__ Sym3 regularize(const Sym3& cov, int method) {
   return recompose(V, values);
 }
 
+// ---- cold paths, kept OUT OF LINE ----
+// The kernel's hot loop (fine-grid candidate scan + packed insertion + exact sort + covariance + Jacobi) has
+// to live in the 32 KB instruction cache; with everything inlined the kernel was 12 000 SASS instructions
+// (190 KB) and ncu showed instruction fetch (no_instruction) as its top stall. The rare paths - coarse
+// pyramid levels for isolated points, the exact 64-bit list for crowded distance buckets - are separate
+// functions that hand their result back through local memory.
+template <int K, int M>
+__device__ __noinline__ void knn_coarse_packed(GridView<unsigned> G1, GridView<unsigned> G2, float qx, float qy, float qz, int kbits, int rings, unsigned* out) {
+  TopKPacked<K, M> ap;
+  ap.kbits = kbits;
+  ap.sh = kbits - 1;
+#pragma unroll 1
+  for (int l = 0; l < 2; l++) {
+    ap.init();
+    if (grid_search(l ? G2 : G1, qx, qy, qz, __int_as_float(0x7f800000), ap, l ? 0x7fffffff : rings)) break;
+  }
+#pragma unroll
+  for (int j = 0; j < M; j++) out[j] = ap.a[j];
+}
+
+template <int K, typename CellT>
+__device__ __noinline__ void knn_exact(GridView<CellT> G0, GridView<unsigned> G1, GridView<unsigned> G2, float qx, float qy, float qz, int rings,
+                                       unsigned long long* out) {
+  TopK<K> tk;
+  tk.init();
+  if (!grid_search(G0, qx, qy, qz, __int_as_float(0x7f800000), tk, rings)) {
+#pragma unroll 1
+    for (int l = 0; l < 2; l++) {
+      tk.init();
+      if (grid_search(l ? G2 : G1, qx, qy, qz, __int_as_float(0x7f800000), tk, l ? 0x7fffffff : rings)) break;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < K; j++) out[j] = tk.key[j];
+}
+
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kKnnThreads, 1)
-knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int fine_rings, int* __restrict__ knn_out) {
+knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int fine_rings, int idx_off, int* __restrict__ knn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;  // next unclaimed query of the tile
   const int4 tile = tiles[blockIdx.x];
@@ -54,10 +90,12 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   const float4* gspts = cs.spts + base;
   const unsigned* gcells = cs.cells + cs.cell_off[c];
 
-  typedef typename std::conditional<STAGED, uint16_t, unsigned>::type CellT;
+  typedef typename std::conditional<STAGED, uint16_t, unsigned>::type CellT;  // also the type of a stored neighbour index
   GridView<CellT> G;
   G.g = g;
   G.n = n;
+  // this thread's neighbour list (entry j at nbr[j * blockDim.x]: conflict-free), behind the staged grid
+  CellT* nbr = reinterpret_cast<CellT*>(smem_raw + idx_off) + threadIdx.x;
   if (STAGED) {
     float4* s_pts = reinterpret_cast<float4*>(smem_raw);
     uint16_t* s_cells = reinterpret_cast<uint16_t*>(smem_raw + sizeof(float4) * (size_t)n);
@@ -70,6 +108,7 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
     G.cells = reinterpret_cast<const CellT*>(gcells);
     __syncthreads();
   }
+  const int nstride = blockDim.x;
 
   const float4* opts = cs.pts + base;  // original order, for the neighbour gather
   const double inv_div = (double)k;
@@ -105,53 +144,59 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
     // 64-bit list. Either way the result is the exact (d2, index)-ordered top-k.
     // Both searches go through the grid pyramid: fine grid for a few rings, coarser levels for the
     // rare isolated point.
-    TopK<K> tk;
     bool done = false;
     if (use_packed) {
       TopKPacked<K, K + 4> ap;
       ap.kbits = kbits;
       ap.sh = kbits - 1;
       ap.init();
-      pyramid_search<CellT, TopKPacked<K, K + 4>, true>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), ap, fine_rings);
+      if (!grid_search(G, p.x, p.y, p.z, __int_as_float(0x7f800000), ap, fine_rings)) {
+        unsigned tmp[K + 4];
+        knn_coarse_packed<K, K + 4>(coarse_view(cs, 0, c), coarse_view(cs, 1, c), p.x, p.y, p.z, kbits, fine_rings, tmp);
+#pragma unroll
+        for (int j = 0; j < K + 4; j++) ap.a[j] = tmp[j];
+      }
       if (ap.complete()) {
+        TopK<K> tk;
         exact_from_packed(ap, p.x, p.y, p.z, opts, tk);
+#pragma unroll
+        for (int j = 0; j < K; j++) nbr[j * nstride] = (CellT)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
         done = true;
       }
     }
     if (!done) {
-      tk.init();
-      pyramid_search<CellT, TopK<K>, true>(G, cs, c, p.x, p.y, p.z, __int_as_float(0x7f800000), tk, fine_rings);
-    }
-
-    // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324)
-    double mx = 0.0, my = 0.0, mz = 0.0;
+      unsigned long long fb[K];
+      knn_exact<K, CellT>(G, coarse_view(cs, 0, c), coarse_view(cs, 1, c), p.x, p.y, p.z, fine_rings, fb);
 #pragma unroll
-    for (int j = 0; j < K; j++) {
-      if (j < k) {
-        unsigned idx = (unsigned)(tk.key[j] & 0xFFFFFFFFull);
-        if (idx >= (unsigned)n) idx = self;  // non-finite query: no neighbour found
-        const float4 nb = opts[idx];
-        mx = dadd(mx, (double)nb.x);
-        my = dadd(my, (double)nb.y);
-        mz = dadd(mz, (double)nb.z);
-      }
+      for (int j = 0; j < K; j++) nbr[j * nstride] = (CellT)(unsigned)(fb[j] & 0xFFFFFFFFull);
+    }
+    // (an entry that is not a valid index - all ones, truncated to CellT - marks "no neighbour": non-finite query)
+
+    // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324); rolled loops over the stored list
+    double mx = 0.0, my = 0.0, mz = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < k; j++) {
+      unsigned idx = (unsigned)nbr[j * nstride];
+      if (idx >= (unsigned)n) idx = self;
+      const float4 nb = opts[idx];
+      mx = dadd(mx, (double)nb.x);
+      my = dadd(my, (double)nb.y);
+      mz = dadd(mz, (double)nb.z);
     }
     mx = mx / inv_div; my = my / inv_div; mz = mz / inv_div;
     Sym3 cov{0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      if (j < k) {
-        unsigned idx = (unsigned)(tk.key[j] & 0xFFFFFFFFull);
-        if (idx >= (unsigned)n) idx = self;
-        const float4 nb = opts[idx];
-        const double dx = dsub((double)nb.x, mx), dy = dsub((double)nb.y, my), dz = dsub((double)nb.z, mz);
-        cov.xx = dadd(cov.xx, dmul(dx, dx));
-        cov.xy = dadd(cov.xy, dmul(dx, dy));
-        cov.xz = dadd(cov.xz, dmul(dx, dz));
-        cov.yy = dadd(cov.yy, dmul(dy, dy));
-        cov.yz = dadd(cov.yz, dmul(dy, dz));
-        cov.zz = dadd(cov.zz, dmul(dz, dz));
-      }
+#pragma unroll 4
+    for (int j = 0; j < k; j++) {
+      unsigned idx = (unsigned)nbr[j * nstride];
+      if (idx >= (unsigned)n) idx = self;
+      const float4 nb = opts[idx];
+      const double dx = dsub((double)nb.x, mx), dy = dsub((double)nb.y, my), dz = dsub((double)nb.z, mz);
+      cov.xx = dadd(cov.xx, dmul(dx, dx));
+      cov.xy = dadd(cov.xy, dmul(dx, dy));
+      cov.xz = dadd(cov.xz, dmul(dx, dz));
+      cov.yy = dadd(cov.yy, dmul(dy, dy));
+      cov.yz = dadd(cov.yz, dmul(dy, dz));
+      cov.zz = dadd(cov.zz, dmul(dz, dz));
     }
     cov.xx /= inv_div; cov.xy /= inv_div; cov.xz /= inv_div; cov.yy /= inv_div; cov.yz /= inv_div; cov.zz /= inv_div;
     const Sym3 r = regularize(cov, method);
@@ -160,9 +205,11 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
     cs.cov2[base + q] = make_double2(r.yz, r.zz);
     if (knn_out) {
       int* row = knn_out + ((size_t)base + self) * k;
-#pragma unroll
-      for (int j = 0; j < K; j++)
-        if (j < k) row[j] = (int)(unsigned)(tk.key[j] & 0xFFFFFFFFull);
+#pragma unroll 1
+      for (int j = 0; j < k; j++) {
+        const unsigned idx = (unsigned)nbr[j * nstride];
+        row[j] = idx < (unsigned)n ? (int)idx : -1;
+      }
     }
   }
 }
@@ -170,12 +217,18 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
 template <int K>
 cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm, int* knn_out,
                      cudaStream_t stream) {
+  // dynamic shared memory: [staged grid | per-thread neighbour lists: K entries of 2 (staged) or 4 bytes]
   if (staged) {
-    cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    const size_t idx_off = (smem_bytes + 15) & ~(size_t)15;
+    const size_t total = idx_off + sizeof(uint16_t) * K * kKnnThreads;
+    cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
     if (e != cudaSuccess) return e;
-    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, smem_bytes, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, knn_out);
+    knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, (int)idx_off, knn_out);
   } else {
-    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, 0, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, knn_out);
+    const size_t total = sizeof(unsigned) * K * kKnnThreads;
+    cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+    if (e != cudaSuccess) return e;
+    knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, 0, knn_out);
   }
   return cudaGetLastError();
 }

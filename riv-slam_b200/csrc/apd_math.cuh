@@ -118,14 +118,32 @@ APD_HD Sym3 inverse(const Sym3& a) {
 // the whole decomposition stays in registers. Every operation rounds once (dmul/dadd/dsub), in the
 // same order as the CPU oracle (oracle/linalg.hpp sym_eig3), so both follow the same rotation
 // sequence bit for bit even on ill-conditioned neighbourhoods.
+// The rotation angle of one Jacobi step: the divisions and square roots expand to a few hundred SASS
+// instructions, so the three rotations of a sweep share ONE out-of-line copy (instruction-cache footprint of
+// the kNN + covariance kernel); the cheap application of the rotation stays inline.
+struct JacobiCS {
+  double c, s, tapq;
+};
+#ifdef __CUDACC__
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+JacobiCS jacobi_cs(double app, double aqq, double apq) {
+  const double theta = dsub(aqq, app) / dmul(2.0, apq);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / dadd(fabs(theta), sqrt(dadd(dmul(theta, theta), 1.0)));
+  JacobiCS r;
+  r.c = 1.0 / sqrt(dadd(dmul(t, t), 1.0));
+  r.s = dmul(t, r.c);
+  r.tapq = dmul(t, apq);
+  return r;
+}
+
 APD_HD void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq,
                        double& v0p, double& v0q, double& v1p, double& v1q, double& v2p, double& v2q) {
   if (apq == 0.0) return;
-  const double theta = dsub(aqq, app) / dmul(2.0, apq);
-  const double t = (theta >= 0.0 ? 1.0 : -1.0) / dadd(fabs(theta), sqrt(dadd(dmul(theta, theta), 1.0)));
-  const double c = 1.0 / sqrt(dadd(dmul(t, t), 1.0));
-  const double s = dmul(t, c);
-  const double tapq = dmul(t, apq);
+  const JacobiCS r = jacobi_cs(app, aqq, apq);
+  const double c = r.c, s = r.s, tapq = r.tapq;
   app = dsub(app, tapq);
   aqq = dadd(aqq, tapq);
   apq = 0.0;

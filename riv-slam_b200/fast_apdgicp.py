@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libapdgicp_b200.so")
+LIB_PATH = os.environ.get("APDGICP_B200_LIB") or os.path.join(_PKG, "libapdgicp_b200.so")  # the override serves kernel-variant experiments
 
 # fast_gicp::RegularizationMethod (gicp/gicp_settings.hpp:6)
 NONE, MIN_EIG, NORMALIZED_MIN_EIG, PLANE, FROBENIUS = range(5)
