@@ -227,6 +227,7 @@ struct CountWithin {
   int count;
   __device__ __forceinline__ float bound2() const { return __int_as_float(0x7f800000); }
   __device__ __forceinline__ void offer(float d2, unsigned, int) { count += ((double)d2 <= r2) ? 1 : 0; }
+  __device__ __forceinline__ void end_run() {}
 };
 
 __global__ void radius_flag_kernel(CloudSetView cs, double r2, float r2_up, int min_pts, unsigned char* __restrict__ flag) {
