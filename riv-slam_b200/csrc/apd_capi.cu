@@ -96,7 +96,7 @@ struct DevBuf {
 struct apd_cloudset_s {
   int n_clouds = 0;
   long long total = 0;
-  int max_n = 0, min_n = 0;
+  int max_n = 0, min_n = 0, max_cap = 0;
   long long total_cells = 0;
   std::vector<int> h_off;
   DevBuf pt_off, cell_off, pts, spts, cells, grid, cov0, cov1, cov2, cell_cap, tiles_build, tiles_knn, inv0;
@@ -164,6 +164,7 @@ struct apd_context {
   int max_teams_opt = 0;  // 0 = as many as fit
   int knn_packed = 1;
   int no_fused_build = 0;
+  int no_smem_build = 0;
   double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
   // scratch (grow-only)
@@ -274,6 +275,8 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
     }
     need_max = 0;
   }
+  cs->max_cap = 0;
+  for (int c = 0; c < nc; c++) cs->max_cap = std::max(cs->max_cap, cap[c]);
   cs->staged = staged && nc > 0;
   cs->staged_smem = (need_max + 15) & ~(size_t)15;
   long long off = 0;
@@ -395,7 +398,10 @@ int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
       cursor[l + 1] = h->ws_cursor.as<unsigned>() + off;
       off += (size_t)cs->c_total_cells[l];
     }
-    CK(launch_grid_build_fused(cs->view(), cap, cellid, cursor, h->stream, &h->stats));
+    // shared-memory build when the largest cloud's sorted points and fine cell table fit one CTA
+    size_t build_smem = sizeof(float4) * (size_t)cs->max_n + sizeof(unsigned) * ((size_t)cs->max_cap + 4) + 16;
+    if (build_smem + 2048 > h->smem_optin || h->no_smem_build) build_smem = 0;
+    CK(launch_grid_build_fused(cs->view(), cap, cellid, cursor, build_smem, h->stream, &h->stats));
     cs->grid_built = true;
     return APD_OK;
   }
@@ -760,6 +766,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "max_teams") h->max_teams_opt = (int)value;
   else if (n == "knn_packed") h->knn_packed = value != 0;
   else if (n == "fused_build") h->no_fused_build = value == 0;
+  else if (n == "smem_build") h->no_smem_build = value == 0;
   else if (n == "fitness_max_range") h->fitness_max_range = value;
   else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);

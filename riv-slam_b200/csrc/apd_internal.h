@@ -179,7 +179,7 @@ cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, 
                               long long total_cells, bool finest_level, cudaStream_t stream, LaunchStats* st);
 // all pyramid levels of every cloud in ONE launch (clouds small enough for one CTA per cloud and level)
 cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap[1 + kCoarseLevels], int* const cellid[1 + kCoarseLevels],
-                                    unsigned* const cursor[1 + kCoarseLevels], cudaStream_t stream, LaunchStats* st);
+                                    unsigned* const cursor[1 + kCoarseLevels], size_t smem_bytes /*0: global-memory version*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,
