@@ -92,7 +92,7 @@ __device__ __forceinline__ float dec_f(unsigned u) { return __uint_as_float((u &
 
 __global__ void __launch_bounds__(kPT) voxel_grid_kernel(const float4* __restrict__ in, const int* __restrict__ n_in_dev, int n_in_host, float leaf, VoxelWs ws,
                                                          float4* __restrict__ out, int* __restrict__ n_out) {
-  extern __shared__ unsigned s_dyn[];   // 16 * kPT digit counters / offsets
+  __shared__ unsigned s_hist[kPT / 32][256];  // per-warp digit histograms / scatter cursors
   __shared__ unsigned s_warp[33];
   __shared__ unsigned s_box[6];
   __shared__ int s_minb[3], s_mul[3], s_small;
@@ -169,26 +169,56 @@ __global__ void __launch_bounds__(kPT) voxel_grid_kernel(const float4* __restric
   __syncthreads();
   const unsigned maxkey = s_maxkey;
 
-  // stable LSD radix sort, 4 bits per pass, every thread owns a contiguous segment (stability)
+  // Stable LSD radix sort, 8 bits per pass. Every warp owns a contiguous band of 32-element rows (coalesced
+  // loads and stores) and a private 256-bin histogram; bins are ranked digit-major / warp-minor, and inside a
+  // row the lanes that share a digit are ordered by lane (__match_any_sync), so equal keys keep their input order.
   unsigned *ka = ws.key_a, *va = ws.val_a, *kb = ws.key_b, *vb = ws.val_b;
-  const int seg = (n + kPT - 1) / kPT;
-  const int j0 = min(tid * seg, n), j1 = min(j0 + seg, n);
-  for (int shift = 0; shift < 32 && (maxkey >> shift) != 0u; shift += 4) {
-#pragma unroll
-    for (int d = 0; d < 16; d++) s_dyn[d * kPT + tid] = 0u;
-    for (int j = j0; j < j1; j++) s_dyn[((ka[j] >> shift) & 15u) * kPT + tid]++;
-    unsigned carry = 0u;
-    for (int d = 0; d < 16; d++) {
-      unsigned total;
-      const unsigned ex = block_excl_scan(s_dyn[d * kPT + tid], s_warp, &total);
-      s_dyn[d * kPT + tid] = carry + ex;
-      carry += total;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int rows = (n + 31) >> 5;
+  const int band = (rows + (kPT >> 5) - 1) / (kPT >> 5);
+  const int r0 = min(warp * band, rows), r1 = min(r0 + band, rows);
+  for (int shift = 0; shift < 32 && (maxkey >> shift) != 0u; shift += 8) {
+    for (int d = lane; d < 256; d += 32) s_hist[warp][d] = 0u;
+    __syncwarp();
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      if (j < n) atomicAdd(&s_hist[warp][(ka[j] >> shift) & 255u], 1u);
     }
-    for (int j = j0; j < j1; j++) {
-      const unsigned k = ka[j];
-      const unsigned dst = s_dyn[((k >> shift) & 15u) * kPT + tid]++;
-      kb[dst] = k;
-      vb[dst] = va[j];
+    __syncthreads();
+    {  // exclusive scan of the 256 x 32 bins in (digit, warp) order: 8 consecutive bins per thread
+      unsigned loc[8], sum = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int e = tid * 8 + k;
+        loc[k] = s_hist[e & 31][e >> 5];
+        sum += loc[k];
+      }
+      unsigned total;
+      unsigned run = block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int e = tid * 8 + k;
+        s_hist[e & 31][e >> 5] = run;
+        run += loc[k];
+      }
+    }
+    __syncthreads();
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      const bool valid = j < n;
+      const unsigned k = valid ? ka[j] : 0u;
+      const unsigned d = valid ? ((k >> shift) & 255u) : (0x10000u + (unsigned)lane);
+      const unsigned same = __match_any_sync(0xFFFFFFFFu, d);
+      const unsigned rank = __popc(same & ((1u << lane) - 1u));
+      unsigned dst = 0u;
+      if (valid) {
+        dst = s_hist[warp][d] + rank;
+        kb[dst] = k;
+        vb[dst] = va[j];
+      }
+      __syncwarp();
+      if (valid && rank == 0u) s_hist[warp][d] += __popc(same);
+      __syncwarp();
     }
     __syncthreads();
     unsigned* t = ka; ka = kb; kb = t;
@@ -196,12 +226,22 @@ __global__ void __launch_bounds__(kPT) voxel_grid_kernel(const float4* __restric
   }
 
   // voxel heads -> segment starts (valid keys only), then one thread per voxel accumulates its points in order
-  unsigned heads = 0u;
-  for (int j = j0; j < j1; j++) heads += (ka[j] != 0xFFFFFFFFu && (j == 0 || ka[j] != ka[j - 1])) ? 1u : 0u;
+  unsigned carry = 0u;
+  for (int r = r0; r < r1; r++) {
+    const int j = (r << 5) + lane;
+    const bool head = j < n && ka[j] != 0xFFFFFFFFu && (j == 0 || ka[j] != ka[j - 1]);
+    carry += __popc(__ballot_sync(0xFFFFFFFFu, head));
+  }
   unsigned total;
-  unsigned pos = block_excl_scan(heads, s_warp, &total);
-  for (int j = j0; j < j1; j++)
-    if (ka[j] != 0xFFFFFFFFu && (j == 0 || ka[j] != ka[j - 1])) ws.seg_start[pos++] = j;
+  unsigned pos = block_excl_scan(lane == 0 ? carry : 0u, s_warp, &total);
+  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+  for (int r = r0; r < r1; r++) {
+    const int j = (r << 5) + lane;
+    const bool head = j < n && ka[j] != 0xFFFFFFFFu && (j == 0 || ka[j] != ka[j - 1]);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+    if (head) ws.seg_start[pos + __popc(m & ((1u << lane) - 1u))] = j;
+    pos += __popc(m);
+  }
   __syncthreads();
   const int n_vox = (int)total;
   // number of valid (finite) points = first index with key 0xFFFFFFFF; find it from the last segment
@@ -314,10 +354,7 @@ cudaError_t launch_distance_filter(const float4* in, int n, double near_t, doubl
 cudaError_t launch_voxel_grid(const float4* in, const int* n_in_dev, int n_in_host, float leaf, unsigned* ws_u32 /*4*n*/, int* seg_start /*n+1*/, float4* out, int* n_out,
                               cudaStream_t stream, LaunchStats* st) {
   VoxelWs ws{ws_u32, ws_u32 + n_in_host, ws_u32 + 2 * (size_t)n_in_host, ws_u32 + 3 * (size_t)n_in_host, seg_start};
-  const size_t smem = sizeof(unsigned) * 16 * kPT;
-  cudaError_t e = cudaFuncSetAttribute(voxel_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  voxel_grid_kernel<<<1, kPT, smem, stream>>>(in, n_in_dev, n_in_host, leaf, ws, out, n_out);
+  voxel_grid_kernel<<<1, kPT, 0, stream>>>(in, n_in_dev, n_in_host, leaf, ws, out, n_out);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -4,7 +4,7 @@
 "next" row 8(f)-1 (fitness scoring), each with the CPU oracle timed beside it on a bounded sample.
 One JSON line per measurement on stdout; run on the GPU box:
 
-    python scripts/bench_configs.py [c3] [c4] [c5] [fit]  > gpurun_out/configs.jsonl
+    python scripts/bench_configs.py [c1] [c3] [c4] [c5] [fit] [pre] [submap]  > gpurun_out/configs.jsonl
 """
 from __future__ import annotations
 
@@ -249,7 +249,70 @@ def fit():
          algorithmic_GBps=n * per * 32 / t / 1e9, cpu_scores_per_s=len(cpu) / sum(cpu), cpu_note="kd-tree build + single-threaded queries, as the reference")
 
 
+def pre():
+    """8(f)-4: distance filter -> 0.1 m voxel grid -> radius outlier removal of raw scans (preprocessing_nodelet.cpp:812-815)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_preprocess import raw_scan, oracle_pipeline
+    H = F.Handle(0)
+    for n in (5000, 20000):
+        clouds = [np.concatenate([raw_scan(100 + 7 * i + j, 5000) for j in range(n // 5000)]) for i in range(6)]
+        outs = [F.preprocess(H, c) for c in clouds]  # warm-up
+        ts = []
+        for _ in range(5):
+            for c in clouds:
+                t0 = time.perf_counter()
+                F.preprocess(H, c)
+                ts.append(time.perf_counter() - t0)
+        cpu = []
+        for c, g in zip(clouds[:3], outs[:3]):
+            t0 = time.perf_counter()
+            want = oracle_pipeline(c)
+            cpu.append(time.perf_counter() - t0)
+            assert want.tobytes() == g.tobytes()
+        emit(config="8(f)-4 preprocessing filters (distance, VoxelGrid 0.1 m, RadiusOutlierRemoval 0.8 m / 2)", points_in=int(len(clouds[0])), points_out=int(len(outs[0])),
+             gpu_ms_p50=float(np.median(ts) * 1e3), cpu_oracle_ms=float(np.median(cpu) * 1e3), bit_exact=True,
+             note="host PointXYZI-like array in, host array out, per call; the CPU oracle's outlier filter is a brute-force O(n^2) restatement, not PCL's kd-tree")
+
+
+def submap():
+    """8(f)-2: accumulate the last keyframes into the scan-to-map target (scan_matching_odometry_nodelet.cpp:606-616) on the device."""
+    from oracle import oracle as O
+    per = 5000
+    for n_key in (5, 20):
+        scans, poses = datagen.make_drive(3, 1, n_key + 1, per, workers=min(16, os.cpu_count() or 1))
+        clouds = [np.ascontiguousarray(np.concatenate([s[:, :3], np.full((len(s), 1), 1.0, np.float32)], axis=1)) for s in scans]
+        which = list(range(n_key))
+        rel = [np.linalg.inv(poses[i]) @ poses[n_key] for i in which]
+        reg = F.FastAPDGICP(0)
+        reg.handle().set_params(**LAUNCH_PARAMS)
+        H = reg.handle()
+        ks = F.CloudSet(H, clouds)
+        got = F.build_submap(H, ks, which, rel, 0.1, cache_key=1)
+        t_build = gpu_time(H, lambda: F.build_submap(H, ks, which, rel, 0.1, cache_key=0, want_cloud=False), reps=5)
+        t0 = time.perf_counter()
+        want = O.accumulate_submap([clouds[i] for i in which], rel, 0.1)
+        t_cpu = time.perf_counter() - t0
+        assert want.tobytes() == got.tobytes()
+
+        def host_path():  # what the reference does: build the submap on the host, hand it to setInputTarget
+            reg.setInputTarget(want, cache_key=0)
+            reg.computeCovariances()
+        def dev_path():
+            F.build_submap(H, ks, which, rel, 0.1, cache_key=0, want_cloud=False)
+            reg.computeCovariances()
+        reg.setInputSource(clouds[n_key])
+        host_path(); dev_path()
+        t_host = gpu_time(H, host_path, reps=5)
+        t_dev = gpu_time(H, dev_path, reps=5)
+        emit(config="8(f)-2 submap accumulation (transform + concatenate + VoxelGrid 0.1 m -> target)", keyframes=n_key, points_in=n_key * per, points_out=int(len(got)),
+             gpu_build_ms=t_build * 1e3, cpu_oracle_build_ms=t_cpu * 1e3, bit_exact=True,
+             target_ready_ms_device_resident=t_dev * 1e3, target_ready_ms_host_cloud_upload=t_host * 1e3,
+             reference_flow_ms=(t_cpu + t_host) * 1e3,
+             note="target_ready = submap + grid + kNN + covariances, i.e. until align can start; host_cloud_upload takes a submap that already exists on "
+                  "the host, reference_flow adds the CPU oracle's time to build it there (what the nodelet does before setInputTarget)")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c3", "c4", "fit", "c5"]
+    which = sys.argv[1:] or ["c1", "c3", "c4", "fit", "pre", "submap", "c5"]
     for w in which:
-        {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fit": fit}[w]()
+        {"c1": c1, "c3": c3, "c4": c4, "c5": c5, "fit": fit, "pre": pre, "submap": submap}[w]()
