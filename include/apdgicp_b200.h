@@ -204,6 +204,8 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
  * its rel_pose (row-major double[16], pcl::transformPointCloud in double), concatenated, then pcl::VoxelGrid if downsample_resolution > 0.
  * The result becomes the handle's TARGET without leaving the device (setInputTarget(keyframe_cloud_s2m), :615); out_xyzi (host, packed
  * x y z intensity, capacity out_capacity points, may be NULL) receives a copy. The 4th float of the set's points is taken as intensity. */
+/* Number of clouds and total number of points of a cloud set (sizes the out buffer of apd_build_submap). */
+int apd_cloudset_info(apd_cloudset cs, int32_t* n_clouds, int64_t* total_points);
 int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which, int n_sel, const double* rel_poses, double downsample_resolution,
                      uint64_t cache_key, float* out_xyzi, int out_capacity, int* n_out);
 

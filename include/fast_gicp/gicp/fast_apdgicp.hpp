@@ -103,6 +103,39 @@ public:
     tgt_dirty_ = true;
   }
 
+  // Scan-to-map target built on the device: what ScanMatchingOdometryNodelet does at
+  // scan_matching_odometry_nodelet.cpp:606-616 - transform the selected keyframe clouds by rel_pose (double),
+  // concatenate, pcl::VoxelGrid with leaf `downsample_resolution` (<= 0: no down-sampling), setInputTarget - in one
+  // call on a cloud set that already lives in HBM (apd_cloudset_create with sizeof(PointT) stride). The submap is
+  // returned as a PCL cloud (keyframe_cloud_s2m) and registered as the target WITHOUT being uploaded again.
+  typename pcl::PointCloud<PointTarget>::Ptr setInputTargetFromKeyframes(apd_cloudset keyframes, const std::vector<int>& which,
+                                                                         const std::vector<Eigen::Matrix4d>& rel_poses, double downsample_resolution) {
+    typename pcl::PointCloud<PointTarget>::Ptr cloud(new pcl::PointCloud<PointTarget>());
+    if (!handle_ || which.size() != rel_poses.size()) return cloud;
+    int64_t total = 0;
+    if (apd_cloudset_info(keyframes, nullptr, &total) != APD_OK) return cloud;
+    std::vector<double> poses(16 * which.size());
+    for (size_t k = 0; k < which.size(); k++)
+      for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) poses[16 * k + 4 * r + c] = rel_poses[k](r, c);
+    std::vector<float> xyzi(4 * (size_t)std::max<int64_t>(total, 1));
+    int n = 0;
+    if (apd_build_submap(handle_, keyframes, which.data(), (int)which.size(), poses.data(), downsample_resolution, reinterpret_cast<uint64_t>(cloud.get()),
+                         xyzi.data(), (int)total, &n) != APD_OK) {
+      std::fprintf(stderr, "[apdgicp_b200] build_submap failed: %s\n", apd_last_error(handle_));
+      return cloud;
+    }
+    cloud->resize(n);
+    for (int i = 0; i < n; i++) {
+      PointTarget& p = cloud->points[i];
+      p.x = xyzi[4 * i]; p.y = xyzi[4 * i + 1]; p.z = xyzi[4 * i + 2]; p.intensity = xyzi[4 * i + 3];
+    }
+    pcl::Registration<PointSource, PointTarget, Scalar>::setInputTarget(cloud);  // PCL's own bookkeeping (target_, tree_)
+    target_covs_.clear();
+    tgt_covs_injected_ = false;
+    tgt_dirty_ = false;  // the device already holds this cloud under the key cloud.get()
+    return cloud;
+  }
+
   // fast_apdgicp_impl.hpp:111-118
   virtual void setSourceCovariances(const CovarianceList& covs) { source_covs_ = covs; src_covs_injected_ = true; src_cov_dirty_ = true; }
   virtual void setTargetCovariances(const CovarianceList& covs) { target_covs_ = covs; tgt_covs_injected_ = true; tgt_cov_dirty_ = true; }

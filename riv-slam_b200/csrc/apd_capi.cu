@@ -1404,6 +1404,14 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
   return APD_OK;
 }
 
+int apd_cloudset_info(apd_cloudset cs, int32_t* n_clouds, int64_t* total_points) {
+  if (!cs) return APD_ERR_INVALID;
+  const apd_cloudset_s* s = deref(cs);
+  if (n_clouds) *n_clouds = s->n_clouds;
+  if (total_points) *total_points = s->total;
+  return APD_OK;
+}
+
 int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which, int n_sel, const double* rel_poses, double downsample_resolution, uint64_t cache_key,
                      float* out_xyzi, int out_capacity, int* n_out) {
   if (!h || !keyframes || !n_out || n_sel < 0 || (n_sel > 0 && (!which || !rel_poses))) return APD_ERR_INVALID;

@@ -109,6 +109,7 @@ _PROTOTYPES = {
     "apd_fitness_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _ip, _ip, _fp, C.c_int, C.c_double, _dp]),
     "apd_default_preprocess_params": (C.c_int, [C.POINTER(ApdPreprocessParams)]),
     "apd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(ApdPreprocessParams), C.c_void_p, _ip]),
+    "apd_cloudset_info": (C.c_int, [C.c_void_p, _ip, C.POINTER(C.c_int64)]),
     "apd_build_submap": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, _dp, C.c_double, C.c_uint64, C.c_void_p, C.c_int, _ip]),
     "apd_odometry_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_int, _fp, C.c_void_p]),
     "apd_synchronize": (C.c_int, [C.c_void_p]),

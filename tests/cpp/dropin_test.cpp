@@ -103,6 +103,31 @@ int main(int argc, char** argv) {
     gicp->align(*aligned);  // no source any more: PCL returns from initCompute (converged_ keeps its previous value)
     std::printf("cleared converged %d\n", gicp->hasConverged() ? 1 : 0);
   }
+  // scan-to-map: the submap of the first three scans, built on the device, becomes the target (SMO:606-616)
+  if (n_scans >= 4) {
+    auto gicp = std::make_shared<fast_gicp::FastAPDGICP<PointT, PointT>>();
+    gicp->setMaxCorrespondenceDistance(2.0);
+    gicp->setTransformationEpsilon(0.1);
+    gicp->setAzimuthVar(1.0);
+    std::vector<PointT> all;
+    std::vector<int32_t> off(1, 0);
+    for (int s = 0; s < 3; s++) {
+      all.insert(all.end(), scans[s]->points.begin(), scans[s]->points.end());
+      off.push_back((int32_t)all.size());
+    }
+    apd_cloudset ks = nullptr;
+    if (apd_cloudset_create(gicp->nativeHandle(), reinterpret_cast<const float*>(all.data()), (int)sizeof(PointT), off.data(), 3, APD_MEM_HOST, &ks) != APD_OK) return 3;
+    std::vector<Eigen::Matrix4d> rel(3, Eigen::Matrix4d::Identity());
+    rel[0](0, 3) = 0.30; rel[0](1, 3) = -0.02;  // made-up keyframe offsets; the Python side uses the same numbers
+    rel[1](0, 3) = 0.15; rel[1](1, 3) = 0.01;
+    auto submap = gicp->setInputTargetFromKeyframes(ks, std::vector<int>{0, 1, 2}, rel, 0.1);
+    gicp->setInputSource(scans[3]);
+    gicp->align(*aligned);
+    const auto Tm = gicp->getFinalTransformation();
+    std::printf("submap n %zu p0 %.9g %.9g %.9g %.9g converged %d T03 %.9g T13 %.9g T23 %.9g fitness %.17g\n", submap->size(), submap->points[0].x, submap->points[0].y,
+                submap->points[0].z, submap->points[0].intensity, gicp->hasConverged() ? 1 : 0, Tm(0, 3), Tm(1, 3), Tm(2, 3), gicp->lastFitnessScore());
+    apd_cloudset_destroy(gicp->nativeHandle(), ks);
+  }
   // loop-closure style call without a target: align must print and leave hasConverged() false
   pcl::Registration<PointT, PointT>::Ptr fresh = select_registration_method();
   fresh->setInputSource(scans[0]);

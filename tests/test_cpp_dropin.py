@@ -94,6 +94,22 @@ def test_dropin_matches_python_path_and_oracle(tmp_path):
     assert int(bwd[2]) == int(convb) and int(bwd[3]) == int(convb)
     assert float(bwd[5]) < 1e-6                      # swapped object == fresh object with injected covariances
     assert abs(float(bwd[7]) - Tb0[0, 3]) < 1e-4
+    # scan-to-map target built on the device from three keyframes (setInputTargetFromKeyframes)
+    from oracle import oracle as O
+    rel = [np.eye(4) for _ in range(3)]
+    rel[0][0, 3], rel[0][1, 3] = 0.30, -0.02
+    rel[1][0, 3], rel[1][1, 3] = 0.15, 0.01
+    want = O.accumulate_submap([np.ascontiguousarray(s[:, :4]) for s in scans[:3]], rel, 0.1)
+    sm = next(l for l in lines if l[0] == "submap")
+    assert int(sm[2]) == len(want)
+    assert np.array_equal(np.array(sm[4:8], dtype=np.float32), want[0])
+    om = Oracle(**LAUNCH_PARAMS)
+    om.set_source(scans[3]); om.set_target(want)
+    rc, Tm0, convm, itm = om.align()
+    assert int(sm[9]) == int(convm)
+    assert np.abs(np.array(sm[11:16:2], dtype=np.float64) - Tm0[:3, 3]).max() < 1e-4
+    fm = om.fitness()
+    assert abs(float(sm[17]) - fm) <= 1e-5 * fm
     # after clearSource() PCL's align returns from initCompute before touching converged_ (stale value, as in PCL)
     assert any(l[:2] == ["cleared", "converged"] for l in lines)
     assert ["notarget", "converged", "0"] in lines
