@@ -157,6 +157,11 @@ def c4():
     e2e()
     t_e2e = gpu_time(H, e2e, reps=2)
     lin, err, _ = H.work_counters()
+    # device-resident path: sets uploaded once, then grid + kNN + covariances ("prepare") and one align launch.
+    # prepare is idempotent, so it is timed on fresh sets after one warm-up round (first-use allocations).
+    S, T = F.CloudSet(H, (ps, os_)), F.CloudSet(H, (pt, ot))
+    S.prepare(); T.prepare(); H.synchronize()
+    S.destroy(); T.destroy()
     S, T = F.CloudSet(H, (ps, os_)), F.CloudSet(H, (pt, ot))
     t_prep = gpu_time(H, lambda: (S.prepare(), T.prepare()), reps=1)
     t_align = gpu_time(H, lambda: F.align_pairs(H, S, T), reps=2)
