@@ -116,11 +116,20 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_cores() -> int:
+    """Threads the CPU arm uses: every core this process may run on. torchrun exports OMP_NUM_THREADS=1, which must
+    not shrink the reference arm to one thread, so the count is taken from the affinity mask, not from OpenMP."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_registrations(scans, order, n_sample, threads, time_budget_s):
     """The CPU path on pairs 0..n_sample-1 of the same drive: kd-tree build + kNN/covariances once per
     scan, align + fitness per pair. Returns (registrations/s, pairs done, cores, per-pair seconds)."""
-    from oracle.oracle import Oracle, max_threads
-    cores = threads or max_threads()
+    from oracle.oracle import Oracle
+    cores = threads or host_cores()
     o = Oracle(num_threads=cores, **LAUNCH_PARAMS)
     per = []
     t_start = time.perf_counter()
@@ -153,8 +162,7 @@ def run_reference(args):
         return
     n_sample = min(args.pairs, args.cpu_sample)
     scans, order = make_workload(args.pairs, args.unique, 0, args.workers)
-    from oracle.oracle import max_threads
-    cores = max_threads()
+    cores = host_cores()
     rates = []
     for s in range(args.warmup + args.steps):
         rate, done, cores, per = cpu_registrations(scans, order, n_sample, cores, args.cpu_budget)
