@@ -28,4 +28,17 @@ print(res["status"], res["converged"])
 print(F.odometry_align(H, [src, tgt, src[:400], tgt[:350]])["iterations"])
 S = F.CloudSet(H, clouds[:3])
 print(F.fitness_pairs(H, S, S, src_idx=[0, 1], tgt_idx=[2, 2], max_range=4.0))
+# pre-processing filters and submap accumulation (single-CTA kernels with shared-memory histograms / warp votes)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_preprocess import raw_scan
+raw = raw_scan(5, 1500)
+print(len(F.preprocess(H, raw)), len(F.preprocess(H, raw, outlier_removal=0, downsample_resolution=0.25)), len(F.preprocess(H, raw, use_distance_filter=0, downsample_resolution=0.0)))
+xyzi = [np.ascontiguousarray(np.concatenate([c[:, :3], np.ones((len(c), 1), np.float32)], axis=1)) for c in (src, tgt, src[:400])]
+K = F.CloudSet(H, xyzi)
+print(len(F.build_submap(H, K, [0, 1, 2], [np.eye(4)] * 3, 0.1)), len(F.build_submap(H, K, [2, 0], [np.eye(4)] * 2, 0.0)))
+# fallback global-memory build (the shared-memory one is the default for these sizes)
+H2 = F.Handle(0)
+H2.set_params(**LAUNCH_PARAMS)
+H2.set_option("smem_build", 0)
+print(F.batch_align(H2, [src, tgt[:500]], [tgt, src])["iterations"])
 print("done")
