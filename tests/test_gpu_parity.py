@@ -389,6 +389,45 @@ def test_full_size_properties(pair5k):
     assert r4[0]["fitness"] < 1e-5
 
 
+def test_drive_parity_statistics():
+    """SURVEY 8(d) parity gates over a drive at the benchmark size: 96 consecutive 5000-point pairs (config C2, identity
+    guess) and the same pairs with chained guesses. Every pair: same converged flag and iteration count as the oracle,
+    transform within 1e-5 rad / 1e-4 m, fitness within 1e-5 relative."""
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import Handle, odometry_align
+    n_pairs = 96
+    scans, poses = datagen.make_drive(2, 5, n_pairs + 1, 5000, workers=8)
+    H = Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+    res = odometry_align(H, scans)
+    o = _oracle(LAUNCH_PARAMS)
+    ref, guesses = [], [np.eye(4, dtype=np.float32)]
+    for t in range(n_pairs):
+        if t == 0:
+            o.set_target(scans[0])
+        else:
+            o.swap()  # the previous source becomes the target with its covariances
+        o.set_source(scans[t + 1])
+        rc, T0, conv0, it0 = o.align()
+        ref.append((T0, conv0, it0, o.fitness()))
+        guesses.append(T0.astype(np.float32))  # constant-velocity guess for the next pair (SMO:461-465 without the ego-velocity term)
+    bad = []
+    for t, (T0, conv0, it0, f0) in enumerate(ref):
+        if bool(res[t]["converged"]) != conv0 or int(res[t]["iterations"]) != it0:
+            bad.append((t, int(res[t]["iterations"]), it0))
+        _assert_same_transform(res[t]["T"], T0)
+        assert abs(res[t]["fitness"] - f0) <= 1e-5 * f0
+    assert not bad, bad
+    # chained guesses: pair t starts from the oracle's result of pair t-1
+    res2 = odometry_align(H, scans, guesses=np.stack(guesses[:n_pairs]))
+    o2 = _oracle(LAUNCH_PARAMS)
+    for t in range(0, n_pairs, 4):
+        o2.set_source(scans[t + 1]); o2.set_target(scans[t])
+        rc, T0, conv0, it0 = o2.align(guesses[t])
+        assert bool(res2[t]["converged"]) == conv0 and int(res2[t]["iterations"]) == it0
+        _assert_same_transform(res2[t]["T"], T0)
+
+
 # ---------------------------------------------------------------- large clouds (configs C3 / C5)
 
 def test_large_clouds_grid_team():
