@@ -1,12 +1,14 @@
 // TEST INFRASTRUCTURE — CPU oracle for the FastAPDGICP hot path. Not part of the product.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 //
-// PARITY UNPINNED at the reference level: the reference holds no golden vector, known-answer test or
-// fixture for FastAPDGICP (its only test, fast_apdgicp/src/test/gicp_test.cpp:99-128, never builds
-// it and its data/ directory is absent), and the reference cannot be compiled here (PCL, Eigen,
-// FLANN, Boost are not installed). This file is a restatement written from the cited lines; it is
-// cross-checked by an independent numpy/LAPACK/cKDTree twin (oracle/pyref.py) and, where the mini
-// Eigen/PCL stand-ins allow, by the reference's own translation units (oracle/_ref, see Makefile).
+// PARITY: pinned for the nearest-neighbour search, UNPINNED beyond it. The reference holds no golden vector,
+// known-answer test or fixture for FastAPDGICP (its only test, fast_apdgicp/src/test/gicp_test.cpp:99-128, never
+// builds it and its data/ directory is absent), and FastAPDGICP cannot be compiled here (PCL, Eigen, FLANN, Boost
+// are not installed). The exact kd-tree the reference vendors (radar_graph_slam/include/scan_context/nanoflann.hpp,
+// nanoflann 1.3.2: FLANN's L2_Simple float metric) does compile from the reference tree (oracle/_ref, `make ref`,
+// oracle/ref_nanoflann.cpp) and pins the kNN / 1-NN results of this file (tests/test_reference_knn.py,
+// tests/golden/knn_nanoflann_v1.npz). Covariances, APD model, Mahalanobis, H/b and the LM loop are a restatement
+// written from the cited lines, cross-checked by an independent numpy/LAPACK twin (oracle/pyref.py) only.
 //
 // Restates, line by line (paths relative to /root/reference/fast_apdgicp/include/fast_gicp):
 //   FastAPDGICP            gicp/impl/fast_apdgicp_impl.hpp:14-363   (APD_I)

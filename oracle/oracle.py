@@ -286,3 +286,29 @@ def accumulate_submap(clouds, rel_poses, leaf=0.0):
     out = np.zeros_like(a)
     n = lib().oracle_accumulate_submap(_ptr(a, C.c_float), _ptr(off, C.c_int), len(clouds), _ptr(P, C.c_double), leaf, _ptr(out, C.c_float))
     return out[:n]
+
+
+# ---- oracle/_ref: the reference's own vendored exact kd-tree (nanoflann 1.3.2), see oracle/ref_nanoflann.cpp ----
+
+_REF_PATH = os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_PATH)
+
+
+def ref_nanoflann_knn(cloud, queries, k, leaf_size=10):
+    """kNN by the kd-tree the reference vendors (compiled from /root/reference by `make -C oracle ref`): (idx int32 (m, k), d2 float32 (m, k))."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(_REF_PATH)
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        L.ref_nanoflann_knn.argtypes = [fp, C.c_int, fp, C.c_int, C.c_int, C.c_int, ip, fp]
+        _ref = L
+    c = _f32(np.asarray(cloud)[:, :3])
+    q = _f32(np.asarray(queries)[:, :3])
+    idx = np.zeros((q.shape[0], k), dtype=np.int32)
+    d2 = np.zeros((q.shape[0], k), dtype=np.float32)
+    _ref.ref_nanoflann_knn(_ptr(c, C.c_float), c.shape[0], _ptr(q, C.c_float), q.shape[0], k, leaf_size, _ptr(idx, C.c_int), _ptr(d2, C.c_float))
+    return idx, d2
