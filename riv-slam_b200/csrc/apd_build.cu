@@ -253,22 +253,10 @@ struct FusedLevels {
   unsigned* cursor[1 + kCoarseLevels];    // scatter cursors (workspace, laid out like the level's cell table)
 };
 
-__global__ void __launch_bounds__(1024) build_fused_kernel(CloudSetView cs, FusedLevels L) {
-  __shared__ unsigned s_box[32][6];
-  __shared__ GridParams s_g;
-  __shared__ unsigned s_warp[32];
-  const int c = blockIdx.x, level = blockIdx.y;
+// Step 1 of both fused builds: bounding box of the cloud's finite points (block-wide), grid parameters from the box and
+// the level's cell budget (thread 0), published to the level's GridParams slot and returned to every thread.
+__device__ __forceinline__ GridParams block_grid_params(const float4* __restrict__ pts, int n, long long cap, GridParams* out_slot, unsigned (*s_box)[6], GridParams* s_g) {
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const int base = cs.pt_off[c];
-  const int n = cs.pt_off[c + 1] - base;
-  const float4* pts = cs.pts + base;
-  float4* spts = (level == 0 ? cs.spts : cs.coarse[level - 1].spts) + base;
-  const long long coff = level == 0 ? cs.cell_off[c] : cs.coarse[level - 1].cell_off[c];
-  unsigned* cells = (level == 0 ? cs.cells : cs.coarse[level - 1].cells) + coff;
-  unsigned* cursor = L.cursor[level] + coff;
-  int* cellid = L.cellid[level] + base;
-
-  // 1. bounding box of the finite points
   unsigned mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
   for (int i = tid; i < n; i += T) {
     const float4 p = pts[i];
@@ -299,11 +287,30 @@ __global__ void __launch_bounds__(1024) build_fused_kernel(CloudSetView cs, Fuse
       if (l > h) { lo[a] = 0.f; hi[a] = 0.f; }
       else { lo[a] = dec_f(l); hi[a] = dec_f(h); }
     }
-    s_g = make_grid_params(lo, hi, L.cap[level][c]);
-    (level == 0 ? cs.grid : cs.coarse[level - 1].grid)[c] = s_g;
+    *s_g = make_grid_params(lo, hi, cap);
+    *out_slot = *s_g;
   }
   __syncthreads();
-  const GridParams g = s_g;
+  return *s_g;
+}
+
+__global__ void __launch_bounds__(1024) build_fused_kernel(CloudSetView cs, FusedLevels L) {
+  __shared__ unsigned s_box[32][6];
+  __shared__ GridParams s_g;
+  __shared__ unsigned s_warp[32];
+  const int c = blockIdx.x, level = blockIdx.y;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int base = cs.pt_off[c];
+  const int n = cs.pt_off[c + 1] - base;
+  const float4* pts = cs.pts + base;
+  float4* spts = (level == 0 ? cs.spts : cs.coarse[level - 1].spts) + base;
+  const long long coff = level == 0 ? cs.cell_off[c] : cs.coarse[level - 1].cell_off[c];
+  unsigned* cells = (level == 0 ? cs.cells : cs.coarse[level - 1].cells) + coff;
+  unsigned* cursor = L.cursor[level] + coff;
+  int* cellid = L.cellid[level] + base;
+
+  // 1. bounding box of the finite points -> grid parameters
+  const GridParams g = block_grid_params(pts, n, L.cap[level][c], &(level == 0 ? cs.grid : cs.coarse[level - 1].grid)[c], s_box, &s_g);
   const int total = g.ncells + 1;
 
   // 2. zero the counters, 3. count
@@ -390,42 +397,8 @@ __global__ void __launch_bounds__(1024) build_fused_smem_kernel(CloudSetView cs,
   float4* s_pts = reinterpret_cast<float4*>(sm_raw);
   unsigned* s_arr = reinterpret_cast<unsigned*>(sm_raw + sizeof(float4) * (size_t)n);
 
-  // 1. bounding box of the finite points
-  unsigned mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
-  for (int i = tid; i < n; i += T) {
-    const float4 p = pts[i];
-    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
-      const unsigned e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        mn[a] = min(mn[a], e[a]);
-        mx[a] = max(mx[a], e[a]);
-      }
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
-    mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int a = 0; a < 3; a++) { s_box[warp][a] = mn[a]; s_box[warp][3 + a] = mx[a]; }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    float lo[3], hi[3];
-    for (int a = 0; a < 3; a++) {
-      unsigned l = 0xFFFFFFFFu, h = 0u;
-      for (int w = 0; w < (T >> 5); w++) { l = min(l, s_box[w][a]); h = max(h, s_box[w][3 + a]); }
-      if (l > h) { lo[a] = 0.f; hi[a] = 0.f; }
-      else { lo[a] = dec_f(l); hi[a] = dec_f(h); }
-    }
-    s_g = make_grid_params(lo, hi, L.cap[level][c]);
-    (level == 0 ? cs.grid : cs.coarse[level - 1].grid)[c] = s_g;
-  }
-  __syncthreads();
-  const GridParams g = s_g;
+  // 1. bounding box of the finite points -> grid parameters
+  const GridParams g = block_grid_params(pts, n, L.cap[level][c], &(level == 0 ? cs.grid : cs.coarse[level - 1].grid)[c], s_box, &s_g);
   const int E = g.ncells + 1;  // entries of the cell table
 
   // 2. zero the counters, 3. count

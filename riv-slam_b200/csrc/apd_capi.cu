@@ -99,9 +99,17 @@ struct apd_cloudset_s {
   int max_n = 0, min_n = 0, max_cap = 0;
   long long total_cells = 0;
   std::vector<int> h_off;
-  DevBuf pt_off, cell_off, pts, spts, cells, grid, cov0, cov1, cov2, cell_cap, tiles_build, tiles_knn, inv0;
+  DevBuf pts, spts, cells, grid, cov0, cov1, cov2, inv0;
+  // the small per-cloud tables live in ONE device block filled by one copy from pinned staging memory (cloudset_layout)
+  DevBuf tables;
+  int* d_pt_off = nullptr;
+  long long* d_cell_off = nullptr;
+  int* d_cell_cap = nullptr;
+  int4 *d_tiles_build = nullptr, *d_tiles_knn = nullptr;
+  long long* d_c_cell_off[kCoarseLevels] = {nullptr, nullptr};
+  int* d_c_cell_cap[kCoarseLevels] = {nullptr, nullptr};
   // coarse pyramid levels (cell budget / 64 and / 4096): own sorted copy, cell table and grid parameters
-  DevBuf c_spts[kCoarseLevels], c_cells[kCoarseLevels], c_grid[kCoarseLevels], c_cell_off[kCoarseLevels], c_cell_cap[kCoarseLevels];
+  DevBuf c_spts[kCoarseLevels], c_cells[kCoarseLevels], c_grid[kCoarseLevels];
   long long c_total_cells[kCoarseLevels] = {0, 0};
   int n_tiles_build = 0, n_tiles_knn = 0;
   bool grid_built = false, cov_valid = false;
@@ -109,9 +117,9 @@ struct apd_cloudset_s {
   bool staged = false;      // every cloud's grid fits the shared-memory staging area
   size_t staged_smem = 0;   // bytes needed for the largest cloud
   explicit apd_cloudset_s(const std::shared_ptr<Pool>& pool) {
-    for (DevBuf* b : {&pt_off, &cell_off, &pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &cell_cap, &tiles_build, &tiles_knn, &inv0}) b->pool = pool;
+    for (DevBuf* b : {&pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &inv0, &tables}) b->pool = pool;
     for (int l = 0; l < kCoarseLevels; l++)
-      for (DevBuf* b : {&c_spts[l], &c_cells[l], &c_grid[l], &c_cell_off[l], &c_cell_cap[l]}) b->pool = pool;
+      for (DevBuf* b : {&c_spts[l], &c_cells[l], &c_grid[l]}) b->pool = pool;
   }
   // the view the build kernels use to construct coarse level l (same points, that level's tables)
   CloudSetView level_view(int l) const {
@@ -119,15 +127,15 @@ struct apd_cloudset_s {
     v.spts = c_spts[l].as<float4>();
     v.cells = c_cells[l].as<unsigned>();
     v.grid = c_grid[l].as<GridParams>();
-    v.cell_off = c_cell_off[l].as<long long>();
+    v.cell_off = d_c_cell_off[l];
     return v;
   }
   CloudSetView view() const {
     CloudSetView v;
     v.n_clouds = n_clouds;
     v.total_points = (int)total;
-    v.pt_off = pt_off.as<int>();
-    v.cell_off = cell_off.as<long long>();
+    v.pt_off = d_pt_off;
+    v.cell_off = d_cell_off;
     v.pts = pts.as<float4>();
     v.spts = spts.as<float4>();
     v.cells = cells.as<unsigned>();
@@ -140,7 +148,7 @@ struct apd_cloudset_s {
       v.coarse[l].spts = c_spts[l].as<float4>();
       v.coarse[l].cells = c_cells[l].as<unsigned>();
       v.coarse[l].grid = c_grid[l].as<GridParams>();
-      v.coarse[l].cell_off = c_cell_off[l].as<long long>();
+      v.coarse[l].cell_off = d_c_cell_off[l];
     }
     return v;
   }
@@ -178,6 +186,10 @@ struct apd_context {
   std::vector<double> lm_trace;
   bool last_lin_valid = false;  // scratch slot 0 holds correspondences of the current src/tgt
   long long work_lin = 0, work_err = 0, work_pairs = 0;
+  // pinned staging buffer for small host->device table uploads (grow-only) and the event that guards its reuse
+  unsigned char* stage_host = nullptr;
+  size_t stage_cap = 0;
+  cudaEvent_t stage_ev = nullptr;
   apd_handle helper = nullptr;   // second stream/pool for pipelined batches (pipelined_align)
   long long helper_launches_seen = 0;
 };
@@ -238,6 +250,29 @@ DeviceParams device_params(const apd_params& p) {
 // shared memory a staged grid may take: the opt-in maximum minus the align kernel's static state and
 // minus room for the kNN kernel's per-thread neighbour lists (up to 32 two-byte entries per thread)
 size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem() - 512 - 32 * sizeof(uint16_t) * kKnnThreads; }
+
+// Copy `bytes` of small tables to the device through the handle's pinned staging buffer: `fill` writes them into the
+// buffer, one asynchronous copy moves them. The buffer is reused by the next call, so its previous copy must have
+// completed (an event, normally long signalled); no stream synchronisation is needed and the caller's own host
+// vectors may die at once.
+template <typename Fill>
+int stage_upload(apd_handle h, size_t bytes, Fill fill, void* dst) {
+  if (bytes == 0) return APD_OK;
+  if (!h->stage_ev) CK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(h->stage_ev));
+  if (bytes > h->stage_cap) {
+    if (h->stage_host) cudaFreeHost(h->stage_host);
+    h->stage_host = nullptr;
+    h->stage_cap = 0;
+    const size_t want = std::max<size_t>(bytes + bytes / 2, 64u << 10);
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->stage_host), want));
+    h->stage_cap = want;
+  }
+  fill(h->stage_host);
+  CK(cudaMemcpyAsync(dst, h->stage_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->stage_ev, h->stream));
+  return APD_OK;
+}
 
 // Build the device-side description of a ragged batch: offsets, per-cloud cell budgets, tile lists.
 int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
@@ -324,35 +359,56 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   cs->n_tiles_build = (int)tb.size();
   cs->n_tiles_knn = (int)tk.size();
 
-  CK(cs->pt_off.reserve(sizeof(int) * (nc + 1)));
-  CK(cs->cell_off.reserve(sizeof(long long) * (nc + 1)));
-  CK(cs->cell_cap.reserve(sizeof(int) * std::max(nc, 1)));
+  // one device block for the small tables, one copy from the handle's pinned staging buffer: a dozen synchronous
+  // copies from pageable vectors plus a stream synchronisation cost ~50 us per cloud set, most of setInputSource
+  struct Part { const void* src; size_t bytes; size_t off; };
+  Part parts[5 + 2 * kCoarseLevels];
+  int np_ = 0;
+  size_t off_b = 0;
+  auto add = [&](const void* src, size_t bytes) {
+    parts[np_] = Part{src, bytes, off_b};
+    off_b = (off_b + std::max<size_t>(bytes, 16) + 15) & ~(size_t)15;
+    return np_++;
+  };
+  const int i_pt = add(cs->h_off.data(), sizeof(int) * (nc + 1));
+  const int i_co = add(cell_off.data(), sizeof(long long) * (nc + 1));
+  const int i_cc = add(cap.data(), sizeof(int) * nc);
+  const int i_tb = add(tb.data(), sizeof(int4) * tb.size());
+  const int i_tk = add(tk.data(), sizeof(int4) * tk.size());
+  int i_lo[kCoarseLevels], i_lc[kCoarseLevels];
+  for (int l = 0; l < kCoarseLevels; l++) {
+    i_lo[l] = add(ccell_off[l].data(), sizeof(long long) * (nc + 1));
+    i_lc[l] = add(ccap[l].data(), sizeof(int) * nc);
+  }
+  CK(cs->tables.reserve(off_b));
+  unsigned char* dbase = cs->tables.as<unsigned char>();
+  cs->d_pt_off = reinterpret_cast<int*>(dbase + parts[i_pt].off);
+  cs->d_cell_off = reinterpret_cast<long long*>(dbase + parts[i_co].off);
+  cs->d_cell_cap = reinterpret_cast<int*>(dbase + parts[i_cc].off);
+  cs->d_tiles_build = reinterpret_cast<int4*>(dbase + parts[i_tb].off);
+  cs->d_tiles_knn = reinterpret_cast<int4*>(dbase + parts[i_tk].off);
+  for (int l = 0; l < kCoarseLevels; l++) {
+    cs->d_c_cell_off[l] = reinterpret_cast<long long*>(dbase + parts[i_lo[l]].off);
+    cs->d_c_cell_cap[l] = reinterpret_cast<int*>(dbase + parts[i_lc[l]].off);
+  }
+  int rc_stage = stage_upload(h, off_b, [&](unsigned char* host) {
+    for (int i = 0; i < np_; i++)
+      if (parts[i].bytes) memcpy(host + parts[i].off, parts[i].src, parts[i].bytes);
+  }, dbase);
+  if (rc_stage) return rc_stage;
   CK(cs->grid.reserve(sizeof(GridParams) * std::max(nc, 1)));
-  CK(cs->tiles_build.reserve(sizeof(int4) * std::max<size_t>(tb.size(), 1)));
-  CK(cs->tiles_knn.reserve(sizeof(int4) * std::max<size_t>(tk.size(), 1)));
   CK(cs->pts.reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
   CK(cs->spts.reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
   CK(cs->cov0.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
   CK(cs->cov1.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
   CK(cs->cov2.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
   CK(cs->cells.reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->total_cells, 1)));
-  // small tables: synchronous copies from stack/heap vectors are fine (the vectors die at return)
-  CK(cudaMemcpyAsync(cs->pt_off.p, cs->h_off.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(cs->cell_off.p, cell_off.data(), sizeof(long long) * (nc + 1), cudaMemcpyHostToDevice, h->stream));
-  if (nc) CK(cudaMemcpyAsync(cs->cell_cap.p, cap.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, h->stream));
-  if (!tb.empty()) CK(cudaMemcpyAsync(cs->tiles_build.p, tb.data(), sizeof(int4) * tb.size(), cudaMemcpyHostToDevice, h->stream));
-  if (!tk.empty()) CK(cudaMemcpyAsync(cs->tiles_knn.p, tk.data(), sizeof(int4) * tk.size(), cudaMemcpyHostToDevice, h->stream));
   CK(cs->inv0.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
   for (int l = 0; l < kCoarseLevels; l++) {
     CK(cs->c_spts[l].reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
     CK(cs->c_cells[l].reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->c_total_cells[l], 1)));
     CK(cs->c_grid[l].reserve(sizeof(GridParams) * std::max(nc, 1)));
-    CK(cs->c_cell_off[l].reserve(sizeof(long long) * (nc + 1)));
-    CK(cs->c_cell_cap[l].reserve(sizeof(int) * std::max(nc, 1)));
-    CK(cudaMemcpyAsync(cs->c_cell_off[l].p, ccell_off[l].data(), sizeof(long long) * (nc + 1), cudaMemcpyHostToDevice, h->stream));
-    if (nc) CK(cudaMemcpyAsync(cs->c_cell_cap[l].p, ccap[l].data(), sizeof(int) * nc, cudaMemcpyHostToDevice, h->stream));
   }
-  CK(cudaStreamSynchronize(h->stream));
   return APD_OK;
 }
 
@@ -388,12 +444,12 @@ int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
     const int* cap[1 + kCoarseLevels];
     int* cellid[1 + kCoarseLevels];
     unsigned* cursor[1 + kCoarseLevels];
-    cap[0] = cs->cell_cap.as<int>();
+    cap[0] = cs->d_cell_cap;
     cellid[0] = h->ws_cellid.as<int>();
     cursor[0] = h->ws_cursor.as<unsigned>();
     size_t off = (size_t)cs->total_cells;
     for (int l = 0; l < kCoarseLevels; l++) {
-      cap[l + 1] = cs->c_cell_cap[l].as<int>();
+      cap[l + 1] = cs->d_c_cell_cap[l];
       cellid[l + 1] = h->ws_cellid.as<int>() + np * (l + 1);
       cursor[l + 1] = h->ws_cursor.as<unsigned>() + off;
       off += (size_t)cs->c_total_cells[l];
@@ -409,9 +465,9 @@ int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
   CK(h->ws_cellid.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
   CK(h->ws_cursor.reserve(sizeof(unsigned) * (size_t)cs->total_cells));
   BuildWorkspace ws{h->ws_bbox.as<unsigned>(), h->ws_cellid.as<int>(), h->ws_cursor.as<unsigned>()};
-  CK(launch_grid_build(cs->view(), ws, cs->tiles_build.as<int4>(), cs->n_tiles_build, cs->cell_cap.as<int>(), cs->total_cells, true, h->stream, &h->stats));
+  CK(launch_grid_build(cs->view(), ws, cs->d_tiles_build, cs->n_tiles_build, cs->d_cell_cap, cs->total_cells, true, h->stream, &h->stats));
   for (int l = 0; l < kCoarseLevels; l++)
-    CK(launch_grid_build(cs->level_view(l), ws, cs->tiles_build.as<int4>(), cs->n_tiles_build, cs->c_cell_cap[l].as<int>(), cs->c_total_cells[l], false, h->stream,
+    CK(launch_grid_build(cs->level_view(l), ws, cs->d_tiles_build, cs->n_tiles_build, cs->d_c_cell_cap[l], cs->c_total_cells[l], false, h->stream,
                          &h->stats));
   cs->grid_built = true;
   return APD_OK;
@@ -428,7 +484,7 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
   DeviceParams dp = device_params(h->prm);
   dp.knn_packed = h->knn_packed;
   dp.knn_fine_rings = h->knn_fine_rings;
-  CK(launch_knn_cov(cs->view(), cs->tiles_knn.as<int4>(), cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
+  CK(launch_knn_cov(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
   cs->cov_reg = h->prm.regularization;
@@ -725,6 +781,8 @@ int apd_destroy(apd_handle h) {
   h->src.reset();
   h->tgt.reset();
   if (h->helper) apd_destroy(h->helper);
+  if (h->stage_host) cudaFreeHost(h->stage_host);
+  if (h->stage_ev) cudaEventDestroy(h->stage_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return APD_OK;
