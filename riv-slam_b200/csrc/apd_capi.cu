@@ -187,9 +187,9 @@ struct apd_context {
   bool last_lin_valid = false;  // scratch slot 0 holds correspondences of the current src/tgt
   long long work_lin = 0, work_err = 0, work_pairs = 0;
   // pinned staging buffer for small host->device table uploads (grow-only) and the event that guards its reuse
-  unsigned char* stage_host = nullptr;
-  size_t stage_cap = 0;
-  cudaEvent_t stage_ev = nullptr;
+  unsigned char* stage_host[2] = {nullptr, nullptr};  // slot 0: cloud-set tables, slot 1: small point uploads
+  size_t stage_cap[2] = {0, 0};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   apd_handle helper = nullptr;   // second stream/pool for pipelined batches (pipelined_align)
   long long helper_launches_seen = 0;
 };
@@ -256,21 +256,21 @@ size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem()
 // completed (an event, normally long signalled); no stream synchronisation is needed and the caller's own host
 // vectors may die at once.
 template <typename Fill>
-int stage_upload(apd_handle h, size_t bytes, Fill fill, void* dst) {
+int stage_upload(apd_handle h, int slot, size_t bytes, Fill fill, void* dst) {
   if (bytes == 0) return APD_OK;
-  if (!h->stage_ev) CK(cudaEventCreateWithFlags(&h->stage_ev, cudaEventDisableTiming));
-  else CK(cudaEventSynchronize(h->stage_ev));
-  if (bytes > h->stage_cap) {
-    if (h->stage_host) cudaFreeHost(h->stage_host);
-    h->stage_host = nullptr;
-    h->stage_cap = 0;
+  if (!h->stage_ev[slot]) CK(cudaEventCreateWithFlags(&h->stage_ev[slot], cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(h->stage_ev[slot]));
+  if (bytes > h->stage_cap[slot]) {
+    if (h->stage_host[slot]) cudaFreeHost(h->stage_host[slot]);
+    h->stage_host[slot] = nullptr;
+    h->stage_cap[slot] = 0;
     const size_t want = std::max<size_t>(bytes + bytes / 2, 64u << 10);
-    CK(cudaMallocHost(reinterpret_cast<void**>(&h->stage_host), want));
-    h->stage_cap = want;
+    CK(cudaMallocHost(reinterpret_cast<void**>(&h->stage_host[slot]), want));
+    h->stage_cap[slot] = want;
   }
-  fill(h->stage_host);
-  CK(cudaMemcpyAsync(dst, h->stage_host, bytes, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaEventRecord(h->stage_ev, h->stream));
+  fill(h->stage_host[slot]);
+  CK(cudaMemcpyAsync(dst, h->stage_host[slot], bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->stage_ev[slot], h->stream));
   return APD_OK;
 }
 
@@ -391,7 +391,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
     cs->d_c_cell_off[l] = reinterpret_cast<long long*>(dbase + parts[i_lo[l]].off);
     cs->d_c_cell_cap[l] = reinterpret_cast<int*>(dbase + parts[i_lc[l]].off);
   }
-  int rc_stage = stage_upload(h, off_b, [&](unsigned char* host) {
+  int rc_stage = stage_upload(h, 0, off_b, [&](unsigned char* host) {
     for (int i = 0; i < np_; i++)
       if (parts[i].bytes) memcpy(host + parts[i].off, parts[i].src, parts[i].bytes);
   }, dbase);
@@ -415,15 +415,25 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
 int cloudset_fill(apd_handle h, apd_cloudset_s* cs, const float* xyz, int stride_bytes, int mem) {
   const long long n = cs->total;
   if (n == 0) return APD_OK;
+  // a small host cloud (one scan) goes through the pinned staging buffer: a host memcpy plus a truly asynchronous copy
+  // instead of the driver's blocking pageable path
+  constexpr size_t kStageMax = 1u << 20;
   if (stride_bytes == 16) {
-    CK(cudaMemcpyAsync(cs->pts.p, xyz, sizeof(float4) * n, mem == APD_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    const size_t bytes = sizeof(float4) * (size_t)n;
+    if (mem == APD_MEM_HOST && bytes <= kStageMax) return stage_upload(h, 1, bytes, [&](unsigned char* host) { memcpy(host, xyz, bytes); }, cs->pts.p);
+    CK(cudaMemcpyAsync(cs->pts.p, xyz, bytes, mem == APD_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
     return APD_OK;
   }
   const float* dev_xyz = xyz;
   if (mem == APD_MEM_HOST) {
     const size_t bytes = (size_t)(n - 1) * stride_bytes + 12;
     CK(h->raw_upload.reserve(bytes + 16));
-    CK(cudaMemcpyAsync(h->raw_upload.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (bytes <= kStageMax) {
+      int rc = stage_upload(h, 1, bytes, [&](unsigned char* host) { memcpy(host, xyz, bytes); }, h->raw_upload.p);
+      if (rc) return rc;
+    } else {
+      CK(cudaMemcpyAsync(h->raw_upload.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     dev_xyz = h->raw_upload.as<float>();
   }
   CK(launch_pack_points(dev_xyz, stride_bytes / 4, n, cs->pts.as<float4>(), h->stream, &h->stats));
@@ -781,8 +791,10 @@ int apd_destroy(apd_handle h) {
   h->src.reset();
   h->tgt.reset();
   if (h->helper) apd_destroy(h->helper);
-  if (h->stage_host) cudaFreeHost(h->stage_host);
-  if (h->stage_ev) cudaEventDestroy(h->stage_ev);
+  for (int i = 0; i < 2; i++) {
+    if (h->stage_host[i]) cudaFreeHost(h->stage_host[i]);
+    if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
+  }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return APD_OK;
