@@ -396,7 +396,7 @@ def test_drive_parity_statistics():
     from riv_slam_b200 import datagen
     from riv_slam_b200.fast_apdgicp import Handle, odometry_align
     n_pairs = 96
-    scans, poses = datagen.make_drive(2, 5, n_pairs + 1, 5000, workers=8)
+    scans, poses = datagen.make_drive(2, 5, n_pairs + 1, 5000)  # generated in-process: no fork next to a live CUDA context
     H = Handle(0)
     H.set_params(**LAUNCH_PARAMS)
     res = odometry_align(H, scans)
