@@ -208,11 +208,16 @@ def main():
         run_reference(args)
         return
 
-    import torch
-    import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    P = args.pairs
+    # synthetic scans first: the generator forks worker processes, which must happen before this process owns a CUDA context
+    scans, order = make_workload(P, args.unique, rank, max(1, args.workers // max(1, min(world, 8))))   # each rank drives its own segment
+    host_np, off = to_pointxyzi(scans, order)
+
+    import torch
+    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -234,9 +239,6 @@ def main():
     L = H.L
     import ctypes as C
 
-    P = args.pairs
-    scans, order = make_workload(P, args.unique, rank, args.workers)   # each rank drives its own segment
-    host_np, off = to_pointxyzi(scans, order)
     host = torch.from_numpy(host_np).pin_memory()
     dev_pts = host.to(dev, non_blocking=False)
     res_dev = torch.zeros(P * 96, dtype=torch.uint8, device=dev)
