@@ -62,3 +62,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("CPU oracle", "").replace("the oracle", "").replace("oracle/linalg.hpp", ""), f
+
+
+def test_build_staleness_is_decided_by_content_hash(lib_path):
+    """A snapshot copied to the GPU box does not keep a usable mtime order: the library is stale only when the hash
+    of its sources and flags differs from the one stored beside it (an 8-rank bench once raced on a needless rebuild)."""
+    from riv_slam_b200 import build
+    assert os.path.exists(build.HASH_PATH)
+    assert not build.needs_build()
+    src = os.path.join(build.CSRC, build.SOURCES[0])
+    st = os.stat(src)
+    try:
+        os.utime(src, (st.st_atime, st.st_mtime + 3600))   # "newer" source, same content
+        assert not build.needs_build()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+    assert open(build.HASH_PATH).read().strip() == build._source_hash()
