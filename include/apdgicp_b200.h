@@ -184,15 +184,16 @@ int apd_fitness_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const in
  * the code defaults, the launch file overrides several: radar_graph_slam/launch/radar_graph_slam.launch:50-63). */
 typedef struct apd_preprocess_params {
   int32_t use_distance_filter;      /* preprocessing_nodelet.cpp:201 (true)                                   */
-  int32_t outlier_removal;          /* 0 = NONE, 1 = RADIUS (pcl::RadiusOutlierRemoval); STATISTICAL is not implemented */
+  int32_t outlier_removal;          /* 0 = NONE, 1 = RADIUS (pcl::RadiusOutlierRemoval), 2 = STATISTICAL (pcl::StatisticalOutlierRemoval, the nodelet's code default :166) */
   int32_t radius_min_neighbors;     /* :178 (2)                                                                */
-  int32_t reserved;
+  int32_t statistical_mean_k;       /* :168 (20); at most 31                                                    */
   double distance_near_thresh;      /* :202 (1.0)   */
   double distance_far_thresh;       /* :203 (100.0) */
   double z_low_thresh;              /* :204 (-5.0)  */
   double z_high_thresh;             /* :205 (20.0)  */
   double downsample_resolution;     /* :138 (0.1); <= 0 = downsample_method NONE; otherwise pcl::VoxelGrid with this leaf */
   double radius_radius;             /* :177 (0.8)   */
+  double statistical_stddev;        /* :169 (1.0)   */
 } apd_preprocess_params;
 int apd_default_preprocess_params(apd_preprocess_params* p);
 /* distance_filter -> downsample -> outlier_removal (preprocessing_nodelet.cpp:812-815) of one cloud on the GPU.

@@ -87,6 +87,7 @@ def lib():
         L.oracle_distance_filter.argtypes = [fp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, fp]
         L.oracle_voxel_grid.argtypes = [fp, C.c_int, C.c_float, fp]
         L.oracle_radius_outlier_removal.argtypes = [fp, C.c_int, C.c_double, C.c_int, fp]
+        L.oracle_statistical_outlier_removal.argtypes = [fp, C.c_int, C.c_int, C.c_double, fp]
         L.oracle_accumulate_submap.argtypes = [fp, ip, C.c_int, dp, C.c_float, fp]
         _lib = L
     return _lib
@@ -275,6 +276,13 @@ def radius_outlier_removal(cloud, radius, min_pts):
     a = _xyzi(cloud)
     out = np.zeros_like(a)
     n = lib().oracle_radius_outlier_removal(_ptr(a, C.c_float), a.shape[0], radius, min_pts, _ptr(out, C.c_float))
+    return out[:n]
+
+
+def statistical_outlier_removal(cloud, mean_k, stddev_mult):
+    a = _xyzi(cloud)
+    out = np.zeros_like(a)
+    n = lib().oracle_statistical_outlier_removal(_ptr(a, C.c_float), a.shape[0], mean_k, stddev_mult, _ptr(out, C.c_float))
     return out[:n]
 
 

@@ -229,6 +229,11 @@ int oracle_radius_outlier_removal(const float* xyzi, int n, double radius, int m
   std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
   return (int)r.size();
 }
+int oracle_statistical_outlier_removal(const float* xyzi, int n, int mean_k, double stddev_mult, float* out) {
+  const auto r = apd_oracle::statistical_outlier_removal(to_pts(xyzi, n), mean_k, stddev_mult);
+  std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
+  return (int)r.size();
+}
 int oracle_accumulate_submap(const float* xyzi, const int* offsets, int n_clouds, const double* rel_poses16, float leaf, float* out) {
   std::vector<std::vector<apd_oracle::PointI>> clouds(n_clouds);
   std::vector<const double*> poses(n_clouds);

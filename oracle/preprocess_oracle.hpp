@@ -120,6 +120,49 @@ inline std::vector<PointI> radius_outlier_removal(const std::vector<PointI>& in,
   return out;
 }
 
+// pcl::StatisticalOutlierRemoval (preprocessing_nodelet.cpp:165-174, the nodelet's code default when the rosparam is absent;
+// pcl/filters/impl/statistical_outlier_removal.hpp applyFilterIndices, PCL 1.10): mean distance of every point to its
+// mean_k nearest neighbours (the search asks for mean_k + 1 and skips the point itself), then
+// threshold = mean + stddev_mult * stddev over all points; a point is removed when its mean distance exceeds it.
+// Arithmetic as written there: dist_sum (double) += sqrt(nn_dists[k]) with nn_dists float (unqualified sqrt on a float
+// promotes to double with <cmath> alone, the convention taken here), distances[i] = float(dist_sum / mean_k),
+// sum (double) += distance, sq_sum (double) += distance * distance (a float product), both in index order.
+// Clouds with fewer than mean_k + 1 points are returned unchanged (the search cannot deliver mean_k neighbours).
+inline std::vector<PointI> statistical_outlier_removal(const std::vector<PointI>& in, int mean_k, double stddev_mult) {
+  const size_t n = in.size();
+  if (mean_k < 1 || n < (size_t)mean_k + 1) return in;
+  std::vector<float> distances(n, 0.f);
+  std::vector<float> d2(n);
+  int valid = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (!finite3(in[i])) continue;
+    for (size_t j = 0; j < n; j++) {
+      const float dx = in[i].x - in[j].x, dy = in[i].y - in[j].y, dz = in[i].z - in[j].z;
+      float s = dx * dx;
+      s = s + dy * dy;
+      s = s + dz * dz;
+      d2[j] = s;
+    }
+    std::partial_sort(d2.begin(), d2.begin() + mean_k + 1, d2.end());
+    double dist_sum = 0.0;
+    for (int k = 1; k < mean_k + 1; k++) dist_sum += std::sqrt((double)d2[k]);  // k = 0 is the query point
+    distances[i] = (float)(dist_sum / mean_k);
+    valid++;
+  }
+  double sum = 0.0, sq_sum = 0.0;
+  for (const float d : distances) {
+    sum += d;
+    sq_sum += d * d;
+  }
+  const double mean = sum / (double)valid;
+  const double variance = (sq_sum - sum * sum / (double)valid) / ((double)valid - 1);
+  const double threshold = mean + stddev_mult * std::sqrt(variance);
+  std::vector<PointI> out;
+  for (size_t i = 0; i < n; i++)
+    if (!((double)distances[i] > threshold)) out.push_back(in[i]);
+  return out;
+}
+
 // scan_matching_odometry_nodelet.cpp:606-616: keyframe clouds moved by rel_pose (double 4x4, row-major here) and concatenated
 inline std::vector<PointI> accumulate_submap(const std::vector<std::vector<PointI>>& clouds, const std::vector<const double*>& rel_poses) {
   std::vector<PointI> out;

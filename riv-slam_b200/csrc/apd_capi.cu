@@ -1399,6 +1399,8 @@ int apd_default_preprocess_params(apd_preprocess_params* p) {
   p->z_high_thresh = 20.0;
   p->downsample_resolution = 0.1;
   p->radius_radius = 0.8;
+  p->statistical_mean_k = 20;
+  p->statistical_stddev = 1.0;
   return APD_OK;
 }
 
@@ -1420,7 +1422,8 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
   if (stride_bytes < 16 || stride_bytes % 4) return fail(h, APD_ERR_INVALID, "stride_bytes must be a multiple of 4 and at least 16 (x, y, z, intensity)");
   if (intensity_offset_bytes < 12 || intensity_offset_bytes % 4 || intensity_offset_bytes + 4 > stride_bytes)
     return fail(h, APD_ERR_INVALID, "intensity_offset_bytes must address a float inside the record, after x, y, z");
-  if (p->outlier_removal < 0 || p->outlier_removal > 1) return fail(h, APD_ERR_UNSUPPORTED, "outlier_removal must be 0 (NONE) or 1 (RADIUS)");
+  if (p->outlier_removal < 0 || p->outlier_removal > 2) return fail(h, APD_ERR_UNSUPPORTED, "outlier_removal must be 0 (NONE), 1 (RADIUS) or 2 (STATISTICAL)");
+  if (p->outlier_removal == 2 && (p->statistical_mean_k < 1 || p->statistical_mean_k > 31)) return fail(h, APD_ERR_UNSUPPORTED, "statistical_mean_k must be in [1, 31]");
   if (p->outlier_removal == 1 && (p->radius_min_neighbors < 0 || !(p->radius_radius > 0))) return fail(h, APD_ERR_INVALID, "bad radius outlier parameters");
   if (n == 0) return APD_OK;
   if (!points || !out) return fail(h, APD_ERR_INVALID, "null point pointer");
@@ -1445,7 +1448,7 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
     std::swap(cur, other);
     cur_n = nd + 1;
   }
-  if (p->outlier_removal == 1) {
+  if (p->outlier_removal != 0) {
     int m = 0;
     CK(cudaMemcpyAsync(&m, cur_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1457,7 +1460,15 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
       if (rc) return rc;
       rc = cloudset_build_grid(h, cs.get());
       if (rc) return rc;
-      CK(launch_radius_flags(cs->view(), m, p->radius_radius, p->radius_min_neighbors, flag, h->stream, &h->stats));
+      if (p->outlier_removal == 1) {
+        CK(launch_radius_flags(cs->view(), m, p->radius_radius, p->radius_min_neighbors, flag, h->stream, &h->stats));
+      } else if (m >= p->statistical_mean_k + 1) {
+        CK(h->pp_seg.reserve(sizeof(float) * (size_t)m + 16));  // reused as the mean-distance array
+        CK(launch_statistical_flags(cs->view(), m, cur_n, p->statistical_mean_k, p->statistical_stddev, h->pp_seg.as<float>(),
+                                    reinterpret_cast<double*>(h->pp_n.as<int>() + 4), flag, h->stream, &h->stats));
+      } else {
+        CK(cudaMemsetAsync(flag, 1, (size_t)m, h->stream));  // fewer than mean_k + 1 points: returned unchanged
+      }
       CK(launch_compact(cur, flag, cur_n, other, nd + 2, h->stream, &h->stats));
       std::swap(cur, other);
       cur_n = nd + 2;

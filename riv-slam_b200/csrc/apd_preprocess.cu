@@ -286,6 +286,50 @@ __global__ void radius_flag_kernel(CloudSetView cs, double r2, float r2_up, int 
   flag[__float_as_uint(p.w)] = (v.count >= min_pts + 1) ? 1 : 0;
 }
 
+// pcl::StatisticalOutlierRemoval, first pass (statistical_outlier_removal.hpp applyFilterIndices): the mean distance of every
+// point to its mean_k nearest neighbours. The exact search keeps the 32 smallest (d2, index) keys; entries 1 .. mean_k are the
+// neighbours (entry 0 is the point itself), summed in ascending order as sqrt in double, stored as float in ORIGINAL order.
+__global__ void __launch_bounds__(256) stat_mean_dist_kernel(CloudSetView cs, int mean_k, float* __restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // position in the sorted order of cloud 0
+  const int n = cs.pt_off[1] - cs.pt_off[0];
+  if (i >= n) return;
+  GridView<unsigned> G;
+  G.g = cs.grid[0];
+  G.n = n;
+  G.spts = cs.spts;
+  G.cells = cs.cells + cs.cell_off[0];
+  const float4 p = cs.spts[i];
+  TopK<32> tk;
+  tk.init();
+  pyramid_search<unsigned, TopK<32>, true>(G, cs, 0, p.x, p.y, p.z, __int_as_float(0x7f800000), tk, kFineRingsKnn);
+  double dist_sum = 0.0;
+#pragma unroll
+  for (int k = 1; k < 32; k++)
+    if (k <= mean_k) dist_sum = dadd(dist_sum, sqrt((double)__uint_as_float((unsigned)(tk.key[k] >> 32))));
+  dist[__float_as_uint(p.w)] = (float)(dist_sum / (double)mean_k);
+}
+
+// second pass: mean and standard deviation of the distances, accumulated by ONE thread in index order (the sums are
+// order-dependent doubles; a few ten thousand additions), then the keep flag of every point
+__global__ void stat_threshold_kernel(const float* __restrict__ dist, const int* __restrict__ n_dev, double stddev_mult, double* __restrict__ thr) {
+  const int n = *n_dev;
+  double sum = 0.0, sq_sum = 0.0;
+  for (int i = 0; i < n; i++) {
+    const float d = dist[i];
+    sum = dadd(sum, (double)d);
+    sq_sum = dadd(sq_sum, (double)fmul(d, d));
+  }
+  const double mean = sum / (double)n;
+  const double variance = dsub(sq_sum, dmul(sum, sum) / (double)n) / dsub((double)n, 1.0);
+  *thr = dadd(mean, dmul(stddev_mult, sqrt(variance)));
+}
+
+__global__ void stat_flag_kernel(const float* __restrict__ dist, const int* __restrict__ n_dev, const double* __restrict__ thr, unsigned char* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_dev) return;
+  flag[i] = ((double)dist[i] > *thr) ? 0 : 1;
+}
+
 __global__ void __launch_bounds__(kPT) compact_kernel(const float4* __restrict__ in, const unsigned char* __restrict__ flag, const int* __restrict__ n_dev,
                                                       float4* __restrict__ out, int* __restrict__ n_out) {
   __shared__ unsigned s_warp[33];
@@ -365,6 +409,18 @@ cudaError_t launch_radius_flags(const CloudSetView& cs, int n, double radius, in
   float up = (float)r2;
   if ((double)up < r2) up = nextafterf(up, INFINITY);
   radius_flag_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cs, r2, up, min_pts, flag);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_statistical_flags(const CloudSetView& cs, int n, const int* n_dev, int mean_k, double stddev_mult, float* dist, double* thr, unsigned char* flag,
+                                     cudaStream_t stream, LaunchStats* st) {
+  if (n == 0) return cudaSuccess;
+  stat_mean_dist_kernel<<<(n + 255) / 256, 256, 0, stream>>>(cs, mean_k, dist);
+  APD_LAUNCH_CHECK();
+  stat_threshold_kernel<<<1, 1, 0, stream>>>(dist, n_dev, stddev_mult, thr);
+  APD_LAUNCH_CHECK();
+  stat_flag_kernel<<<(n + 255) / 256, 256, 0, stream>>>(dist, n_dev, thr, flag);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -53,9 +53,9 @@ class ApdResult(C.Structure):
 class ApdPreprocessParams(C.Structure):
     """apd_preprocess_params: the PreprocessingNodelet parameters (preprocessing_nodelet.cpp:137-205)."""
     _fields_ = [
-        ("use_distance_filter", C.c_int32), ("outlier_removal", C.c_int32), ("radius_min_neighbors", C.c_int32), ("reserved", C.c_int32),
+        ("use_distance_filter", C.c_int32), ("outlier_removal", C.c_int32), ("radius_min_neighbors", C.c_int32), ("statistical_mean_k", C.c_int32),
         ("distance_near_thresh", C.c_double), ("distance_far_thresh", C.c_double), ("z_low_thresh", C.c_double), ("z_high_thresh", C.c_double),
-        ("downsample_resolution", C.c_double), ("radius_radius", C.c_double),
+        ("downsample_resolution", C.c_double), ("radius_radius", C.c_double), ("statistical_stddev", C.c_double),
     ]
 
 

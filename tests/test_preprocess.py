@@ -39,7 +39,7 @@ def raw_scan(seed, n=3000, with_bad=True):
 
 
 def oracle_pipeline(cloud, use_distance_filter=1, distance_near_thresh=1.0, distance_far_thresh=100.0, z_low_thresh=-5.0, z_high_thresh=20.0,
-                    downsample_resolution=0.1, outlier_removal=1, radius_radius=0.8, radius_min_neighbors=2):
+                    downsample_resolution=0.1, outlier_removal=1, radius_radius=0.8, radius_min_neighbors=2, statistical_mean_k=20, statistical_stddev=1.0):
     from oracle import oracle as O
     c = cloud
     if use_distance_filter:
@@ -50,6 +50,8 @@ def oracle_pipeline(cloud, use_distance_filter=1, distance_near_thresh=1.0, dist
         c = c[np.isfinite(c[:, :3]).all(axis=1)]  # pcl::removeNaNFromPointCloud, preprocessing_nodelet.cpp:852-856
     if outlier_removal == 1:
         c = O.radius_outlier_removal(c, radius_radius, radius_min_neighbors)
+    elif outlier_removal == 2:
+        c = O.statistical_outlier_removal(c, statistical_mean_k, statistical_stddev)
     return c
 
 
@@ -95,6 +97,26 @@ def twin_radius_outlier(c, radius, min_pts):
     return c[~(radius * radius < kth)]
 
 
+def twin_statistical_outlier(c, mean_k, stddev_mult):
+    if len(c) < mean_k + 1:
+        return c
+    x = c[:, :3]
+    d = (x[:, None, :] - x[None, :, :]).astype(np.float32)
+    d2 = ((d[..., 0] * d[..., 0]).astype(np.float32) + (d[..., 1] * d[..., 1]).astype(np.float32)).astype(np.float32) + (d[..., 2] * d[..., 2]).astype(np.float32)
+    nn = np.sort(d2, axis=1)[:, 1:mean_k + 1].astype(np.float64)
+    acc = np.zeros(len(c))
+    for k in range(mean_k):            # ascending neighbours, one addition at a time
+        acc = acc + np.sqrt(nn[:, k])
+    dist = (acc / mean_k).astype(np.float32)
+    s = q = 0.0
+    for v in dist:                     # index order, like the reference loop
+        s += float(v)
+        q += float(np.float32(v * v))
+    n = len(c)
+    thr = s / n + stddev_mult * np.sqrt((q - s * s / n) / (n - 1.0))
+    return c[~(dist.astype(np.float64) > thr)]
+
+
 # ---------------------------------------------------------------- CPU: oracle vs twins
 
 @pytest.mark.parametrize("seed", [0, 1])
@@ -136,6 +158,17 @@ def test_oracle_radius_outlier_matches_twin(radius, min_pts):
     assert 0 < len(got) < len(c)
 
 
+@pytest.mark.parametrize("mean_k,mult", [(20, 1.0), (8, 0.5), (30, 1.2)])
+def test_oracle_statistical_outlier_matches_twin(mean_k, mult):
+    from oracle import oracle as O
+    c = O.voxel_grid(raw_scan(4, 700, with_bad=False), 0.1)
+    got, want = O.statistical_outlier_removal(c, mean_k, mult), twin_statistical_outlier(c, mean_k, mult)
+    assert np.array_equal(got, want)
+    assert 0 < len(got) < len(c)
+    few = c[:mean_k]                    # fewer than mean_k + 1 points: unchanged
+    assert np.array_equal(O.statistical_outlier_removal(few, mean_k, mult), few)
+
+
 def test_oracle_submap_matches_twin():
     from oracle import oracle as O
     from riv_slam_b200 import datagen
@@ -167,6 +200,8 @@ CASES = [
     dict(use_distance_filter=0, downsample_resolution=0.0, outlier_removal=0),
     dict(distance_near_thresh=2.0, distance_far_thresh=60.0, z_low_thresh=-2.0, z_high_thresh=6.0, downsample_resolution=0.25, radius_radius=0.5,
          radius_min_neighbors=5),
+    dict(outlier_removal=2),                                        # the nodelet's code defaults: STATISTICAL 20 / 1.0
+    dict(outlier_removal=2, statistical_mean_k=30, statistical_stddev=1.2, downsample_resolution=0.2),   # launch-file values of the statistical parameters
 ]
 
 
@@ -201,7 +236,10 @@ def test_preprocess_edge_cases():
     assert preprocess(H, lone).shape == (0, 4)                                          # fewer points than min_neighbors + 1
     assert np.array_equal(preprocess(H, lone, outlier_removal=0), lone)
     with pytest.raises(ApdError):
-        preprocess(H, lone, outlier_removal=2)                                          # STATISTICAL is not implemented: loud, no fallback
+        preprocess(H, lone, outlier_removal=3)                                          # unknown method: loud, no fallback
+    with pytest.raises(ApdError):
+        preprocess(H, lone, outlier_removal=2, statistical_mean_k=40)                   # more neighbours than the kernel keeps
+    assert np.array_equal(preprocess(H, lone, outlier_removal=2), lone)                 # fewer than mean_k + 1 points: unchanged
     # a 20k-point raw scan (several CTA-sized segments per thread)
     big = np.concatenate([raw_scan(40 + i, 5000) for i in range(3)])
     assert preprocess(H, big).tobytes() == oracle_pipeline(big).tobytes()
