@@ -109,7 +109,7 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
 // The passes only write per-point results, so the assignment does not influence any sum. A CTA with fewer
 // points than threads (cluster and grid teams) spreads them thinly over all its warps.
 struct ChunkPlan {
-  int chunk, lane;
+  int chunk, lane, begin_, end_;
 };
 __device__ __forceinline__ ChunkPlan chunk_begin(AlignShared& S, int begin, int end) {
   __syncthreads();
@@ -119,6 +119,8 @@ __device__ __forceinline__ ChunkPlan chunk_begin(AlignShared& S, int begin, int 
   ChunkPlan c;
   c.chunk = max(1, min(32, (end - begin + n_warps - 1) / n_warps));
   c.lane = threadIdx.x & 31;
+  c.begin_ = begin;
+  c.end_ = end;
   return c;
 }
 // returns false when the pass is over; otherwise i is this lane's point or -1 (idle lane of the chunk)
@@ -127,7 +129,9 @@ __device__ __forceinline__ bool chunk_next(AlignShared& S, const ChunkPlan& c, i
   if (c.lane == 0) i0 = atomicAdd(&S.next, c.chunk);
   i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
   if (i0 >= end) return false;
-  i = (c.lane < c.chunk && i0 + c.lane < end) ? i0 + c.lane : -1;
+  // handed out from the end of the cell-sorted order: the sparse high-z cells, whose searches are the long ones, go first
+  const int j = c.end_ - 1 - (i0 - c.begin_) - c.lane;
+  i = (c.lane < c.chunk && j >= c.begin_) ? j : -1;
   return true;
 }
 

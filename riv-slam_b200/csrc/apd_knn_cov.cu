@@ -134,8 +134,10 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
     if (lane == 0) q0 = atomicAdd(&s_next, qpw);
     q0 = __shfl_sync(0xFFFFFFFFu, q0, 0);
     if (q0 >= tile_end) break;
-    const int q = q0 + lane;
-    if (lane >= qpw || q >= tile_end) continue;
+    // chunks are handed out from the END of the cell-sorted order: the last cells (high z: clutter above the scene) are the
+    // sparse, expensive ones, and starting them last left them alone in the tail of the CTA
+    const int q = tile_end - 1 - (q0 - tile.y) - lane;
+    if (lane >= qpw || q < tile.y) continue;
     const float4 p = G.spts[q];
     const unsigned self = __float_as_uint(p.w);
     // Fast path: collect candidates in a packed 32-bit list (min/max insertion, see TopKPacked), then
