@@ -76,13 +76,17 @@ __device__ __noinline__ void knn_exact(GridView<CellT> G0, GridView<unsigned> G1
   for (int j = 0; j < K; j++) out[j] = tk.key[j];
 }
 
+constexpr int kMaxRankedChunks = 1024;  // tiles with more chunks than this are not ranked (6 KB of shared memory)
+
 template <int K, bool STAGED>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int packed_path, int fine_rings, int idx_off, int* __restrict__ knn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ int s_next;  // next unclaimed query of the tile
+  __shared__ int s_next;  // next unclaimed chunk of the tile
+  __shared__ unsigned s_span[kMaxRankedChunks];
+  __shared__ uint16_t s_order[kMaxRankedChunks];
   const int4 tile = tiles[blockIdx.x];
-  if (threadIdx.x == 0) s_next = tile.y;
+  if (threadIdx.x == 0) s_next = 0;
   const int c = tile.x;
   const int base = cs.pt_off[c];
   const int n = cs.pt_off[c + 1] - base;
@@ -129,15 +133,38 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   const int lane = threadIdx.x & 31;
   const int n_warps = blockDim.x >> 5;
   const int qpw = imax(1, imin(32, (tile.z + n_warps - 1) / n_warps));
+  // Longest chunk first: a chunk of adjacent queries that spreads over many cells lies in a sparse region, and its
+  // searches walk more rings (or fall back to the coarse levels). The chunks are ranked by that cell span and handed
+  // out in descending order, so the long ones do not end up alone in the tail of the CTA (with the plain sorted order
+  // the sparse high-z end came last: 12 % of the warp slots idle; from the end first: -7 %; ranked: see DESIGN.md).
+  const int n_chunks = (tile.z + qpw - 1) / qpw;
+  const bool ranked = n_chunks <= kMaxRankedChunks;
+  if (ranked) {
+    for (int ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
+      const float4 a = G.spts[tile.y + ch * qpw], b = G.spts[imin(tile.y + ch * qpw + qpw, tile_end) - 1];
+      s_span[ch] = (unsigned)(cell_index(g, b.x, b.y, b.z) - cell_index(g, a.x, a.y, a.z));
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < n_chunks; ch += blockDim.x) {
+      const unsigned mine = s_span[ch];
+      int rank = 0;
+      for (int j = 0; j < n_chunks; j++) {
+        const unsigned o = s_span[j];
+        rank += (o > mine || (o == mine && j < ch)) ? 1 : 0;
+      }
+      s_order[rank] = (uint16_t)ch;
+    }
+    __syncthreads();
+  }
   for (;;) {
-    int q0 = 0;
-    if (lane == 0) q0 = atomicAdd(&s_next, qpw);
-    q0 = __shfl_sync(0xFFFFFFFFu, q0, 0);
-    if (q0 >= tile_end) break;
-    // chunks are handed out from the END of the cell-sorted order: the last cells (high z: clutter above the scene) are the
-    // sparse, expensive ones, and starting them last left them alone in the tail of the CTA
-    const int q = tile_end - 1 - (q0 - tile.y) - lane;
-    if (lane >= qpw || q < tile.y) continue;
+    int k0 = 0;
+    if (lane == 0) k0 = atomicAdd(&s_next, 1);
+    k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+    if (k0 >= n_chunks) break;
+    // unranked (very many chunks): from the end of the cell-sorted order, where the sparse high-z cells are
+    const int chunk = ranked ? (int)s_order[k0] : n_chunks - 1 - k0;
+    const int q = tile.y + chunk * qpw + lane;
+    if (lane >= qpw || q >= tile_end) continue;
     const float4 p = G.spts[q];
     const unsigned self = __float_as_uint(p.w);
     // Fast path: collect candidates in a packed 32-bit list (min/max insertion, see TopKPacked), then
