@@ -8,5 +8,5 @@ python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_${tag}_refere
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv python bench.py --steps 2 --warmup 1 --unique 32 --no-cpu --latency-pairs 4 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:knn_cov_kernel -s 1 -c 1 -o $out/prof_knn_$tag -f python bench.py --steps 2 --warmup 1 --unique 32 --no-cpu --latency-pairs 4 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:align_kernel -s 1 -c 1 -o $out/prof_align_$tag -f python bench.py --steps 2 --warmup 1 --unique 32 --no-cpu --latency-pairs 4 > /dev/null 2>&1
-python scripts/bench_configs.py c1 c3 c4 fit pre submap c5 > $out/configs_$tag.jsonl 2> $out/configs_$tag.err; tail -c 300 $out/configs_$tag.err
+python scripts/bench_configs.py ${CONFIGS:-c1 c3 c4 fit pre submap c5} > $out/configs_$tag.jsonl 2> $out/configs_$tag.err; tail -c 300 $out/configs_$tag.err
 ls -la $out | tail -12
