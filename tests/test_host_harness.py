@@ -14,8 +14,8 @@ from oracle.oracle import knn_bruteforce
 _fp, _ip, _dp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_double)
 
 
-@pytest.fixture(scope="module")
-def hh():
+def load_harness():
+    """Compile (when stale) and load tests/_host_harness.so: the product's search header as plain C++."""
     src = os.path.join(ROOT, "tests", "host_harness.cpp")
     out = os.path.join(ROOT, "tests", "_host_harness.so")
     deps = [src] + [os.path.join(ROOT, "riv-slam_b200", "csrc", f) for f in ("apd_grid.cuh", "apd_math.cuh")]
@@ -31,6 +31,11 @@ def hh():
     L.hh_ldlt6.argtypes = [_dp, _dp, _dp]
     L.hh_so3_exp.argtypes = [_dp, _dp]
     return L
+
+
+@pytest.fixture(scope="module")
+def hh():
+    return load_harness()
 
 
 def _knn(L, cloud, q, k, cap):

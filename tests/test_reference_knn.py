@@ -112,3 +112,24 @@ def test_gpu_search_matches_reference_fixture():
     reg.evaluateCost(np.eye(4))
     corr, sq = reg.getCorrespondences()
     assert np.array_equal(sq, g["nn1_d2"]) and np.array_equal(corr, g["nn1_idx"].astype(np.int32))
+
+
+def test_product_search_header_matches_reference_kdtree():
+    """The product's own search code (riv-slam_b200/csrc/apd_grid.cuh, compiled as plain C++ by tests/host_harness.cpp:
+    the same source the GPU runs through nvcc) against the reference's vendored kd-tree, and against the frozen fixture
+    where oracle/_ref is not built."""
+    import test_host_harness as hh_mod
+    L = hh_mod.load_harness()
+    from oracle import oracle as O
+    g = np.load(GOLDEN)
+    src, tgt = g["src"], g["tgt"]
+    for cap in (6000, 400):   # cells_per_point 4 and a much coarser grid
+        idx, d2 = hh_mod._knn(L, src, src, 20, cap)
+        assert _same_lists(idx, d2, g["knn20_src_idx"].astype(np.int32), g["knn20_src_d2"]) > 0.94
+        idx, d2 = hh_mod._knn(L, tgt, g["queries_1nn"], 1, cap)
+        assert np.array_equal(d2[:, 0], g["nn1_d2"]) and np.array_equal(idx[:, 0], g["nn1_idx"].astype(np.int32))
+    if O.ref_available():
+        for name, cloud in _clouds().items():
+            ri, rd = O.ref_nanoflann_knn(cloud, cloud, 20)
+            idx, d2 = hh_mod._knn(L, cloud, cloud, 20, 4 * len(cloud))
+            _same_lists(idx, d2, ri, rd)
