@@ -104,6 +104,9 @@ int apd_get_params(apd_handle h, apd_params* p);
  * cache_key carries the reference's pointer-identity cache (fast_apdgicp_impl.hpp:91,102): a call
  * with the key the slot already holds returns at once; a key held by the OTHER slot moves its grid
  * and covariances across instead of recomputing them (results are identical). 0 = no caching.
+ * A key names DATA: the caller must not reuse a key for other points while a slot still holds it (the reference compares
+ * shared_ptrs it keeps alive; the drop-in class pushes every new cloud to the device at once, so the device only ever holds
+ * keys of clouds the object itself keeps alive).
  * mem says whether xyz is a host or a device pointer. ---- */
 int apd_set_source(apd_handle h, const float* xyz, int stride_bytes, int n, uint64_t cache_key, int mem);
 int apd_set_target(apd_handle h, const float* xyz, int stride_bytes, int n, uint64_t cache_key, int mem);
@@ -130,6 +133,17 @@ int apd_transform_source(apd_handle h, const float T[16], float* out_xyz, int ou
  * arbitrary pose (fast_apdgicp_impl.hpp:198-272). H, b may be NULL. */
 int apd_linearize(apd_handle h, const float pose[16], double H[36], double b[6], double* error);
 int apd_get_final_hessian(apd_handle h, double H[36]); /* getFinalHessian, lsq_registration_impl.hpp:45-47 */
+/* The protected hooks of the reference class at a DOUBLE pose (they take an Eigen::Isometry3d; row-major double[16]):
+ * FastAPDGICP::linearize (fast_apdgicp_impl.hpp:198-272: update_correspondences, then H, b, error; H and b may be NULL, which is
+ * also all update_correspondences (:133-194) needs) and FastAPDGICP::compute_error (:275-298: sum e^T M e at `pose` with the
+ * correspondences and Mahalanobis matrices the LAST linearize left behind). */
+int apd_linearize_d(apd_handle h, const double pose[16], double H[36], double b[6], double* error);
+int apd_compute_error(apd_handle h, const double pose[16], double* error);
+/* ScanMatchingOdometryNodelet::publish_scan_matching_status (radar_graph_slam/apps/scan_matching_odometry_nodelet.cpp:698-712): number of
+ * points of the aligned cloud (source moved by T; NULL = the last final transformation) whose nearest target point is STRICTLY closer
+ * than max_dist (k_sq_dists[0] < max_dist * max_dist; the nodelet uses 0.5 m). After apd_align and with T == NULL no search runs:
+ * the align kernel keeps every point's squared 1-NN distance at the final pose. */
+int apd_inlier_count(apd_handle h, const float T[16], double max_dist, int64_t* n_inliers);
 
 /* ---- state the reference exposes or that parity tests read. which: 0 = source, 1 = target ---- */
 int apd_compute_covariances(apd_handle h);             /* calculate_covariances for stale clouds, fast_apdgicp_impl.hpp:122-127 */
@@ -178,6 +192,17 @@ int apd_set_option(apd_handle h, const char* name, double value);
  * of `src` (cloud2) against cloud tgt_idx[i] of `tgt` (cloud1) at poses[i] (n_pairs*16 floats, NULL = identity). */
 int apd_fitness_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int32_t* src_idx, const int32_t* tgt_idx, const float* poses,
                       int n_pairs, double max_range, double* scores);
+
+/* "Next" row SURVEY.md §8(f)-3: LoopDetector::matching over ALL loop candidates (radar_graph_slam/src/radar_graph_slam/loop_detector.cpp:379-441,
+ * disabled in the reference because it is too slow on the CPU) as ONE launch: target = cloud keyframe_idx of `keyframes`
+ * (registration->setInputTarget(new_keyframe->cloud)), sources = clouds cand_idx[0..n) of `candidates` (NULL = 0..n-1), guesses = n*16 floats
+ * or NULL. Selection as at :415-423 (skip a candidate that did not converge or scores above the best so far: the earliest of equal scores
+ * wins) and :431-434 (no loop if the best score exceeds fitness_score_thresh): *best = position in cand_idx or -1, relative_pose = its
+ * final transformation, *best_score = its getFitnessScore(fitness_score_max_range) (DBL_MAX if none converged); records (may be NULL)
+ * receives all n results. The two cloud-set arguments may be the same set. */
+int apd_match_candidates(apd_handle h, apd_cloudset candidates, const int32_t* cand_idx, int n_candidates, apd_cloudset keyframes, int keyframe_idx,
+                         const float* guesses, double fitness_score_max_range, double fitness_score_thresh, int32_t* best, float relative_pose[16],
+                         double* best_score, apd_result* records);
 
 /* ---- "next" rows SURVEY.md §8(f)-4 and §8(f)-2: the filters in front of the scan matcher and the submap behind it ----
  * Parameters of PreprocessingNodelet (radar_graph_slam/apps/preprocessing_nodelet.cpp:137-205; apd_default_preprocess_params gives

@@ -2,24 +2,29 @@
 // (reference fast_apdgicp/include/fast_gicp/gicp/fast_apdgicp.hpp:33-110, impl/fast_apdgicp_impl.hpp).
 // Same class name, namespace, include path and public surface, so
 //   #include <fast_gicp/gicp/fast_apdgicp.hpp>
-// in radar_graph_slam/src/radar_graph_slam/registrations.cpp:38-50 picks this header up when this
+// in radar_graph_slam/src/radar_graph_slam/registrations.cpp:15,38-50 picks this header up when this
 // repository's include/ directory precedes the reference's, and the nodelets keep holding a
-// pcl::Registration<PointXYZI, PointXYZI>::Ptr. Header-only: everything forwards to the C ABI of
-// libapdgicp_b200.so (kNN, covariances, APD Mahalanobis, H/b reduction and the LM loop all run on
-// the GPU). There is no CPU fallback.
+// pcl::Registration<PointXYZI, PointXYZI>::Ptr. It is the ONLY header this repository puts on a reference
+// include path: <fast_gicp/gicp/gicp_settings.hpp> below is the reference's own file, and the GPU base class lives
+// under a name of its own (apdgicp_b200/lsq_registration_b200.hpp), so registrations.cpp:13-14 (the reference's
+// fast_gicp.hpp / fast_vgicp.hpp on the reference's LsqRegistration) keeps compiling and linking libfast_gicp.so
+// unchanged (tests/cpp/coexist_test.cpp). Header-only: everything forwards to the C ABI of libapdgicp_b200.so (kNN,
+// covariances, APD Mahalanobis, H/b reduction and the LM loop all run on the GPU). There is no CPU fallback.
 #pragma once
+#include <limits>
 #include <memory>
 #include <vector>
 
-#include <fast_gicp/gicp/lsq_registration.hpp>
+#include <fast_gicp/gicp/gicp_settings.hpp>
+#include <apdgicp_b200/lsq_registration_b200.hpp>
 
 namespace fast_gicp {
 
 template <typename PointSource, typename PointTarget>
-class FastAPDGICP : public LsqRegistration<PointSource, PointTarget> {
+class FastAPDGICP : public LsqRegistrationB200<PointSource, PointTarget> {
 public:
   using Scalar = float;
-  using Lsq = LsqRegistration<PointSource, PointTarget>;
+  using Lsq = LsqRegistrationB200<PointSource, PointTarget>;
   using Matrix4 = typename Lsq::Matrix4;
   using PointCloudSource = typename Lsq::PointCloudSource;
   using PointCloudSourcePtr = typename PointCloudSource::Ptr;
@@ -28,17 +33,12 @@ public:
   using PointCloudTargetPtr = typename PointCloudTarget::Ptr;
   using PointCloudTargetConstPtr = typename PointCloudTarget::ConstPtr;
   using CovarianceList = std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>>;
-#ifdef PCL_VERSION_CALC
-#if PCL_VERSION >= PCL_VERSION_CALC(1, 10, 0)
+#if PCL_VERSION >= PCL_VERSION_CALC(1, 10, 0)  // fast_apdgicp.hpp:33-39
   using Ptr = pcl::shared_ptr<FastAPDGICP<PointSource, PointTarget>>;
   using ConstPtr = pcl::shared_ptr<const FastAPDGICP<PointSource, PointTarget>>;
 #else
   using Ptr = boost::shared_ptr<FastAPDGICP<PointSource, PointTarget>>;
   using ConstPtr = boost::shared_ptr<const FastAPDGICP<PointSource, PointTarget>>;
-#endif
-#else
-  using Ptr = std::shared_ptr<FastAPDGICP<PointSource, PointTarget>>;
-  using ConstPtr = std::shared_ptr<const FastAPDGICP<PointSource, PointTarget>>;
 #endif
 
 protected:
@@ -57,6 +57,9 @@ public:
 
   // fast_apdgicp_impl.hpp:34-65
   void setNumThreads(int n) { params_.num_threads = n; }  // kept for source compatibility; the GPU path ignores it
+  // Deliberate deviation: the reference keeps covariances it has already computed until the CLOUD changes
+  // (fast_apdgicp_impl.hpp:122-127 tests only the sizes), so a new k / regularisation silently applies to later clouds only.
+  // Here the device recomputes stale covariances at the next align (the result a caller of these setters expects).
   void setCorrespondenceRandomness(int k) { params_.k_correspondences = k; invalidate_covariances(); }
   void setRegularizationMethod(RegularizationMethod method) { params_.regularization = static_cast<int>(method); invalidate_covariances(); }
   void setAzimuthVar(double var) { params_.azimuth_var = var; }
@@ -69,38 +72,43 @@ public:
     source_covs_.swap(target_covs_);
     std::swap(src_dirty_, tgt_dirty_);
     std::swap(src_covs_injected_, tgt_covs_injected_);
+    std::swap(src_cov_dirty_, tgt_cov_dirty_);  // injected covariances that were not pushed yet travel with their cloud
     if (handle_) apd_swap_source_and_target(handle_);
     this->target_cloud_updated_ = true;  // PCL rebuilds its own tree_ on the next align
   }
   void clearSource() override {
     input_.reset();
     source_covs_.clear();
-    src_covs_injected_ = false;
+    src_covs_injected_ = src_cov_dirty_ = src_dirty_ = false;
     if (handle_) apd_clear_source(handle_);
   }
   void clearTarget() override {
     target_.reset();
     target_covs_.clear();
-    tgt_covs_injected_ = false;
+    tgt_covs_injected_ = tgt_cov_dirty_ = tgt_dirty_ = false;
     if (handle_) apd_clear_target(handle_);
   }
 
-  // fast_apdgicp_impl.hpp:90-108: identical pointer -> nothing to do; otherwise the cloud is uploaded
-  // (lazily, at the next align) with the pointer as the device cache key, so the scan that was the
-  // source of the previous registration keeps its grid and covariances when it becomes the target.
+  // fast_apdgicp_impl.hpp:90-108: identical pointer -> nothing to do; otherwise the cloud goes to the device AT ONCE
+  // (asynchronous upload, where the reference builds its kd-tree) with the pointer as the device cache key, so the scan
+  // that was the source of the previous registration keeps its grid and covariances when it becomes the target
+  // (scan_matching_odometry_nodelet.cpp:591-592). Pushing eagerly also means the device never holds the key of a cloud
+  // this object no longer keeps alive: an address the allocator hands out again can not hit a stale cache entry.
   void setInputSource(const PointCloudSourceConstPtr& cloud) override {
     if (input_ == cloud) return;
     pcl::Registration<PointSource, PointTarget, Scalar>::setInputSource(cloud);
     source_covs_.clear();
-    src_covs_injected_ = false;
+    src_covs_injected_ = src_cov_dirty_ = false;
     src_dirty_ = true;
+    push_clouds();
   }
   void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
     if (target_ == cloud) return;
     pcl::Registration<PointSource, PointTarget, Scalar>::setInputTarget(cloud);
     target_covs_.clear();
-    tgt_covs_injected_ = false;
+    tgt_covs_injected_ = tgt_cov_dirty_ = false;
     tgt_dirty_ = true;
+    push_clouds();
   }
 
   // Scan-to-map target built on the device: what ScanMatchingOdometryNodelet does at
@@ -144,20 +152,37 @@ public:
   const CovarianceList& getTargetCovariances() { fetch_covariances(1, target_ ? target_->points.size() : 0, target_covs_); return target_covs_; }
 
 protected:
-  bool sync_inputs() override {
-    if (!Lsq::sync_inputs()) return false;
-    if (!input_ || !target_ || input_->points.empty() || target_->points.empty()) return false;
+  // fast_apdgicp.hpp:77-83: the protected virtuals of the reference class, same signatures (linearize and compute_error are
+  // inherited from the GPU base with the reference's signatures; computeTransformation likewise)
+  virtual void update_correspondences(const Eigen::Isometry3d& trans) { this->linearize(trans, nullptr, nullptr); }
+
+  // upload whichever cloud changed; a cloud that is null / empty clears its device slot
+  bool push_clouds() {
+    if (!handle_) return false;
     // target first: when it is the previous source the device moves its data across instead of re-uploading
     if (tgt_dirty_) {
-      if (apd_set_target(handle_, reinterpret_cast<const float*>(target_->points.data()), (int)sizeof(PointTarget), (int)target_->points.size(),
-                         reinterpret_cast<uint64_t>(target_.get()), APD_MEM_HOST) != APD_OK) return false;
+      const int rc = (target_ && !target_->points.empty())
+                         ? apd_set_target(handle_, reinterpret_cast<const float*>(target_->points.data()), (int)sizeof(PointTarget), (int)target_->points.size(),
+                                          reinterpret_cast<uint64_t>(target_.get()), APD_MEM_HOST)
+                         : apd_clear_target(handle_);
+      if (rc != APD_OK) return false;
       tgt_dirty_ = false;
     }
     if (src_dirty_) {
-      if (apd_set_source(handle_, reinterpret_cast<const float*>(input_->points.data()), (int)sizeof(PointSource), (int)input_->points.size(),
-                         reinterpret_cast<uint64_t>(input_.get()), APD_MEM_HOST) != APD_OK) return false;
+      const int rc = (input_ && !input_->points.empty())
+                         ? apd_set_source(handle_, reinterpret_cast<const float*>(input_->points.data()), (int)sizeof(PointSource), (int)input_->points.size(),
+                                          reinterpret_cast<uint64_t>(input_.get()), APD_MEM_HOST)
+                         : apd_clear_source(handle_);
+      if (rc != APD_OK) return false;
       src_dirty_ = false;
     }
+    return true;
+  }
+
+  bool sync_inputs() override {
+    if (!Lsq::sync_inputs()) return false;
+    if (!input_ || !target_ || input_->points.empty() || target_->points.empty()) return false;
+    if (!push_clouds()) return false;
     if (src_cov_dirty_ && src_covs_injected_ && source_covs_.size() == input_->points.size()) {
       if (apd_set_covariances(handle_, 0, reinterpret_cast<const double*>(source_covs_.data()), (int)source_covs_.size()) != APD_OK) return false;
       src_cov_dirty_ = false;

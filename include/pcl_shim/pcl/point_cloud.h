@@ -4,6 +4,12 @@
 #include <memory>
 #include <vector>
 
+// pcl/pcl_config.h: the reference headers switch their Ptr aliases on these (fast_apdgicp.hpp:33-39)
+#ifndef PCL_VERSION_CALC
+#define PCL_VERSION_CALC(MAJ, MIN, PATCH) (MAJ * 100000 + MIN * 100 + PATCH)
+#define PCL_VERSION PCL_VERSION_CALC(1, 10, 0)
+#endif
+
 namespace pcl {
 
 template <typename T> using shared_ptr = std::shared_ptr<T>;

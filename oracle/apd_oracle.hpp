@@ -159,13 +159,18 @@ public:
       std::vector<int> k_indices;
       std::vector<float> k_sq;
       tree.knn(cloud[i], k, k_indices, k_sq);  // APD_I:316 (includes i itself)
+      // Fewer than k results: a non-finite query point (no neighbour at all) or a cloud with fewer than k finite
+      // points. The reference then reads whatever PCL's resize left in k_indices; the convention here (and in
+      // the CUDA kernel) pads with the query itself and reports -1 in the index set.
+      const int found = (int)k_indices.size();
+      k_indices.resize(k, i);
       double mean[3] = {0, 0, 0};
       for (int j = 0; j < k; j++) {
         const P3& p = cloud[k_indices[j]];
         mean[0] += (double)p.x;
         mean[1] += (double)p.y;
         mean[2] += (double)p.z;
-        knn_out[(size_t)i * k + j] = k_indices[j];
+        knn_out[(size_t)i * k + j] = j < found ? k_indices[j] : -1;
       }
       for (double& m : mean) m /= k;  // APD_I:323 rowwise().mean()
       Mat3 cov = Mat3::zero();
@@ -259,6 +264,10 @@ public:
       std::vector<int> k_indices;
       std::vector<float> k_sq;
       tgt_tree_.knn(pt, 1, k_indices, k_sq);
+      if (k_indices.empty()) {  // non-finite query (kdtree.hpp): no neighbour, no correspondence
+        sq_dist_[i] = INFINITY;
+        continue;
+      }
       sq_dist_[i] = k_sq[0];
       corr_[i] = ((double)k_sq[0] < thr) ? k_indices[0] : -1;
       if (corr_[i] < 0) continue;
@@ -457,12 +466,14 @@ public:
     lm_lambda_ = -1.0;
     trace_.clear();
     nr_iterations_ = 0;
+    lm_failed_ = false;
     for (int i = 0; i < prm.max_iterations && !converged_; i++) {
       nr_iterations_ = i;
       Iso delta = Iso::identity();
       const bool ok = (prm.optimizer == OPT_GAUSS_NEWTON) ? step_gn(x0, delta) : step_lm(x0, delta, i);
       if (!ok) {
         if (verbose_) std::fprintf(stderr, "lm not converged!!\n");
+        lm_failed_ = true;  // LSQ_I:71-74: converged_ stays false
         break;
       }
       converged_ = is_converged(delta);
@@ -538,6 +549,7 @@ public:
   int nr_iterations_ = 0;
   double lm_lambda_ = -1.0;
   bool verbose_ = false;
+  bool lm_failed_ = false;  // the last align printed "lm not converged!!" (LSQ_I:72)
 
 private:
   static void load(std::vector<P3>& dst, const float* xyz, int stride_floats, int n) {

@@ -8,8 +8,15 @@
 //   results ascending; k clamped to the cloud size
 // FLANN's order among exactly equal distances depends on tree traversal; the convention fixed for
 // this project (BASELINE.json north_star) is ascending (d2, index).
+//
+// Non-finite points: pcl::KdTreeFLANN::convertCloudToArray (PCL 1.8-1.10 kdtree_flann.hpp, not under
+// /root/reference) leaves every point whose coordinates are not all finite out of the index, so such a
+// point is never anybody's neighbour; a query with a non-finite coordinate only produces NaN distances,
+// which never beat a result-set entry in FLANN, i.e. it finds nothing. Both are restated here: build()
+// skips non-finite points and knn() / knn_bruteforce() return an EMPTY result for a non-finite query.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <numeric>
 #include <vector>
@@ -54,10 +61,16 @@ struct KBest {
   }
 };
 
+inline bool finite_pt(const P3& p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); }
+
 inline void knn_bruteforce(const std::vector<P3>& pts, const P3& q, int k, std::vector<int>& out_idx, std::vector<float>& out_d2) {
-  k = std::min<int>(k, (int)pts.size());
+  int n_finite = 0;
+  for (const P3& p : pts) n_finite += finite_pt(p) ? 1 : 0;
+  k = std::min<int>(k, n_finite);
+  if (!finite_pt(q)) k = 0;
   KBest best(k);
-  for (int i = 0; i < (int)pts.size(); i++) best.offer(sqdist(q, pts[i]), i);
+  for (int i = 0; i < (int)pts.size() && k > 0; i++)
+    if (finite_pt(pts[i])) best.offer(sqdist(q, pts[i]), i);
   out_idx.assign(best.idx.begin(), best.idx.begin() + best.count);
   out_d2.assign(best.d2.begin(), best.d2.begin() + best.count);
 }
@@ -66,9 +79,11 @@ class KdTree {
 public:
   void build(const std::vector<P3>* pts) {
     pts_ = pts;
-    const int n = (int)pts->size();
-    order_.resize(n);
-    std::iota(order_.begin(), order_.end(), 0);
+    order_.clear();
+    order_.reserve(pts->size());
+    for (int i = 0; i < (int)pts->size(); i++)
+      if (finite_pt((*pts)[i])) order_.push_back(i);  // convertCloudToArray: invalid points are not indexed
+    const int n = (int)order_.size();
     nodes_.clear();
     nodes_.reserve(n / 4 + 16);
     if (n > 0) build_rec(0, n);
@@ -78,7 +93,8 @@ public:
   const std::vector<P3>* cloud() const { return pts_; }
 
   void knn(const P3& q, int k, std::vector<int>& out_idx, std::vector<float>& out_d2) const {
-    k = std::min<int>(k, (int)pts_->size());
+    k = std::min<int>(k, (int)order_.size());
+    if (!finite_pt(q)) k = 0;  // NaN distances never enter FLANN's result set
     KBest best(k);
     if (k > 0) search(0, q, best);
     out_idx.assign(best.idx.begin(), best.idx.begin() + best.count);

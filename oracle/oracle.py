@@ -71,6 +71,11 @@ def lib():
         L.oracle_compute_covariances.argtypes = [C.c_void_p]
         L.oracle_linearize.argtypes = [C.c_void_p, fp, dp, dp]
         L.oracle_linearize.restype = C.c_double
+        L.oracle_linearize_d.argtypes = [C.c_void_p, dp, dp, dp]
+        L.oracle_linearize_d.restype = C.c_double
+        L.oracle_compute_error_d.argtypes = [C.c_void_p, dp]
+        L.oracle_compute_error_d.restype = C.c_double
+        L.oracle_lm_failed.argtypes = [C.c_void_p]
         L.oracle_get_knn.argtypes = [C.c_void_p, C.c_int, ip]
         L.oracle_get_covariances.argtypes = [C.c_void_p, C.c_int, dp]
         L.oracle_set_covariances.argtypes = [C.c_void_p, C.c_int, dp, C.c_int]
@@ -137,6 +142,7 @@ class Oracle:
     def set_target(self, pts):
         a = _f32(pts)
         self.n_tgt = a.shape[0]
+        self._tgt_np = np.ascontiguousarray(a[:, :3])
         self.L.oracle_set_target(self.h, _ptr(a, C.c_float), a.shape[1], a.shape[0])
 
     def swap(self):
@@ -150,6 +156,10 @@ class Oracle:
         it = C.c_int(0)
         rc = self.L.oracle_align(self.h, _ptr(g, C.c_float), _ptr(T, C.c_float), C.byref(conv), C.byref(it))
         return rc, T.reshape(4, 4), bool(conv.value), it.value
+
+    def lm_failed(self) -> bool:
+        """True when the last align ended with "lm not converged!!" (LSQ_I:71-74)."""
+        return bool(self.L.oracle_lm_failed(self.h))
 
     def fitness(self, max_range=float(np.finfo(np.float64).max)):
         return self.L.oracle_fitness(self.h, max_range)
@@ -168,6 +178,26 @@ class Oracle:
         b = np.zeros(6)
         e = self.L.oracle_linearize(self.h, _ptr(g, C.c_float), _ptr(H, C.c_double), _ptr(b, C.c_double))
         return e, H.reshape(6, 6), b
+
+    def linearize_d(self, pose):
+        """linearize at a double pose (the protected hook takes an Isometry3d, APD_I:198-272)."""
+        g = np.ascontiguousarray(pose, dtype=np.float64).reshape(16)
+        H = np.zeros(36)
+        b = np.zeros(6)
+        e = self.L.oracle_linearize_d(self.h, _ptr(g, C.c_double), _ptr(H, C.c_double), _ptr(b, C.c_double))
+        return e, H.reshape(6, 6), b
+
+    def compute_error_d(self, pose):
+        """compute_error at a double pose with the correspondences of the last linearize (APD_I:275-298)."""
+        g = np.ascontiguousarray(pose, dtype=np.float64).reshape(16)
+        return self.L.oracle_compute_error_d(self.h, _ptr(g, C.c_double))
+
+    def inlier_count(self, T, max_dist):
+        """publish_scan_matching_status (scan_matching_odometry_nodelet.cpp:698-712): aligned points whose nearest target point
+        is strictly closer than max_dist (float squared distance < double max_dist^2)."""
+        q = self.transform_source(T)
+        idx, d2 = knn_kdtree(self._tgt_np, q, 1)
+        return int((d2[:, 0].astype(np.float64) < float(max_dist) * float(max_dist)).sum())
 
     def knn(self, which):
         n = self.n_tgt if which else self.n_src

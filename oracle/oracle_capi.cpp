@@ -80,6 +80,8 @@ int oracle_align(void* h, const float* guess16, float* T16, int* converged, int*
   return rc;
 }
 
+int oracle_lm_failed(void* h) { return static_cast<FastAPDGICP*>(h)->lm_failed_ ? 1 : 0; }
+
 // InformationMatrixCalculator::calc_fitness_score (information_matrix_calculator.cpp:55-86): same pass with an explicit pose
 double oracle_fitness_score(void* h, const float* T16, double max_range) {
   auto* o = static_cast<FastAPDGICP*>(h);
@@ -106,6 +108,26 @@ double oracle_linearize(void* h, const float* pose16, double* H36, double* b6) {
   }
   return e;
 }
+
+// the protected hooks at a DOUBLE pose (they take an Eigen::Isometry3d): linearize (APD_I:198-272) and compute_error (APD_I:275-298)
+static apd_oracle::Iso iso_from_d16(const double* p) {
+  apd_oracle::Iso x;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) x.R[i][j] = p[i * 4 + j];
+    x.t[i] = p[i * 4 + 3];
+  }
+  return x;
+}
+double oracle_linearize_d(void* h, const double* pose16, double* H36, double* b6) {
+  auto* o = static_cast<FastAPDGICP*>(h);
+  if (!o->ensure_covariances()) return -1.0;
+  double H[6][6], b[6];
+  const double e = o->linearize(iso_from_d16(pose16), H, b);
+  if (H36) std::memcpy(H36, H, sizeof(H));
+  if (b6) std::memcpy(b6, b, sizeof(b));
+  return e;
+}
+double oracle_compute_error_d(void* h, const double* pose16) { return static_cast<FastAPDGICP*>(h)->compute_error(iso_from_d16(pose16)); }
 
 // which: 0 = source, 1 = target
 int oracle_get_knn(void* h, int which, int* out) {

@@ -438,7 +438,13 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
 
     if (threadIdx.x == 0) {
       // x0 = Isometry3d(guess.cast<double>())  (lsq_registration_impl.hpp:56)
-      if (B.guesses) {
+      if (B.guesses64) {
+        const double* g = B.guesses64 + (size_t)pair * 16;
+        for (int i = 0; i < 3; i++) {
+          for (int j = 0; j < 3; j++) S.x0[i * 3 + j] = g[i * 4 + j];
+          S.x0[9 + i] = g[i * 4 + 3];
+        }
+      } else if (B.guesses) {
         const float* g = B.guesses + (size_t)pair * 16;
         for (int i = 0; i < 3; i++) {
           for (int j = 0; j < 3; j++) S.x0[i * 3 + j] = (double)g[i * 4 + j];
@@ -463,7 +469,17 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       status = APD_ERR_TOO_FEW_POINTS;
     }
 
-    for (int it = 0; have_input && it < (B.mode == 1 ? 1 : (B.mode == 2 ? 0 : P.max_iterations)); it++) {
+    if (have_input && B.mode == 3) {
+      // ---- compute_error(x0) alone: stale correspondences and Mahalanobis of the last linearize (fast_apdgicp_impl.hpp:275-298) ----
+#pragma unroll
+      for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
+      accumulate_pass<false>(B, S.x0, T, sspts, begin, end, sbase, acc);
+      acc[0] = acc[27];
+      team_reduce<TEAM, 1>(acc, S, tc);
+      last_y0 = S.red[0];
+      __syncthreads();
+    }
+    for (int it = 0; have_input && it < (B.mode == 1 ? 1 : (B.mode >= 2 ? 0 : P.max_iterations)); it++) {
       iterations = it;
       // ---- linearize(x0) ----
       correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
@@ -574,7 +590,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     // ---- final_transformation_ = x0.cast<float>() (:78) and getFitnessScore ----
 #pragma unroll
     for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-    if (have_input && B.mode != 1) fitness_pass(B, S, T, sspts, begin, end, sbase, B.mode == 0 && P.max_iterations > 0, acc);
+    if (have_input && B.mode != 1 && B.mode != 3) fitness_pass(B, S, T, sspts, begin, end, sbase, B.mode == 0 && P.max_iterations > 0, acc);
     team_reduce<TEAM, 2>(acc, S, tc);
     if (leader) {
       apd_result r;
@@ -696,7 +712,7 @@ int align_max_teams(int team_kind, int team_size, bool stage_target, size_t smem
 // ---- stand-alone getFitnessScore(max_range) for an arbitrary transform ----
 namespace {
 
-__global__ void __launch_bounds__(256) fitness_kernel(CloudSetView src, int s, CloudSetView tgt, int t, const float* __restrict__ Tf, double max_range,
+__global__ void __launch_bounds__(256) fitness_kernel(CloudSetView src, int s, CloudSetView tgt, int t, const float* __restrict__ Tf, double max_range, bool strict,
                                                       double* __restrict__ partials) {
   __shared__ double ws[8][2];
   GridView<unsigned> G;
@@ -716,7 +732,7 @@ __global__ void __launch_bounds__(256) fitness_kernel(CloudSetView src, int s, C
       Top1 v;
       v.init();
       pyramid_search<unsigned, Top1, false>(G, tgt, t, qx, qy, qz, __int_as_float(0x7f800000), v);
-      if (v.pos >= 0 && (double)v.bound2() <= max_range) {
+      if (v.pos >= 0 && (strict ? (double)v.bound2() < max_range : (double)v.bound2() <= max_range)) {
         sum += (double)v.bound2();
         cnt += 1.0;
       }
@@ -744,11 +760,33 @@ __global__ void fitness_final_kernel(const double* __restrict__ partials, int bl
   out[1] = b;
 }
 
+// one CTA: a scan is a few thousand values, and the count has to be exact (integer), so no atomics on doubles
+__global__ void __launch_bounds__(1024) count_below_kernel(const float* __restrict__ d2, int n, double thr, double* __restrict__ out) {
+  __shared__ int ws[32];
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += ((double)d2[i] < thr) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += ws[w];
+    out[0] = (double)t;
+  }
+}
+
 }  // namespace
 
-cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& tgt, int t, const float* T16, double max_range, double* partials, int blocks,
-                           double* out, cudaStream_t stream, LaunchStats* st) {
-  fitness_kernel<<<blocks, 256, 0, stream>>>(src, s, tgt, t, T16, max_range, partials);
+cudaError_t launch_count_below(const float* d2, int n, double thr, double* out, cudaStream_t stream, LaunchStats* st) {
+  count_below_kernel<<<1, 1024, 0, stream>>>(d2, n, thr, out);
+  if (st) st->launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& tgt, int t, const float* T16, double max_range, bool strict, double* partials,
+                           int blocks, double* out, cudaStream_t stream, LaunchStats* st) {
+  fitness_kernel<<<blocks, 256, 0, stream>>>(src, s, tgt, t, T16, max_range, strict, partials);
   if (st) st->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -185,6 +185,7 @@ struct apd_context {
   double final_hessian[36];
   std::vector<double> lm_trace;
   bool last_lin_valid = false;  // scratch slot 0 holds correspondences of the current src/tgt
+  bool fit_valid = false;       // scratch slot 0 also holds the squared 1-NN distances of the last align's final pose
   long long work_lin = 0, work_err = 0, work_pairs = 0;
   // pinned staging buffer for small host->device table uploads (grow-only) and the event that guards its reuse
   unsigned char* stage_host[2] = {nullptr, nullptr};  // slot 0: cloud-set tables, slot 1: small point uploads
@@ -601,6 +602,7 @@ struct AlignCall {
   apd_cloudset_s *src, *tgt;
   const int32_t *src_idx = nullptr, *tgt_idx = nullptr;  // host
   const float* guesses = nullptr;                        // host, n_pairs*16
+  const double* guesses64 = nullptr;                     // host, n_pairs*16 (wins over guesses)
   int n_pairs = 0;
   int mode = 0;
   int min_points = 0;
@@ -642,7 +644,11 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
     CK(cudaMemcpyAsync(h->idx_tgt.p, c.tgt_idx, sizeof(int) * np, cudaMemcpyHostToDevice, h->stream));
     b.tgt_idx = h->idx_tgt.as<int>();
   }
-  if (c.guesses) {
+  if (c.guesses64) {
+    CK(h->guesses.reserve(sizeof(double) * 16 * np));
+    CK(cudaMemcpyAsync(h->guesses.p, c.guesses64, sizeof(double) * 16 * np, cudaMemcpyHostToDevice, h->stream));
+    b.guesses64 = h->guesses.as<double>();
+  } else if (c.guesses) {
     CK(h->guesses.reserve(sizeof(float) * 16 * np));
     CK(cudaMemcpyAsync(h->guesses.p, c.guesses, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, h->stream));
     b.guesses = h->guesses.as<float>();
@@ -704,7 +710,7 @@ int set_cloud(apd_handle h, bool is_source, const float* xyz, int stride_bytes, 
   auto& slot_key = is_source ? h->src_key : h->tgt_key;
   auto& other = is_source ? h->tgt : h->src;
   auto& other_key = is_source ? h->tgt_key : h->src_key;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   if (key != 0 && slot && slot_key == key && slot->total == n) return APD_OK;  // same pointer: fast_apdgicp_impl.hpp:91,102
   if (key != 0 && other && other_key == key && other->total == n) {
     slot = other;  // the other slot already holds this cloud: share its grid and covariances
@@ -817,7 +823,7 @@ int apd_set_params(apd_handle h, const apd_params* p) {
   if (p->regularization < 0 || p->regularization > 4) return fail(h, APD_ERR_INVALID, "unknown regularization method");
   if (p->optimizer < 0 || p->optimizer > 1) return fail(h, APD_ERR_INVALID, "unknown optimizer");
   h->prm = *p;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   return APD_OK;
 }
 
@@ -859,7 +865,7 @@ int apd_swap_source_and_target(apd_handle h) {
   if (!h) return APD_ERR_INVALID;
   std::swap(h->src, h->tgt);
   std::swap(h->src_key, h->tgt_key);
-  h->last_lin_valid = false;  // correspondences_.clear(), fast_apdgicp_impl.hpp:73
+  h->last_lin_valid = h->fit_valid = false;  // correspondences_.clear(), fast_apdgicp_impl.hpp:73
   return APD_OK;
 }
 
@@ -867,7 +873,7 @@ int apd_clear_source(apd_handle h) {
   if (!h) return APD_ERR_INVALID;
   h->src.reset();
   h->src_key = 0;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   return APD_OK;
 }
 
@@ -875,7 +881,7 @@ int apd_clear_target(apd_handle h) {
   if (!h) return APD_ERR_INVALID;
   h->tgt.reset();
   h->tgt_key = 0;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   return APD_OK;
 }
 
@@ -943,6 +949,7 @@ int apd_align(apd_handle h, const float guess[16], apd_result* out) {
   if (any) memcpy(h->final_hessian, fh, sizeof(fh));  // only an accepted step writes final_hessian_
   h->has_last = true;
   h->last_lin_valid = true;
+  h->fit_valid = h->last.status == APD_OK || h->last.status == APD_STATUS_LM_FAILED;  // the fitness pass ran at the final pose
   if (out) *out = h->last;
   return APD_OK;
 }
@@ -964,7 +971,7 @@ int apd_fitness(apd_handle h, double max_range, double* score) {
   double* res = partials + 2 * blocks;
   float* dT = reinterpret_cast<float*>(res + 2);
   CK(cudaMemcpyAsync(dT, T, sizeof(T), cudaMemcpyHostToDevice, h->stream));
-  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, max_range, partials, blocks, res, h->stream, &h->stats));
+  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, max_range, false, partials, blocks, res, h->stream, &h->stats));
   double r[2];
   CK(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -991,12 +998,50 @@ int apd_fitness_score(apd_handle h, const float T[16], double max_range, double*
   double* res = partials + 2 * blocks;
   float* dT = reinterpret_cast<float*>(res + 2);
   CK(cudaMemcpyAsync(dT, Th, sizeof(Th), cudaMemcpyHostToDevice, h->stream));
-  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, max_range, partials, blocks, res, h->stream, &h->stats));
+  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, max_range, false, partials, blocks, res, h->stream, &h->stats));
   double r[2];
   CK(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   *score = r[0];
   if (n_used) *n_used = (int64_t)r[1];
+  return APD_OK;
+}
+
+// publish_scan_matching_status (radar_graph_slam/apps/scan_matching_odometry_nodelet.cpp:698-712): for every point of the aligned cloud
+// (the source moved by the final transformation) one 1-NN query in the target, counted when k_sq_dists[0] < max_dist * max_dist.
+int apd_inlier_count(apd_handle h, const float T[16], double max_dist, int64_t* n_inliers) {
+  if (!h || !n_inliers) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (!h->src || !h->tgt || h->src->total == 0 || h->tgt->total == 0) return fail(h, APD_ERR_NO_INPUT, "source or target cloud not set");
+  const double thr = max_dist * max_dist;
+  double r[2] = {0, 0};
+  if (!T && h->fit_valid) {
+    // the align kernel left the squared 1-NN distance of every source point at the final pose in its scratch: count, no search
+    CK(h->misc.reserve(sizeof(double) * 2));
+    CK(launch_count_below(h->sc_fit.as<float>(), (int)h->src->total, thr, h->misc.as<double>(), h->stream, &h->stats));
+    CK(cudaMemcpyAsync(r, h->misc.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *n_inliers = (int64_t)r[0];
+    return APD_OK;
+  }
+  int rc = cloudset_build_grid(h, h->src.get());
+  if (rc) return rc;
+  rc = cloudset_build_grid(h, h->tgt.get());
+  if (rc) return rc;
+  float Th[16];
+  if (T) memcpy(Th, T, sizeof(Th));
+  else if (h->has_last) memcpy(Th, h->last.T, sizeof(Th));
+  else for (int i = 0; i < 16; i++) Th[i] = (i % 5 == 0) ? 1.f : 0.f;
+  const int blocks = std::max(1, std::min(2 * h->sm_count, (int)((h->src->total + 255) / 256)));
+  CK(h->misc.reserve(sizeof(double) * (2 * blocks + 2) + sizeof(float) * 16));
+  double* partials = h->misc.as<double>();
+  double* res = partials + 2 * blocks;
+  float* dT = reinterpret_cast<float*>(res + 2);
+  CK(cudaMemcpyAsync(dT, Th, sizeof(Th), cudaMemcpyHostToDevice, h->stream));
+  CK(launch_fitness(h->src->view(), 0, h->tgt->view(), 0, dT, thr, true, partials, blocks, res, h->stream, &h->stats));
+  CK(cudaMemcpyAsync(r, res, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *n_inliers = (int64_t)r[1];
   return APD_OK;
 }
 
@@ -1028,7 +1073,7 @@ int apd_fitness_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const in
   CK(cudaMemcpyAsync(r.data(), h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < n_pairs; i++) scores[i] = r[i].fitness;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   return APD_OK;
 }
 
@@ -1061,15 +1106,23 @@ int apd_transform_source(apd_handle h, const float T[16], float* out_xyz, int ou
   return APD_OK;
 }
 
+static int linearize_common(apd_handle h, const float* pose_f, const double* pose_d, double H[36], double b[6], double* error);
 int apd_linearize(apd_handle h, const float pose[16], double H[36], double b[6], double* error) {
   if (!h) return APD_ERR_INVALID;
   DeviceGuard guard(h->device);
+  return linearize_common(h, pose, nullptr, H, b, error);
+}
+
+// the protected hooks of the reference class, callable at a DOUBLE pose (they take an Eigen::Isometry3d):
+// linearize (fast_apdgicp_impl.hpp:198-272) and compute_error (:275-298)
+static int linearize_common(apd_handle h, const float* pose_f, const double* pose_d, double H[36], double b[6], double* error) {
   int rc = single_pair_checks(h);
   if (rc) return rc;
   AlignCall c;
   c.src = h->src.get();
   c.tgt = h->tgt.get();
-  c.guesses = pose;
+  c.guesses = pose_f;
+  c.guesses64 = pose_d;
   c.n_pairs = 1;
   c.mode = 1;
   rc = run_align(h, c);
@@ -1084,6 +1137,32 @@ int apd_linearize(apd_handle h, const float pose[16], double H[36], double b[6],
   if (b) memcpy(b, bh, sizeof(bh));
   if (error) *error = r.error;
   h->last_lin_valid = true;
+  h->fit_valid = false;
+  return APD_OK;
+}
+
+int apd_linearize_d(apd_handle h, const double pose[16], double H[36], double b[6], double* error) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  return linearize_common(h, nullptr, pose, H, b, error);
+}
+
+int apd_compute_error(apd_handle h, const double pose[16], double* error) {
+  if (!h || !error) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  if (!h->last_lin_valid || !h->src || !h->tgt) return fail(h, APD_ERR_NO_INPUT, "compute_error needs the correspondences of a previous linearize on the current clouds");
+  AlignCall c;
+  c.src = h->src.get();
+  c.tgt = h->tgt.get();
+  c.guesses64 = pose;
+  c.n_pairs = 1;
+  c.mode = 3;
+  int rc = run_align(h, c);
+  if (rc) return rc;
+  apd_result r;
+  CK(cudaMemcpyAsync(&r, h->results.p, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *error = r.error;
   return APD_OK;
 }
 
@@ -1132,6 +1211,18 @@ int apd_set_covariances(apd_handle h, int which, const double* c16, int n) {
   apd_cloudset_s* cs = which ? h->tgt.get() : h->src.get();
   if (!cs || cs->total == 0) return fail(h, APD_ERR_NO_INPUT, "cloud not set");
   if (n != cs->total) return fail(h, APD_ERR_INVALID, "covariance count does not match the cloud size");
+  if (h->src && h->src == h->tgt) {
+    // Both slots share one device cloud (same cache key: the previous source became the target). The reference keeps
+    // source_covs_ and target_covs_ apart (fast_apdgicp_impl.hpp:111-118), so the slot being written gets its own copy
+    // first: same points (device-to-device), its own grid, then the injected covariances.
+    auto& slot = which ? h->tgt : h->src;
+    const int32_t off[2] = {0, n};
+    std::shared_ptr<apd_cloudset_s> own;
+    int rc0 = make_cloudset(h, reinterpret_cast<const float*>(cs->pts.p), 16, off, 1, APD_MEM_DEVICE, &own);
+    if (rc0) return rc0;
+    slot = own;
+    cs = own.get();
+  }
   int rc = cloudset_build_grid(h, cs);
   if (rc) return rc;
   CK(h->cov_tmp.reserve(sizeof(double) * 16 * (size_t)n));
@@ -1141,7 +1232,7 @@ int apd_set_covariances(apd_handle h, int which, const double* c16, int n) {
   cs->cov_valid = true;
   cs->cov_k = -1;  // marks "provided by the caller": never recomputed
   cs->cov_reg = -1;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   return APD_OK;
 }
 
@@ -1242,7 +1333,7 @@ int apd_align_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int3
   c.max_range = h->fitness_max_range;
   int rc = run_align(h, c);
   if (rc) return rc;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   if (out_mem == APD_MEM_DEVICE) {
     CK(cudaMemcpyAsync(out, h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToDevice, h->stream));
     h->work_pairs = n_pairs;
@@ -1250,6 +1341,56 @@ int apd_align_pairs(apd_handle h, apd_cloudset src, apd_cloudset tgt, const int3
   }
   CK(cudaMemcpyAsync(out, h->results.p, sizeof(apd_result) * n_pairs, cudaMemcpyDeviceToHost, h->stream));
   return fetch_counters(h, n_pairs);
+}
+
+// LoopDetector::matching over ALL candidates (radar_graph_slam/src/radar_graph_slam/loop_detector.cpp:379-441, #if 0 in the reference because
+// it is too slow on the CPU): registration->setInputTarget(new_keyframe->cloud); for every candidate setInputSource, align(guess),
+// getFitnessScore(fitness_score_max_range); keep the best converged score (:415-423); reject above fitness_score_thresh (:431-434).
+int apd_match_candidates(apd_handle h, apd_cloudset candidates, const int32_t* cand_idx, int n_candidates, apd_cloudset keyframes, int keyframe_idx, const float* guesses,
+                         double fitness_score_max_range, double fitness_score_thresh, int32_t* best, float relative_pose[16], double* best_score, apd_result* records) {
+  if (!h || !candidates || !keyframes || !best || n_candidates < 0) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  *best = -1;
+  if (best_score) *best_score = DBL_MAX;
+  if (n_candidates == 0) return APD_OK;  // :391-393
+  apd_cloudset_s* s = deref(candidates);
+  apd_cloudset_s* t = deref(keyframes);
+  if (keyframe_idx < 0 || keyframe_idx >= t->n_clouds) return fail(h, APD_ERR_INVALID, "keyframe index out of range");
+  std::vector<int32_t> ti((size_t)n_candidates, keyframe_idx);
+  for (int i = 0; i < n_candidates; i++) {
+    const int si = cand_idx ? cand_idx[i] : i;
+    if (si < 0 || si >= s->n_clouds) return fail(h, APD_ERR_INVALID, "candidate index out of range");
+  }
+  AlignCall c;
+  c.src = s;
+  c.tgt = t;
+  c.src_idx = cand_idx;
+  c.tgt_idx = ti.data();
+  c.guesses = guesses;
+  c.n_pairs = n_candidates;
+  c.min_points = h->prm.k_correspondences;
+  c.max_range = fitness_score_max_range;
+  int rc = run_align(h, c);
+  if (rc) return rc;
+  h->last_lin_valid = h->fit_valid = false;
+  std::vector<apd_result> r((size_t)n_candidates);
+  CK(cudaMemcpyAsync(r.data(), h->results.p, sizeof(apd_result) * n_candidates, cudaMemcpyDeviceToHost, h->stream));
+  rc = fetch_counters(h, n_candidates);
+  if (rc) return rc;
+  double bs = DBL_MAX;
+  int bi = -1;
+  for (int i = 0; i < n_candidates; i++) {
+    const double score = r[i].fitness;
+    if (!r[i].converged || r[i].status != APD_OK || score > bs) continue;  // :415-417 (a pair the reference could not even align never converges)
+    bs = score;
+    bi = i;
+  }
+  if (records) memcpy(records, r.data(), sizeof(apd_result) * n_candidates);
+  if (best_score) *best_score = bs;
+  if (bi < 0 || bs > fitness_score_thresh) return APD_OK;  // "loop not found..." (:431-434)
+  *best = bi;
+  if (relative_pose) memcpy(relative_pose, r[bi].T, sizeof(float) * 16);
+  return APD_OK;
 }
 
 // ---- pipelined host-to-host batches ----
@@ -1282,6 +1423,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->max_teams_opt = h->max_teams_opt;
   x->knn_packed = h->knn_packed;
   x->no_fused_build = h->no_fused_build;
+  x->no_smem_build = h->no_smem_build;
   x->fitness_max_range = h->fitness_max_range;
   x->knn_fine_rings = h->knn_fine_rings;
   *out = x;
@@ -1317,6 +1459,15 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
   long long lin = 0, err = 0;
   std::vector<int32_t> idx_s, idx_t;
   int chunk = 0;
+  // Every early return below leaves through this guard: the other slot may still have kernels and an asynchronous copy into
+  // the caller's `out` in flight on its own stream, and its cloud sets go back to the pool when the slots die.
+  struct Drain {
+    ChunkSlot* s;
+    ~Drain() {
+      for (int i = 0; i < 2; i++)
+        if (s[i].h) cudaStreamSynchronize(s[i].h->stream);
+    }
+  } drain{slots};
   // the first chunk's upload is the one nothing can hide: keep it to a single wave of teams when the batch is large
   const int first_pairs = (slots[1].h && n_pairs > 3 * h->sm_count) ? h->sm_count : kChunkPairs;  // measured: 74 / 148 / 256 pairs -> 12.85 / 12.31 / 12.54 ms per 1000 pairs
   for (int p0 = 0, np = 0; p0 < n_pairs; p0 += np, chunk++) {
@@ -1363,7 +1514,7 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
   h->work_lin = lin;
   h->work_err = err;
   h->work_pairs = n_pairs;
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   if (slots[1].h) h->stats.launches += slots[1].h->stats.launches - h->helper_launches_seen, h->helper_launches_seen = slots[1].h->stats.launches;
   return APD_OK;
 }
@@ -1507,7 +1658,7 @@ int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which,
     off[i + 1] = off[i] + (ks->h_off[which[i] + 1] - ks->h_off[which[i]]);
   }
   const int total = off[n_sel];
-  h->last_lin_valid = false;
+  h->last_lin_valid = h->fit_valid = false;
   h->has_last = false;
   if (total == 0) {  // an empty submap: the target is cleared (PCL would refuse an empty target at align time)
     h->tgt.reset();

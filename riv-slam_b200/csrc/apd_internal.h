@@ -146,6 +146,7 @@ struct AlignBatch {
   const int* src_idx;      // [n_pairs] or nullptr (identity map)
   const int* tgt_idx;
   const float* guesses;    // [n_pairs*16] row-major or nullptr (identity)
+  const double* guesses64; // [n_pairs*16] row-major double poses (the protected linearize / compute_error hooks take an Isometry3d); wins over guesses
   apd_result* out;         // [n_pairs] device
   double* final_hessian;   // [n_pairs*36] or nullptr
   double* lin_b;           // [n_pairs*6] or nullptr (mode 1: the gradient of evaluateCost)
@@ -160,7 +161,9 @@ struct AlignBatch {
   DeviceParams prm;
   int min_points;          // pairs with a cloud smaller than this report APD_ERR_TOO_FEW_POINTS (k; 0 = no check)
   int mode;                // 0 = align, 1 = linearize only (evaluateCost): out->error, final_hessian, lin_b,
-                           // 2 = fitness score only at the given pose (calc_fitness_score): out->fitness, out->T = pose
+                           // 2 = fitness score only at the given pose (calc_fitness_score): out->fitness, out->T = pose,
+                           // 3 = compute_error only at the given pose, with the correspondences and Mahalanobis matrices the
+                           //     last linearize left in the slot (fast_apdgicp_impl.hpp:275-298): out->error
   double max_range;        // fitness gate (getFitnessScore max_range)
 };
 
@@ -184,8 +187,11 @@ cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tile
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,
                          LaunchStats* st);
-cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& tgt, int t, const float* T16 /*device*/, double max_range,
+// strict: count d2 < max_range (the status message's inlier test) instead of d2 <= max_range (getFitnessScore)
+cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& tgt, int t, const float* T16 /*device*/, double max_range, bool strict,
                            double* partials /*device [2*blocks]*/, int blocks, double* out /*device [2]: score, count*/, cudaStream_t stream, LaunchStats* st);
+// out[0] = number of entries of d2[0..n) with (double)d2 < thr
+cudaError_t launch_count_below(const float* d2, int n, double thr, double* out /*device [1]*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_pack_points(const float* xyz, int stride_floats, long long n, float4* out, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_transform_points(const float4* pts, int n, const float* T16 /*device*/, float* out, int out_stride_floats, cudaStream_t stream, LaunchStats* st);
 // gather/scatter between original and sorted order for the covariance getters / setters

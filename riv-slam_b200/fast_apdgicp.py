@@ -93,6 +93,10 @@ _PROTOTYPES = {
     "apd_transform_source": (C.c_int, [C.c_void_p, _fp, C.c_void_p, C.c_int, C.c_int]),
     "apd_linearize": (C.c_int, [C.c_void_p, _fp, _dp, _dp, _dp]),
     "apd_get_final_hessian": (C.c_int, [C.c_void_p, _dp]),
+    "apd_linearize_d": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
+    "apd_compute_error": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "apd_inlier_count": (C.c_int, [C.c_void_p, _fp, C.c_double, C.POINTER(C.c_int64)]),
+    "apd_match_candidates": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_void_p, C.c_int, _fp, C.c_double, C.c_double, _ip, _fp, _dp, C.c_void_p]),
     "apd_compute_covariances": (C.c_int, [C.c_void_p]),
     "apd_get_knn": (C.c_int, [C.c_void_p, C.c_int, _ip]),
     "apd_get_covariances": (C.c_int, [C.c_void_p, C.c_int, _dp]),
@@ -374,6 +378,34 @@ class FastAPDGICP:
         e = C.c_double(0)
         self._H.check(self.L.apd_linearize(self.h, g, H.ctypes.data_as(_dp), b.ctypes.data_as(_dp), C.byref(e)))
         return (e.value, H.reshape(6, 6), b) if want_H else e.value
+
+    # ---- the protected hooks of the reference class (fast_apdgicp.hpp:77-83), at a double pose ----
+    def linearize(self, trans, want_H: bool = True):
+        """FastAPDGICP::linearize(Isometry3d, H, b) (fast_apdgicp_impl.hpp:198-272)."""
+        a = np.ascontiguousarray(trans, dtype=np.float64).reshape(16)
+        H = np.zeros(36)
+        b = np.zeros(6)
+        e = C.c_double(0)
+        self._H.check(self.L.apd_linearize_d(self.h, a.ctypes.data_as(_dp), H.ctypes.data_as(_dp) if want_H else None, b.ctypes.data_as(_dp) if want_H else None, C.byref(e)))
+        return (e.value, H.reshape(6, 6), b) if want_H else e.value
+
+    def update_correspondences(self, trans):
+        """FastAPDGICP::update_correspondences(Isometry3d) (fast_apdgicp_impl.hpp:133-194): the first half of linearize."""
+        self.linearize(trans, want_H=False)
+
+    def compute_error(self, trans) -> float:
+        """FastAPDGICP::compute_error(Isometry3d) (fast_apdgicp_impl.hpp:275-298): stale correspondences of the last linearize."""
+        a = np.ascontiguousarray(trans, dtype=np.float64).reshape(16)
+        e = C.c_double(0)
+        self._H.check(self.L.apd_compute_error(self.h, a.ctypes.data_as(_dp), C.byref(e)))
+        return e.value
+
+    def inlierCount(self, max_dist: float = 0.5, T=None) -> int:
+        """publish_scan_matching_status (scan_matching_odometry_nodelet.cpp:698-712): aligned points with a target point closer than max_dist."""
+        keep, t = _mat16(T)
+        n = C.c_int64(0)
+        self._H.check(self.L.apd_inlier_count(self.h, t, float(max_dist), C.byref(n)))
+        return n.value
 
     def getFinalHessian(self) -> np.ndarray:
         H = np.zeros(36)

@@ -30,7 +30,9 @@ class InformationMatrixCalculator:
         self.max_stddev_x = float(g("max_stddev_x", 5.0))
         self.min_stddev_q = float(g("min_stddev_q", 0.05))
         self.max_stddev_q = float(g("max_stddev_q", 0.2))
-        self.fitness_score_thresh = float(g("fitness_score_thresh", 2.5))
+        # information_matrix_calculator.cpp:24 — the constructor both reference callers use (radar_graph_slam_nodelet.cpp, loop_detector.cpp)
+        # reads 0.5; the 2.5 of the header's unused load() template (information_matrix_calculator.hpp:37) never takes effect
+        self.fitness_score_thresh = float(g("fitness_score_thresh", 0.5))
 
     def calc_fitness_score(self, cloud1, cloud2, relpose, max_range: float = DBL_MAX) -> float:
         """information_matrix_calculator.cpp:55-86: kd-tree on cloud1, cloud2 transformed by relpose.cast<float>()."""

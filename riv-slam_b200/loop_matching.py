@@ -9,9 +9,11 @@ selection rule, thresholds and guess construction.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
-from .fast_apdgicp import CloudSet, Handle, align_pairs
+from .fast_apdgicp import RESULT_DTYPE, CloudSet, Handle, _fp, _ip
 
 
 def relative_guess(new_keyframe_estimate: np.ndarray, candidate_estimate: np.ndarray) -> np.ndarray:
@@ -34,21 +36,25 @@ def matching(handle: Handle, candidate_clouds, new_keyframe_cloud, guesses=None,
     n = len(candidate_clouds)
     if n == 0:
         return None, None, float(np.finfo(np.float64).max), np.zeros(0)
-    handle.set_option("fitness_max_range", fitness_score_max_range)
-    try:
-        src = CloudSet(handle, list(candidate_clouds))      # registration->setInputSource(candidate->cloud)
-        tgt = CloudSet(handle, [new_keyframe_cloud])        # registration->setInputTarget(new_keyframe->cloud)
-        res = align_pairs(handle, src, tgt, tgt_idx=np.zeros(n, dtype=np.int32), guesses=guesses)
-    finally:
-        handle.set_option("fitness_max_range", float(np.finfo(np.float64).max))
-    best_score = float(np.finfo(np.float64).max)
-    best = None
-    for i in range(n):
-        score = float(res[i]["fitness"])
-        if not res[i]["converged"] or score > best_score:
-            continue
-        best_score = score
-        best = i
-    if best is None or best_score > fitness_score_thresh:
-        return None, None, best_score, res
-    return best, np.array(res[best]["T"]), best_score, res
+    src = CloudSet(handle, list(candidate_clouds))      # registration->setInputSource(candidate->cloud)
+    tgt = CloudSet(handle, [new_keyframe_cloud])        # registration->setInputTarget(new_keyframe->cloud)
+    return match_candidates(handle, src, None, tgt, 0, guesses, fitness_score_max_range, fitness_score_thresh)
+
+
+def match_candidates(handle: Handle, candidates: CloudSet, cand_idx, keyframes: CloudSet, keyframe_idx: int, guesses=None,
+                     fitness_score_max_range: float = float(np.finfo(np.float64).max), fitness_score_thresh: float = 0.5):
+    """apd_match_candidates on cloud sets that already live on the device (the C entry point a C++ LoopDetector links):
+    selection and thresholds happen behind the C ABI. Same return value as ``matching``."""
+    ci = None if cand_idx is None else np.ascontiguousarray(cand_idx, dtype=np.int32)
+    n = candidates.n_clouds if ci is None else len(ci)
+    g = None if guesses is None else np.ascontiguousarray(guesses, dtype=np.float32).reshape(n, 16)
+    res = np.zeros(n, dtype=RESULT_DTYPE)
+    best = C.c_int32(-1)
+    pose = np.zeros(16, dtype=np.float32)
+    score = C.c_double(0)
+    handle.check(handle.L.apd_match_candidates(handle.h, candidates.cs, None if ci is None else ci.ctypes.data_as(_ip), n, keyframes.cs, int(keyframe_idx),
+                                               None if g is None else g.ctypes.data_as(_fp), float(fitness_score_max_range), float(fitness_score_thresh),
+                                               C.byref(best), pose.ctypes.data_as(_fp), C.byref(score), C.c_void_p(res.ctypes.data)))
+    if best.value < 0:
+        return None, None, score.value, res
+    return best.value, pose.reshape(4, 4), score.value, res

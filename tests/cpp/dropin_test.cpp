@@ -4,9 +4,11 @@
 // loop_detector.cpp:222-236 drive it. Input: a binary file of float32 PointXYZI-layout scans written by
 // tests/test_cpp_dropin.py. Output: one text line per registration.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include <fast_gicp/gicp/fast_apdgicp.hpp>
@@ -26,6 +28,15 @@ static pcl::Registration<PointT, PointT>::Ptr select_registration_method() {
   gicp->setElevationVar(1.0);
   return gicp;
 }
+
+// the protected virtual surface of the reference class (fast_apdgicp.hpp:77-83, lsq_registration.hpp:64-76), reached the way a
+// subclass reaches it
+struct Probe : fast_gicp::FastAPDGICP<PointT, PointT> {
+  using fast_gicp::FastAPDGICP<PointT, PointT>::compute_error;
+  using fast_gicp::FastAPDGICP<PointT, PointT>::is_converged;
+  using fast_gicp::FastAPDGICP<PointT, PointT>::linearize;
+  using fast_gicp::FastAPDGICP<PointT, PointT>::update_correspondences;
+};
 
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
@@ -127,6 +138,87 @@ int main(int argc, char** argv) {
     std::printf("submap n %zu p0 %.9g %.9g %.9g %.9g converged %d T03 %.9g T13 %.9g T23 %.9g fitness %.17g\n", submap->size(), submap->points[0].x, submap->points[0].y,
                 submap->points[0].z, submap->points[0].intensity, gicp->hasConverged() ? 1 : 0, Tm(0, 3), Tm(1, 3), Tm(2, 3), gicp->lastFitnessScore());
     apd_cloudset_destroy(gicp->nativeHandle(), ks);
+  }
+  // protected virtuals at a DOUBLE pose; the status message's inlier count
+  {
+    Probe p;
+    p.setMaxCorrespondenceDistance(2.0);
+    p.setTransformationEpsilon(0.1);
+    p.setAzimuthVar(1.0);
+    p.setInputTarget(scans[0]);
+    p.setInputSource(scans[1]);
+    Eigen::Isometry3d x;  // a pose that is NOT representable in float: the double path must see all of it
+    x.matrix()(0, 3) = 0.1 + 1e-9;
+    x.matrix()(1, 3) = -0.05 - 3e-10;
+    Eigen::Matrix<double, 6, 6> H;
+    Eigen::Matrix<double, 6, 1> b;
+    const double e = p.linearize(x, &H, &b);
+    Eigen::Isometry3d y = x;
+    y.matrix()(0, 3) += 0.02;
+    const double e_same = p.compute_error(x), e_moved = p.compute_error(y);
+    p.update_correspondences(y);
+    const double e_after = p.compute_error(y);
+    Eigen::Isometry3d small, big;
+    small.matrix()(0, 3) = 0.05;
+    big.matrix()(0, 3) = 0.2;
+    std::printf("probe lin %.17g H00 %.17g b3 %.17g err_same %.17g err_moved %.17g err_after %.17g conv_small %d conv_big %d\n", e, H(0, 0), b(3), e_same, e_moved, e_after,
+                p.is_converged(small) ? 1 : 0, p.is_converged(big) ? 1 : 0);
+    p.align(*aligned);
+    std::printf("inliers %lld of %zu at 0.5 ; %lld at 2.0\n", p.lastInlierCount(0.5), aligned->size(), p.lastInlierCount(2.0));
+  }
+  // stale cache keys: clouds die and new ones of the same size appear (possibly at the same address); every align must see the
+  // cloud it was given. Also setSourceCovariances + swapSourceAndTarget BEFORE any align (the injected set must travel).
+  {
+    auto gicp = std::make_shared<fast_gicp::FastAPDGICP<PointT, PointT>>();
+    gicp->setMaxCorrespondenceDistance(2.0);
+    gicp->setTransformationEpsilon(0.1);
+    gicp->setAzimuthVar(1.0);
+    gicp->setInputTarget(scans[0]);
+    for (int rep = 0; rep < 6; rep++) {
+      auto tmp = std::make_shared<Cloud>(*scans[1 + rep % 2]);  // a fresh copy: freed at the end of the iteration
+      if (rep % 2) for (auto& q : tmp->points) q.x += 0.125f;
+      gicp->setInputSource(tmp);
+      gicp->align(*aligned);
+      const auto T = gicp->getFinalTransformation();
+      std::printf("stale rep %d T03 %.9g T13 %.9g\n", rep, T(0, 3), T(1, 3));
+    }
+    auto a = std::make_shared<fast_gicp::FastAPDGICP<PointT, PointT>>();
+    a->setMaxCorrespondenceDistance(2.0);
+    a->setTransformationEpsilon(1e-6);
+    a->setRotationEpsilon(1e-6);
+    a->setAzimuthVar(1.0);
+    a->setInputSource(scans[0]);
+    a->setInputTarget(scans[1]);
+    fast_gicp::FastAPDGICP<PointT, PointT>::CovarianceList wide(scans[0]->size());
+    for (auto& m : wide) { m.setZero(); m(0, 0) = 4.0; m(1, 1) = 4.0; m(2, 2) = 4.0; }
+    a->setSourceCovariances(wide);   // belongs to scans[0]
+    a->swapSourceAndTarget();        // scans[0] is now the TARGET and must keep the injected set
+    a->align(*aligned);
+    const auto Ta = a->getFinalTransformation();
+    std::printf("swapinj converged %d T03 %.9g T13 %.9g T23 %.9g\n", a->hasConverged() ? 1 : 0, Ta(0, 3), Ta(1, 3), Ta(2, 3));
+  }
+  // per-call latency through the C++ class: setInputTarget (cached: the previous source) + setInputSource + align + the fitness
+  // score computed on the GPU; PCL's own kd-tree build and getFitnessScore are excluded (force_no_recompute, lastFitnessScore)
+  if (argc >= 3 && std::string(argv[2]) == "--latency") {
+    auto gicp = std::make_shared<fast_gicp::FastAPDGICP<PointT, PointT>>();
+    gicp->setMaxCorrespondenceDistance(2.0);
+    gicp->setTransformationEpsilon(0.1);
+    gicp->setAzimuthVar(1.0);
+    gicp->setSearchMethodTarget(gicp->getSearchMethodTarget(), true);
+    std::vector<double> ms;
+    gicp->setInputTarget(scans[0]);
+    for (int rep = 0; rep < 60; rep++) {
+      const int t = 1 + rep % (n_scans - 1), prev = rep == 0 ? 0 : 1 + (rep - 1) % (n_scans - 1);
+      const auto t0 = std::chrono::steady_clock::now();
+      gicp->setInputTarget(scans[prev]);
+      gicp->setInputSource(scans[t]);
+      gicp->align(*aligned);
+      volatile double f = gicp->lastFitnessScore();
+      (void)f;
+      ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+    std::sort(ms.begin() + 5, ms.end());
+    std::printf("latency_cpp_p50_ms %.4f n_points %zu\n", ms[5 + (ms.size() - 5) / 2], scans[1]->size());
   }
   // loop-closure style call without a target: align must print and leave hasConverged() false
   pcl::Registration<PointT, PointT>::Ptr fresh = select_registration_method();

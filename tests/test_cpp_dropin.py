@@ -16,7 +16,10 @@ def _build():
     build.build_library()
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     src = os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp")
-    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include", "pcl_shim"), "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+    # include/ first (the drop-in), then the stand-ins for what a ROS machine provides: PCL / Eigen (pcl_shim) and the
+    # reference's own gicp_settings.hpp (ref_shim; /root/reference does not exist on the GPU box)
+    cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "pcl_shim"),
+           "-I", os.path.join(ROOT, "include", "ref_shim"), src, "-o", EXE,
            "-L", os.path.join(ROOT, "riv-slam_b200"), "-lapdgicp_b200", "-Wl,-rpath," + os.path.join(ROOT, "riv-slam_b200")]
     subprocess.run(cmd, check=True, capture_output=True)
     return EXE
@@ -30,6 +33,35 @@ def test_dropin_header_compiles_and_links():
     used = sorted({l.split()[-1] for l in out.splitlines() if " apd_" in l})
     assert "apd_align" in used and "apd_set_source" in used and "apd_set_target" in used
     assert all(u.startswith("apd_") for u in used)
+
+
+REF_INC = "/root/reference/fast_apdgicp/include"
+
+
+def test_only_the_dropin_header_sits_on_a_reference_include_path():
+    """Anything else under include/fast_gicp/ would shadow a reference header of the same path for the reference's own classes."""
+    found = []
+    for d, _, files in os.walk(os.path.join(ROOT, "include", "fast_gicp")):
+        found += [os.path.relpath(os.path.join(d, f), os.path.join(ROOT, "include")) for f in files]
+    assert found == ["fast_gicp/gicp/fast_apdgicp.hpp"], found
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INC), reason="needs the reference tree (build container only)")
+def test_dropin_coexists_with_the_reference_headers():
+    """registrations.cpp:13-15: reference fast_gicp.hpp (on the reference's LsqRegistration / gicp_settings.hpp) and the drop-in
+    fast_apdgicp.hpp in one TU, this repository's include/ FIRST. Compile-only (the image has no Eigen / PCL to link a CPU class)."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    src = os.path.join(ROOT, "tests", "cpp", "coexist_test.cpp")
+    cmd = [cxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused-parameter", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "pcl_shim"),
+           "-I", REF_INC, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and the resolution really is the intended one: gicp_settings.hpp / lsq_registration.hpp / fast_gicp.hpp from the reference
+    deps = subprocess.run(cmd[:2] + ["-MM"] + cmd[3:], capture_output=True, text=True).stdout
+    for hdr in ("gicp_settings.hpp", "lsq_registration.hpp", "fast_gicp.hpp"):
+        assert f"{REF_INC}/fast_gicp/gicp/{hdr}" in deps, (hdr, deps)
+    assert os.path.join(ROOT, "include", "fast_gicp", "gicp", "fast_apdgicp.hpp") in deps
+    assert "ref_shim" not in deps
 
 
 @pytest.mark.gpu
@@ -110,6 +142,53 @@ def test_dropin_matches_python_path_and_oracle(tmp_path):
     assert np.abs(np.array(sm[11:16:2], dtype=np.float64) - Tm0[:3, 3]).max() < 1e-4
     fm = om.fitness()
     assert abs(float(sm[17]) - fm) <= 1e-5 * fm
+    # the protected hooks at a double pose, through a subclass (fast_apdgicp.hpp:77-83)
+    pr = next(l for l in lines if l[0] == "probe")
+    pv = dict(zip(pr[1::2], pr[2::2]))
+    op = Oracle(**LAUNCH_PARAMS)
+    op.set_source(scans[1]); op.set_target(scans[0])
+    x = np.eye(4); x[0, 3] = 0.1 + 1e-9; x[1, 3] = -0.05 - 3e-10
+    y = x.copy(); y[0, 3] += 0.02
+    e0, H0, b0 = op.linearize_d(x)
+    assert abs(float(pv["lin"]) - e0) <= 2e-11 * abs(e0)   # the same pose rounded to float is off by 2.8e-10 relative: the double path is exercised
+    assert abs(op.linearize(x)[0] - e0) > 1e-10 * abs(e0)
+    assert abs(float(pv["H00"]) - H0[0, 0]) <= 1e-5 * np.abs(H0).max() and abs(float(pv["b3"]) - b0[3]) <= 1e-5 * np.abs(b0).max()
+    op.linearize_d(x)
+    assert abs(float(pv["err_same"]) - e0) <= 2e-11 * abs(e0)
+    assert abs(float(pv["err_moved"]) - op.compute_error_d(y)) <= 1e-9 * abs(e0)   # stale correspondences of the linearize at x
+    op.linearize_d(y)
+    assert abs(float(pv["err_after"]) - op.compute_error_d(y)) <= 1e-9 * abs(e0)   # update_correspondences(y) refreshed them
+    assert float(pv["err_after"]) != float(pv["err_moved"])
+    assert (pv["conv_small"], pv["conv_big"]) == ("1", "0")                          # is_converged with trans eps 0.1
+    rc, Tp, convp, itp = op.align()
+    inl = next(l for l in lines if l[0] == "inliers")
+    assert int(inl[1]) == op.inlier_count(Tp, 0.5) and int(inl[3]) == scans[1].shape[0] and int(inl[7]) == op.inlier_count(Tp, 2.0)
+    assert 0 < int(inl[1]) < int(inl[7])
+    # clouds that die and come back at the same size: every align sees the cloud it was given
+    stale = [l for l in lines if l[0] == "stale"]
+    assert len(stale) == 6
+    for l in stale:
+        rep = int(l[2])
+        srcc = scans[1 + rep % 2].copy()
+        if rep % 2:
+            srcc[:, 0] += np.float32(0.125)
+        os_ = Oracle(**LAUNCH_PARAMS)
+        os_.set_source(srcc); os_.set_target(scans[0])
+        rc, Ts, convs, its = os_.align()
+        assert abs(float(l[4]) - Ts[0, 3]) < 1e-4 and abs(float(l[6]) - Ts[1, 3]) < 1e-4, l
+    # setSourceCovariances + swapSourceAndTarget before the first align: the injected set follows its cloud
+    sw = next(l for l in lines if l[0] == "swapinj")
+    oi = Oracle(**T)
+    oi.set_source(scans[1]); oi.set_target(scans[0])
+    oi.compute_covariances()
+    oi.set_covariances(1, np.tile(4.0 * np.eye(3), (scans[0].shape[0], 1, 1)))
+    rc, Ti, convi, iti = oi.align()
+    assert int(sw[2]) == int(convi)
+    assert np.abs(np.array(sw[4:9:2], dtype=np.float64) - Ti[:3, 3]).max() < 1e-4
+    oi2 = Oracle(**T)
+    oi2.set_source(scans[1]); oi2.set_target(scans[0])
+    rc, Ti2, _, _ = oi2.align()
+    assert np.abs(Ti2[:3, 3] - Ti[:3, 3]).max() > 1e-4    # the injected covariances really change the answer
     # after clearSource() PCL's align returns from initCompute before touching converged_ (stale value, as in PCL)
     assert any(l[:2] == ["cleared", "converged"] for l in lines)
     assert ["notarget", "converged", "0"] in lines

@@ -77,3 +77,70 @@ def test_cuda_path_matches_golden(gold):
         assert abs(g.getFitnessScore() - f[0]) <= 1e-5 * f[0] and abs(g.getFitnessScore(1.5) - f[1]) <= 1e-5 * f[1]
         Hf = gold[f"align_{name}_final_hessian"]
         assert np.abs(g.getFinalHessian() - Hf).max() <= 1e-5 * np.abs(Hf).max()
+
+
+# ---------------------------------------------------------------- LM branches (tests/lm_cases.py)
+
+GOLD_LM = os.path.join(ROOT, "tests", "golden", "apd_golden_lm_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def gold_lm():
+    return np.load(GOLD_LM)
+
+
+def _lm_case_names():
+    import lm_cases
+    return list(lm_cases.CASES)
+
+
+@pytest.mark.parametrize("name", _lm_case_names())
+def test_oracle_reproduces_lm_branch_golden(gold_lm, name):
+    """The oracle keeps walking lsq_registration_impl.hpp:127-173 the same way: rejected trials with lambda * nu
+    growth, rejected-but-converged, "lm not converged!!" and a non-default initial lambda factor."""
+    import lm_cases
+    src, tgt, _ = lm_cases.make_pair()
+    r = lm_cases.run_oracle(name, src, tgt)
+    tr, tr0 = r["trace"], gold_lm[f"{name}_trace"]
+    assert tr.shape == tr0.shape and np.array_equal(tr[:, [0, 1, 7]], tr0[:, [0, 1, 7]])
+    assert np.allclose(tr[:, [2, 3, 5, 6]], tr0[:, [2, 3, 5, 6]], rtol=1e-8)
+    assert np.allclose(tr[:, 4], tr0[:, 4], rtol=1e-4, atol=1e-4)  # rho = (y0 - yi) / ...: cancellation near convergence, summation order varies (OpenMP)
+    assert [int(r["converged"]), r["iterations"], int(r["lm_failed"])] == list(gold_lm[f"{name}_state"])
+    assert np.abs(r["T"] - gold_lm[f"{name}_T"]).max() < 1e-6
+    # the case really is what its name says
+    rej = tr[:, 7] == 0
+    if name.startswith("rejected_then_accepted"):
+        assert rej.sum() >= 6 and tr[:, 1].max() >= 6 and tr[-1, 7] == 1 and r["converged"]
+        # lambda doubles, then x4, x8 ... inside the rejected run (nu *= 2 per rejection, :160-163)
+        run = tr[(tr[:, 0] == 1)]
+        assert np.allclose(run[1:, 5] / run[:-1, 5], 2.0 ** np.arange(1, len(run)), rtol=1e-12)
+    elif name == "rejected_but_converged":
+        assert tr[-1, 7] == 0 and r["converged"] and not r["lm_failed"]
+    elif name.startswith("lm_failed"):
+        assert rej.all() and r["lm_failed"] and not r["converged"] and len(tr) == lm_cases.CASES[name][3]["lm_max_iterations"]
+    else:
+        assert not rej.any() and np.isclose(tr[0, 5], 1e-3 * np.abs(np.diag(r["final_hessian"])).max(), rtol=0.5)
+
+
+@pytest.mark.parametrize("name", ["rejected_then_accepted", "rejected_but_converged", "lm_failed_2"])
+def test_numpy_twin_walks_the_same_lm_branches(gold_lm, name):
+    """oracle/pyref.py (LAPACK solve instead of LDL^T, rotation-vector exponential instead of the quaternion formula)
+    takes the same accept / reject / give-up decisions on the injected-covariance cases."""
+    import lm_cases
+    from oracle.pyref import PyRef
+    src, tgt, _ = lm_cases.make_pair()
+    p = lm_cases.case_params(name)
+    r = lm_cases.run_oracle(name, src, tgt)
+    tw = PyRef(k=p["k_correspondences"], max_corr_dist=p["max_corr_dist"], max_iterations=p["max_iterations"], rotation_epsilon=p["rotation_epsilon"],
+               transformation_epsilon=p["transformation_epsilon"], lm_max_iterations=p["lm_max_iterations"], dist_var=p["dist_var"],
+               azimuth_var=p["azimuth_var"], elevation_var=p["elevation_var"])
+    tw.src = np.asarray(src, dtype=np.float32)[:, :3]
+    tw.tgt = np.asarray(tgt, dtype=np.float32)[:, :3]
+    tw.cov_src, tw.cov_tgt = r["cov_src"], r["cov_tgt"]
+    T, conv, it = tw.align()
+    tr0 = gold_lm[f"{name}_trace"]
+    assert tw.trace.shape == tr0.shape and np.array_equal(tw.trace[:, [0, 1, 7]], tr0[:, [0, 1, 7]])
+    assert np.allclose(tw.trace[:, [2, 3, 5, 6]], tr0[:, [2, 3, 5, 6]], rtol=1e-6)
+    assert np.allclose(tw.trace[:, 4], tr0[:, 4], rtol=1e-3, atol=1e-3)
+    assert [int(conv), it] == list(gold_lm[f"{name}_state"][:2])
+    assert np.abs(T - gold_lm[f"{name}_T"]).max() < 1e-5

@@ -531,7 +531,7 @@ def test_information_matrix_fitness_score(small_pair):
     assert calc.calc_fitness_score(tgt, src, T_gt, max_range=-1.0) == np.finfo(np.float64).max   # nothing in range
     inf = calc.calc_information_matrix(tgt, src, T_gt)
     f0 = o.fitness_score(T_gt)
-    w = lambda lo, hi: np.float32(1e-8 * (lo ** 2 + (hi ** 2 - lo ** 2) * (1 - np.exp(-20.0 * f0)) / (1 - np.exp(-20.0 * 2.5))))
+    w = lambda lo, hi: np.float32(1e-8 * (lo ** 2 + (hi ** 2 - lo ** 2) * (1 - np.exp(-20.0 * f0)) / (1 - np.exp(-20.0 * 0.5))))
     assert np.allclose(np.diag(inf)[:3], 1.0 / float(w(0.1, 5.0)), rtol=1e-5) and np.allclose(np.diag(inf)[3:], 1.0 / float(w(0.05, 0.2)), rtol=1e-5)
     # batched over cloud sets
     H = Handle(0)
