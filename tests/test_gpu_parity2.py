@@ -229,7 +229,20 @@ def test_covariances_on_degenerate_clouds(reg):
         C, C0 = g.getSourceCovariances()[:, :3, :3], o.covariances(0)
         assert np.isfinite(C0).all(), name
         scale = np.maximum(np.abs(C0).max(axis=(1, 2)), 1e-300)
-        assert (np.abs(C - C0).max(axis=(1, 2)) <= REL_TOL * scale).all(), (name, reg)   # kernel == oracle, all points
+        tol0 = np.full(len(C0), REL_TOL)
+        if reg == 4:
+            # FROBENIUS inverts (C + 1e-3 I) and the normalised inverse again (fast_apdgicp_impl.hpp:330-333): two inversions of a
+            # matrix whose condition number reaches 1e7 on a neighbourhood stretched over kilometres (the 'one_outlier' point), by
+            # cofactors (Eigen's 3x3 inverse does the same). The cofactors of a nearly rank-1 matrix cancel, so the first inverse
+            # carries entrywise errors of cond * eps, which the second inversion amplifies by cond again: oracle (no FMA
+            # contraction) and kernel (FMA) agree to cond^2 * eps there, not to 1e-5. Scale the tolerance accordingly.
+            P = np.asarray(cloud, np.float32)[:, :3]
+            X = P[knn].astype(np.float64)
+            Xc = X - X.mean(axis=1, keepdims=True)
+            cond = np.linalg.cond(np.einsum("nka,nkb->nab", Xc, Xc) / 20 + 1e-3 * np.eye(3))
+            tol0 = np.maximum(REL_TOL, 1e-15 * cond * cond)
+            report.append((name, "points with a cond-scaled tolerance", float((tol0 > REL_TOL).mean())))
+        assert (np.abs(C - C0).max(axis=(1, 2)) <= tol0 * scale).all(), (name, reg)   # kernel == oracle, all points
         if reg in (0, 4):
             continue
         usv, vsv, S, vals = _lapack_third_opinion(cloud, knn, reg)
