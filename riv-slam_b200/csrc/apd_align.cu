@@ -25,6 +25,7 @@
 #include <type_traits>
 
 #include "apd_internal.h"
+#include "apd_leaf.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -207,11 +208,129 @@ __device__ __forceinline__ void unpack_record(AlignShared& S) {
 
 template <typename CellT>
 struct TargetView {
-  GridView<CellT> G;
+  GridView<CellT> G;                  // grid mode (target in HBM)
+  LeafView L;                         // leaf mode (target staged in shared memory, apd_leaf.cuh)
   const double2 *cov0, *cov1, *cov2;  // global, sorted target order
   const int* inv0;                    // original index -> sorted position (this cloud)
   int cloud;                          // index in B.tgt (for the coarse pyramid levels)
 };
+
+// covariances of a matched pair -> Mahalanobis matrix of the point (fast_apdgicp_impl.hpp:159-192)
+template <typename CellT>
+__device__ __forceinline__ void store_mahalanobis(const AlignBatch& B, const AlignShared& S, const TargetView<CellT>& T, const double2* __restrict__ c0,
+                                                  const double2* __restrict__ c1, const double2* __restrict__ c2, int i, int pos, size_t sbase, float qx, float qy, float qz) {
+  const double2 a0 = c0[i], a1 = c1[i], a2 = c2[i];
+  const double2 b0 = T.cov0[pos], b1 = T.cov1[pos], b2 = T.cov2[pos];
+  const Sym3 Cd = apd_cov(qx, qy, qz, B.prm);
+  const Sym3 CA = Sym3{a0.x, a0.y, a1.x, a1.y, a2.x, a2.y} + Cd;
+  const Sym3 CB = Sym3{b0.x, b0.y, b1.x, b1.y, b2.x, b2.y} + Cd;
+  const Sym3 RCR = CB + rsrt(S.x0, CA);
+  const Sym3 M = inverse(RCR);
+  B.scratch.m0[sbase + i] = make_double2(M.xx, M.xy);
+  B.scratch.m1[sbase + i] = make_double2(M.xz, M.yy);
+  B.scratch.m2[sbase + i] = make_double2(M.yz, M.zz);
+}
+
+// update_correspondences on a LEAF-mode target (staged in shared memory): a warp takes 32 adjacent sorted source points and
+// searches for all of them together (leaf_nn1: warp-uniform control flow, broadcast candidates). Same rules as the grid
+// version below: seeded bound from the previous correspondence, anchors for points without one, strict gate d2 < dmax^2.
+template <typename CellT>
+__device__ __forceinline__ void correspondence_pass_leaf(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts,
+                                                         const double2* __restrict__ c0, const double2* __restrict__ c1, const double2* __restrict__ c2,
+                                                         int begin, int end, size_t sbase, bool seeded) {
+  const float* Tf = S.Tf;
+  const float r00 = Tf[0], r01 = Tf[1], r02 = Tf[2], t0 = Tf[3];
+  const float r10 = Tf[4], r11 = Tf[5], r12 = Tf[6], t1 = Tf[7];
+  const float r20 = Tf[8], r21 = Tf[9], r22 = Tf[10], t2 = Tf[11];
+  const float inf = __int_as_float(0x7f800000);
+  const bool gated = B.prm.corr_limit2 < 3.0e38f;
+  const ChunkPlan cp = chunk_begin(S, begin, end);
+  for (int i; chunk_next(S, cp, end, i);) {   // warp-uniform: every lane of the warp gets a point or -1
+    const bool act = i >= 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) a = sspts[i];
+    const float qx = xform_row_rn(r00, r01, r02, t0, a.x, a.y, a.z);
+    const float qy = xform_row_rn(r10, r11, r12, t1, a.x, a.y, a.z);
+    const float qz = xform_row_rn(r20, r21, r22, t2, a.x, a.y, a.z);
+    const bool finite = isfinite(qx) && isfinite(qy) && isfinite(qz);  // a non-finite query finds nothing (NaN distances)
+    const int prev = (seeded && act) ? B.scratch.corr[sbase + i] : -2;
+    LeafTop1 v;
+    v.idx = 0xFFFFFFFFu;
+    v.pos = -1;
+    v.d2 = inf;
+    bool search = act && finite, full_ring = false, anchored = false;
+    float unexplored = 0.f;
+    if (prev >= 0) {
+      // the previous correspondence bounds the nearest neighbour (capped by the gate: beyond it nothing can match)
+      const float4 t = leaf_point(T.L, prev);
+      v.d2 = fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2);
+    } else if (prev == -1 && gated) {
+      // ANCHOR of a point that had no correspondence: where it was searched and how far every target point is from there at
+      // least. If it has moved by less than the slack between that bound and the gate, nothing can have come inside the gate.
+      const float4 an = B.scratch.anchor[sbase + i];
+      const float moved = sqrtf(sqdist_rn(qx, qy, qz, an.x, an.y, an.z));
+      if (an.w * 0.99999f - moved * 1.00001f - 1e-3f > sqrtf(B.prm.corr_limit2) * 1.00001f) { search = false; anchored = true; }
+      v.d2 = B.prm.corr_limit2;
+      unexplored = sqrtf(B.prm.corr_limit2);  // everything inside the gate radius is examined
+      full_ring = true;
+    } else if (gated) {
+      // first pass: a little beyond the gate, so that a point without correspondence learns how far the target really is
+      v.d2 = B.prm.corr_wide2;
+      unexplored = sqrtf(B.prm.corr_wide2);
+      full_ring = true;
+    }
+    leaf_nn1(T.L, qx, qy, qz, search, v);
+    if (!act) continue;
+    if (anchored) {
+      B.scratch.sqd[sbase + i] = inf;
+      continue;  // corr stays -1, the anchor stays valid
+    }
+    const bool found = search && v.pos >= 0;
+    const float d2 = found ? v.d2 : inf;
+    const bool ok = found && (double)d2 < B.prm.corr_thr2;
+    B.scratch.corr[sbase + i] = ok ? v.pos : -1;
+    B.scratch.sqd[sbase + i] = d2;
+    if (!ok) {
+      // anchor: every target point is at least min(nearest found, radius that was examined) away; after a seeded search that
+      // lost its correspondence nothing is known (bound 0: always search)
+      const float lb = full_ring ? fminf(found ? sqrtf(d2) : FLT_MAX, unexplored) : 0.f;
+      B.scratch.anchor[sbase + i] = make_float4(qx, qy, qz, lb);
+      continue;
+    }
+    store_mahalanobis(B, S, T, c0, c1, c2, i, v.pos, sbase, qx, qy, qz);
+  }
+  __syncthreads();
+}
+
+// pcl::Registration::getFitnessScore on a LEAF-mode target: per-point squared 1-NN distances (the fixed-order sum follows in fitness_pass)
+template <typename CellT>
+__device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
+                                                    size_t sbase, bool seeded) {
+  const float* Tf = S.Tf;
+  const float inf = __int_as_float(0x7f800000);
+  const ChunkPlan cp = chunk_begin(S, begin, end);
+  for (int i; chunk_next(S, cp, end, i);) {
+    const bool act = i >= 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) a = sspts[i];
+    const float qx = xform_row_rn(Tf[0], Tf[1], Tf[2], Tf[3], a.x, a.y, a.z);
+    const float qy = xform_row_rn(Tf[4], Tf[5], Tf[6], Tf[7], a.x, a.y, a.z);
+    const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
+    const bool finite = isfinite(qx) && isfinite(qy) && isfinite(qz);
+    const int prev = (seeded && act) ? B.scratch.corr[sbase + i] : -1;
+    LeafTop1 v;
+    v.idx = 0xFFFFFFFFu;
+    v.pos = -1;
+    v.d2 = inf;
+    if (prev >= 0) {  // seeded by the correspondence of the last linearization
+      const float4 t = leaf_point(T.L, prev);
+      v.d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
+    }
+    leaf_nn1(T.L, qx, qy, qz, act && finite, v);
+    if (act) B.scratch.fit[sbase + i] = (finite && v.pos >= 0) ? v.d2 : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
+  }
+  __syncthreads();
+}
 
 // update_correspondences for the calling thread's points (fast_apdgicp_impl.hpp:146-193)
 template <typename CellT>
@@ -276,22 +395,13 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, AlignSh
       B.scratch.anchor[sbase + i] = make_float4(qx, qy, qz, lb);
       continue;
     }
-    const double2 a0 = c0[i], a1 = c1[i], a2 = c2[i];
-    const double2 b0 = T.cov0[v.pos], b1 = T.cov1[v.pos], b2 = T.cov2[v.pos];
-    const Sym3 Cd = apd_cov(qx, qy, qz, B.prm);
-    const Sym3 CA = Sym3{a0.x, a0.y, a1.x, a1.y, a2.x, a2.y} + Cd;
-    const Sym3 CB = Sym3{b0.x, b0.y, b1.x, b1.y, b2.x, b2.y} + Cd;
-    const Sym3 RCR = CB + rsrt(S.x0, CA);
-    const Sym3 M = inverse(RCR);
-    B.scratch.m0[sbase + i] = make_double2(M.xx, M.xy);
-    B.scratch.m1[sbase + i] = make_double2(M.xz, M.yy);
-    B.scratch.m2[sbase + i] = make_double2(M.yz, M.zz);
+    store_mahalanobis(B, S, T, c0, c1, c2, i, v.pos, sbase, qx, qy, qz);
   }
   __syncthreads();  // the accumulation passes read these records with a different (static) point-to-thread map
 }
 
 // H/b/error accumulation (FULL, fast_apdgicp_impl.hpp:221-258) or error only (:278-296) at pose x
-template <bool FULL, typename CellT>
+template <bool FULL, bool LEAF, typename CellT>
 __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const double* x, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
                                                 size_t sbase, double (&acc)[kNRed]) {
   const double R00 = x[0], R01 = x[1], R02 = x[2], R10 = x[3], R11 = x[4], R12 = x[5], R20 = x[6], R21 = x[7], R22 = x[8];
@@ -300,7 +410,7 @@ __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const doubl
     const int c = B.scratch.corr[sbase + i];
     if (c < 0) continue;
     const float4 a = sspts[i];
-    const float4 bt = T.G.spts[c];
+    const float4 bt = LEAF ? leaf_point(T.L, c) : T.G.spts[c];
     const double2 m0 = B.scratch.m0[sbase + i], m1 = B.scratch.m1[sbase + i], m2 = B.scratch.m2[sbase + i];
     const double Mxx = m0.x, Mxy = m0.y, Mxz = m1.x, Myy = m1.y, Myz = m2.x, Mzz = m2.y;
     const double ax = (double)a.x, ay = (double)a.y, az = (double)a.z;
@@ -338,29 +448,33 @@ __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const doubl
 }
 
 // pcl::Registration::getFitnessScore(max_range): mean squared 1-NN distance of the transformed source
-template <typename CellT>
+template <bool LEAF, typename CellT>
 __device__ __forceinline__ void fitness_pass(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
                                              size_t sbase, bool seeded, double (&acc)[kNRed]) {
   const float* Tf = S.Tf;
-  const ChunkPlan cp = chunk_begin(S, begin, end);
-  for (int i; chunk_next(S, cp, end, i);) {
-    if (i < 0) continue;
-    const float4 a = sspts[i];
-    const float qx = xform_row_rn(Tf[0], Tf[1], Tf[2], Tf[3], a.x, a.y, a.z);
-    const float qy = xform_row_rn(Tf[4], Tf[5], Tf[6], Tf[7], a.x, a.y, a.z);
-    const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
-    Top1 v;
-    v.init();
-    const int prev = seeded ? B.scratch.corr[sbase + i] : -1;
-    if (prev >= 0) {  // seeded by the correspondence of the last linearization
-      const float4 t = T.G.spts[prev];
-      grid_ball_search(T.G, qx, qy, qz, sqdist_rn(qx, qy, qz, t.x, t.y, t.z), v);
-    } else {
-      pyramid_search<CellT, Top1, false>(T.G, B.tgt, T.cloud, qx, qy, qz, __int_as_float(0x7f800000), v);  // only the distance is used
+  if (LEAF) {
+    fitness_search_leaf(B, S, T, sspts, begin, end, sbase, seeded);
+  } else {
+    const ChunkPlan cp = chunk_begin(S, begin, end);
+    for (int i; chunk_next(S, cp, end, i);) {
+      if (i < 0) continue;
+      const float4 a = sspts[i];
+      const float qx = xform_row_rn(Tf[0], Tf[1], Tf[2], Tf[3], a.x, a.y, a.z);
+      const float qy = xform_row_rn(Tf[4], Tf[5], Tf[6], Tf[7], a.x, a.y, a.z);
+      const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
+      Top1 v;
+      v.init();
+      const int prev = seeded ? B.scratch.corr[sbase + i] : -1;
+      if (prev >= 0) {  // seeded by the correspondence of the last linearization
+        const float4 t = T.G.spts[prev];
+        grid_ball_search(T.G, qx, qy, qz, sqdist_rn(qx, qy, qz, t.x, t.y, t.z), v);
+      } else {
+        pyramid_search<CellT, Top1, false>(T.G, B.tgt, T.cloud, qx, qy, qz, __int_as_float(0x7f800000), v);  // only the distance is used
+      }
+      B.scratch.fit[sbase + i] = v.pos >= 0 ? v.bound2() : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
     }
-    B.scratch.fit[sbase + i] = v.pos >= 0 ? v.bound2() : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
+    __syncthreads();
   }
-  __syncthreads();
   // the sum runs in a fixed point-to-thread order, whatever warp searched the point
   for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
     const float d2 = B.scratch.fit[sbase + i];
@@ -375,7 +489,7 @@ template <int TEAM, bool STAGED>
 __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_constant__ AlignBatch B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ AlignShared S;
-  typedef typename std::conditional<STAGED, uint16_t, unsigned>::type CellT;
+  typedef unsigned CellT;  // grid mode reads the 32-bit cell table from HBM; leaf mode (STAGED) has no cell table at all
 
   TeamCtx<TEAM> tc;
   tc.buf = 0;
@@ -411,23 +525,25 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     const size_t sbase = (size_t)tc.id * B.scratch.max_src;
 
     TargetView<CellT> T;
-    T.G.g = B.tgt.grid[t];
+    if (!STAGED) T.G.g = B.tgt.grid[t];
     T.G.n = nt;
     T.cov0 = B.tgt.cov0 + tb; T.cov1 = B.tgt.cov1 + tb; T.cov2 = B.tgt.cov2 + tb;
     T.inv0 = B.tgt.inv0 + tb;
     T.cloud = t;
     if (STAGED) {
-      float4* s_pts = reinterpret_cast<float4*>(smem_raw);
-      uint16_t* s_cells = reinterpret_cast<uint16_t*>(smem_raw + sizeof(float4) * (size_t)nt);
-      if (S.staged_target != t) {  // consecutive pairs on the same target (scan-to-submap) reuse the staged grid
-        const float4* gp = B.tgt.spts + tb;
-        const unsigned* gc = B.tgt.cells + B.tgt.cell_off[t];
-        stage_grid(s_pts, s_cells, gp, gc, nt, T.G.g.ncells);
+      // leaf mode: the target's Hilbert-sorted points (pair layout) and leaf boxes live in shared memory for the whole pair
+      float4* sP = reinterpret_cast<float4*>(smem_raw);
+      const int nleaf = (nt + kLeaf - 1) / kLeaf;
+      float4* sbox = sP + (size_t)nleaf * kLeaf;
+      if (S.staged_target != t) {  // consecutive pairs on the same target (scan-to-submap) reuse the staged cloud
+        leaf_stage(sP, sbox, B.tgt.spts + tb, B.tgt.lbox + 2 * (size_t)B.tgt.leaf_off[t], nt);
         __syncthreads();
         if (threadIdx.x == 0) S.staged_target = t;
       }
-      T.G.spts = s_pts;
-      T.G.cells = reinterpret_cast<const CellT*>(s_cells);
+      T.L.P = sP;
+      T.L.box = sbox;
+      T.L.n = nt;
+      T.L.nleaf = nleaf;
     } else {
       T.G.spts = B.tgt.spts + tb;
       T.G.cells = reinterpret_cast<const CellT*>(B.tgt.cells + B.tgt.cell_off[t]);
@@ -473,7 +589,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       // ---- compute_error(x0) alone: stale correspondences and Mahalanobis of the last linearize (fast_apdgicp_impl.hpp:275-298) ----
 #pragma unroll
       for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-      accumulate_pass<false>(B, S.x0, T, sspts, begin, end, sbase, acc);
+      accumulate_pass<false, STAGED>(B, S.x0, T, sspts, begin, end, sbase, acc);
       acc[0] = acc[27];
       team_reduce<TEAM, 1>(acc, S, tc);
       last_y0 = S.red[0];
@@ -482,10 +598,11 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     for (int it = 0; have_input && it < (B.mode == 1 ? 1 : (B.mode >= 2 ? 0 : P.max_iterations)); it++) {
       iterations = it;
       // ---- linearize(x0) ----
-      correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
+      if (STAGED) correspondence_pass_leaf(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
+      else correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
 #pragma unroll
       for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-      accumulate_pass<true>(B, S.x0, T, sspts, begin, end, sbase, acc);
+      accumulate_pass<true, STAGED>(B, S.x0, T, sspts, begin, end, sbase, acc);
       team_reduce<TEAM, 29>(acc, S, tc);
       if (threadIdx.x == 0) unpack_record(S);
       if (leader) atomicAdd(&B.counters[0], 1ull);
@@ -537,7 +654,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
           // ---- compute_error(xi): stale correspondences and Mahalanobis ----
 #pragma unroll
           for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-          accumulate_pass<false>(B, S.xi, T, sspts, begin, end, sbase, acc);
+          accumulate_pass<false, STAGED>(B, S.xi, T, sspts, begin, end, sbase, acc);
           acc[0] = acc[27];
           team_reduce<TEAM, 1>(acc, S, tc);
           if (leader) atomicAdd(&B.counters[1], 1ull);
@@ -590,7 +707,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     // ---- final_transformation_ = x0.cast<float>() (:78) and getFitnessScore ----
 #pragma unroll
     for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-    if (have_input && B.mode != 1 && B.mode != 3) fitness_pass(B, S, T, sspts, begin, end, sbase, B.mode == 0 && P.max_iterations > 0, acc);
+    if (have_input && B.mode != 1 && B.mode != 3) fitness_pass<STAGED>(B, S, T, sspts, begin, end, sbase, B.mode == 0 && P.max_iterations > 0, acc);
     team_reduce<TEAM, 2>(acc, S, tc);
     if (leader) {
       apd_result r;
@@ -753,6 +870,60 @@ __global__ void __launch_bounds__(256) fitness_kernel(CloudSetView src, int s, C
   }
 }
 
+// the same on a LEAF-mode target: every CTA stages the target (shared memory), its warps take 32 sorted source points at a time
+__global__ void __launch_bounds__(256) fitness_leaf_kernel(CloudSetView src, int s, CloudSetView tgt, int t, const float* __restrict__ Tf, double max_range, bool strict,
+                                                           double* __restrict__ partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double ws[8][2];
+  const int tb = tgt.pt_off[t], nt = tgt.pt_off[t + 1] - tb;
+  const int sb = src.pt_off[s], ns = src.pt_off[s + 1] - sb;
+  LeafView L;
+  L.n = nt;
+  L.nleaf = (nt + kLeaf - 1) / kLeaf;
+  float4* sP = reinterpret_cast<float4*>(smem_raw);
+  float4* sbox = sP + (size_t)L.nleaf * kLeaf;
+  leaf_stage(sP, sbox, tgt.spts + tb, tgt.lbox + 2 * (size_t)tgt.leaf_off[t], nt);
+  L.P = sP;
+  L.box = sbox;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double sum = 0.0, cnt = 0.0;
+  if (nt > 0) {
+    for (int i0 = (blockIdx.x * nw + warp) * 32; i0 < ns; i0 += gridDim.x * nw * 32) {
+      const int i = i0 + lane;
+      const bool act = i < ns;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) a = src.spts[sb + i];
+      const float qx = xform_row_rn(Tf[0], Tf[1], Tf[2], Tf[3], a.x, a.y, a.z);
+      const float qy = xform_row_rn(Tf[4], Tf[5], Tf[6], Tf[7], a.x, a.y, a.z);
+      const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
+      const bool valid = act && isfinite(qx) && isfinite(qy) && isfinite(qz);
+      LeafTop1 v;
+      v.d2 = __int_as_float(0x7f800000);
+      v.idx = 0xFFFFFFFFu;
+      v.pos = -1;
+      leaf_nn1(L, qx, qy, qz, valid, v);
+      if (valid && v.pos >= 0 && (strict ? (double)v.d2 < max_range : (double)v.d2 <= max_range)) {
+        sum += (double)v.d2;
+        cnt += 1.0;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+  }
+  if (lane == 0) { ws[warp][0] = sum; ws[warp][1] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < nw; w++) { a += ws[w][0]; b += ws[w][1]; }
+    partials[blockIdx.x * 2] = a;
+    partials[blockIdx.x * 2 + 1] = b;
+  }
+}
+
 __global__ void fitness_final_kernel(const double* __restrict__ partials, int blocks, double* __restrict__ out) {
   double a = 0.0, b = 0.0;
   for (int i = 0; i < blocks; i++) { a += partials[i * 2]; b += partials[i * 2 + 1]; }
@@ -786,7 +957,14 @@ cudaError_t launch_count_below(const float* d2, int n, double thr, double* out, 
 
 cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& tgt, int t, const float* T16, double max_range, bool strict, double* partials,
                            int blocks, double* out, cudaStream_t stream, LaunchStats* st) {
-  fitness_kernel<<<blocks, 256, 0, stream>>>(src, s, tgt, t, T16, max_range, strict, partials);
+  if (tgt.lbox) {  // leaf-mode target: staged per CTA, so few CTAs (the staging copy is the fixed cost)
+    const size_t smem = (size_t)((tgt.total_points + kLeaf - 1) / kLeaf + tgt.n_clouds) * (kLeaf * 16 + 32);  // >= the largest cloud of the set
+    cudaError_t e = cudaFuncSetAttribute(fitness_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fitness_leaf_kernel<<<blocks, 256, smem, stream>>>(src, s, tgt, t, T16, max_range, strict, partials);
+  } else {
+    fitness_kernel<<<blocks, 256, 0, stream>>>(src, s, tgt, t, T16, max_range, strict, partials);
+  }
   if (st) st->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -10,6 +10,7 @@
 // cell_sort orders every cell's run by original index so the layout, and with it every later
 // summation order, is deterministic regardless of atomic scheduling.
 #include "apd_internal.h"
+#include "apd_leaf.cuh"
 
 namespace apd {
 
@@ -556,6 +557,207 @@ __global__ void corr_export_kernel(AlignBatch b, int slot, int s, int t, int* __
   }
 }
 
+// ---- leaf build (apd_leaf.cuh): Hilbert order + one bounding box per 32 points, ONE CTA per cloud ----
+// Replaces the three-level grid pyramid for clouds that fit shared memory: bounding box -> 30-bit Hilbert key per point ->
+// stable LSD radix sort (4 x 8 bits, keys and 16-bit indices in shared memory) -> sorted points, inverse permutation and
+// leaf boxes. Non-finite points get the key 2^30 and end up behind every finite point; they are left out of the boxes
+// (pcl::KdTreeFLANN::convertCloudToArray leaves them out of the index). Equal keys keep their input order (the sort is
+// stable), so the layout - and with it every later summation order - is deterministic.
+
+// Skilling's transform: 3 x 10 bit coordinates -> 30-bit Hilbert index (consecutive indices are adjacent cells)
+__device__ __forceinline__ unsigned hilbert30(unsigned x, unsigned y, unsigned z) {
+  unsigned X[3] = {x, y, z};
+#pragma unroll
+  for (unsigned Q = 512u; Q > 1u; Q >>= 1) {
+    const unsigned P = Q - 1u;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (X[i] & Q) X[0] ^= P;
+      else { const unsigned t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  unsigned t = 0u;
+#pragma unroll
+  for (unsigned Q = 512u; Q > 1u; Q >>= 1)
+    if (X[2] & Q) t ^= Q - 1u;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  unsigned key = 0u;
+#pragma unroll
+  for (int b = 0; b < 10; b++) key |= ((X[0] >> b) & 1u) << (3 * b + 2) | ((X[1] >> b) & 1u) << (3 * b + 1) | ((X[2] >> b) & 1u) << (3 * b);
+  return key;
+}
+
+__global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  __shared__ unsigned s_hist[32][256];  // per-warp digit histograms / scatter cursors
+  __shared__ unsigned s_box[32][6];
+  __shared__ unsigned s_warp[33];
+  __shared__ float s_lo[3], s_scale;
+  const int c = blockIdx.x;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int base = cs.pt_off[c];
+  const int n = cs.pt_off[c + 1] - base;
+  if (n == 0) return;
+  const float4* pts = cs.pts + base;
+  unsigned* ka = reinterpret_cast<unsigned*>(sm_raw);
+  unsigned* kb = ka + n;
+  uint16_t* va = reinterpret_cast<uint16_t*>(kb + n);
+  uint16_t* vb = va + n;
+
+  // 1. bounding box of the finite points
+  unsigned mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
+  for (int i = tid; i < n; i += T) {
+    const float4 p = pts[i];
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const unsigned e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
+#pragma unroll
+      for (int a = 0; a < 3; a++) { mn[a] = min(mn[a], e[a]); mx[a] = max(mx[a], e[a]); }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    mn[a] = __reduce_min_sync(0xFFFFFFFFu, mn[a]);
+    mx[a] = __reduce_max_sync(0xFFFFFFFFu, mx[a]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { s_box[warp][a] = mn[a]; s_box[warp][3 + a] = mx[a]; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float ext = 0.f;
+    for (int a = 0; a < 3; a++) {
+      unsigned l = 0xFFFFFFFFu, h = 0u;
+      for (int w = 0; w < (T >> 5); w++) { l = min(l, s_box[w][a]); h = max(h, s_box[w][3 + a]); }
+      const float lo = l > h ? 0.f : dec_f(l), hi = l > h ? 0.f : dec_f(h);
+      s_lo[a] = lo;
+      ext = fmaxf(ext, hi - lo);
+    }
+    s_scale = ext > 0.f ? 1023.0f / ext : 0.f;  // cubic cells: the curve's locality is isotropic
+  }
+  __syncthreads();
+
+  // 2. Hilbert keys
+  const float lox = s_lo[0], loy = s_lo[1], loz = s_lo[2], scale = s_scale;
+  for (int i = tid; i < n; i += T) {
+    const float4 p = pts[i];
+    unsigned key = 0x40000000u;
+    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const unsigned qx = min(1023u, (unsigned)fmaxf((p.x - lox) * scale, 0.f));
+      const unsigned qy = min(1023u, (unsigned)fmaxf((p.y - loy) * scale, 0.f));
+      const unsigned qz = min(1023u, (unsigned)fmaxf((p.z - loz) * scale, 0.f));
+      key = hilbert30(qx, qy, qz);
+    }
+    ka[i] = key;
+    va[i] = (uint16_t)i;
+  }
+  __syncthreads();
+
+  // 3. stable LSD radix sort, 8 bits per pass: every warp owns a contiguous band of 32-element rows and a private histogram;
+  //    bins are ranked digit-major / warp-minor, lanes of a row that share a digit are ordered by lane (__match_any_sync)
+  const int rows = (n + 31) >> 5;
+  const int band = (rows + (T >> 5) - 1) / (T >> 5);
+  const int r0 = min(warp * band, rows), r1 = min(r0 + band, rows);
+  for (int shift = 0; shift < 32; shift += 8) {
+    for (int d = lane; d < 256; d += 32) s_hist[warp][d] = 0u;
+    __syncwarp();
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      if (j < n) atomicAdd(&s_hist[warp][(ka[j] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    {  // exclusive scan of the 256 x 32 bins in (digit, warp) order: 8 consecutive bins per thread
+      unsigned loc[8], sum = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int e = tid * 8 + k;
+        loc[k] = s_hist[e & 31][e >> 5];
+        sum += loc[k];
+      }
+      unsigned incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      if (tid < 32) {
+        const unsigned w = s_warp[tid];
+        unsigned wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+          if (tid >= d) wi += t;
+        }
+        s_warp[tid] = wi - w;
+      }
+      __syncthreads();
+      unsigned run = s_warp[warp] + incl - sum;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int e = tid * 8 + k;
+        s_hist[e & 31][e >> 5] = run;
+        run += loc[k];
+      }
+    }
+    __syncthreads();
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      const bool valid = j < n;
+      const unsigned k = valid ? ka[j] : 0u;
+      const unsigned d = valid ? ((k >> shift) & 255u) : (0x10000u + (unsigned)lane);
+      const unsigned same = __match_any_sync(0xFFFFFFFFu, d);
+      const unsigned rank = __popc(same & ((1u << lane) - 1u));
+      if (valid) {
+        const unsigned dst = s_hist[warp][d] + rank;
+        kb[dst] = k;
+        vb[dst] = va[j];
+      }
+      __syncwarp();
+      if (valid && rank == 0u) s_hist[warp][d] += __popc(same);
+      __syncwarp();
+    }
+    __syncthreads();
+    unsigned* tk = ka; ka = kb; kb = tk;
+    uint16_t* tv = va; va = vb; vb = tv;
+  }
+
+  // 4. sorted points, inverse permutation, leaf boxes (finite points only)
+  float4* spts = cs.spts + base;
+  for (int i = tid; i < n; i += T) {
+    const unsigned idx = va[i];
+    const float4 p = pts[idx];
+    spts[i] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
+    cs.inv0[base + idx] = i;
+  }
+  const int nleaf = (n + kLeaf - 1) / kLeaf;
+  float4* box = cs.lbox + 2 * (size_t)cs.leaf_off[c];
+  for (int l = warp; l < nleaf; l += (T >> 5)) {
+    const int i = l * kLeaf + lane;
+    unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    if (i < n) {
+      const float4 p = pts[va[i]];
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        lo[0] = hi[0] = enc_f(p.x); lo[1] = hi[1] = enc_f(p.y); lo[2] = hi[2] = enc_f(p.z);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
+      hi[a] = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
+    }
+    if (lane == 0) {
+      const float inf = __int_as_float(0x7f800000);
+      const bool empty = lo[0] > hi[0];
+      box[2 * l] = empty ? make_float4(inf, inf, inf, 0.f) : make_float4(dec_f(lo[0]), dec_f(lo[1]), dec_f(lo[2]), 0.f);
+      box[2 * l + 1] = empty ? make_float4(-inf, -inf, -inf, 0.f) : make_float4(dec_f(hi[0]), dec_f(hi[1]), dec_f(hi[2]), 0.f);
+    }
+  }
+}
+
 }  // namespace
 
 #define APD_LAUNCH_CHECK()                      \
@@ -612,6 +814,16 @@ cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap
     return cudaSuccess;
   }
   build_fused_kernel<<<dim3(cs.n_clouds, 1 + kCoarseLevels), 1024, 0, stream>>>(cs, L);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st) {
+  if (cs.n_clouds == 0) return cudaSuccess;
+  const size_t smem = (size_t)max_n * (2 * sizeof(unsigned) + 2 * sizeof(uint16_t)) + 16;
+  cudaError_t e = cudaFuncSetAttribute(leaf_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  leaf_build_kernel<<<cs.n_clouds, 1024, smem, stream>>>(cs);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "apd_internal.h"
+#include "apd_leaf.cuh"
 
 using namespace apd;
 
@@ -114,10 +115,13 @@ struct apd_cloudset_s {
   int n_tiles_build = 0, n_tiles_knn = 0;
   bool grid_built = false, cov_valid = false;
   int cov_k = -1, cov_reg = -1;
-  bool staged = false;      // every cloud's grid fits the shared-memory staging area
-  size_t staged_smem = 0;   // bytes needed for the largest cloud
+  bool staged = false;      // LEAF mode (apd_leaf.cuh): every cloud fits the shared-memory staging area; Hilbert-sorted leaves, no cell tables
+  size_t staged_smem = 0;   // bytes the align kernel stages for the largest cloud
+  DevBuf lbox;              // leaf mode: 2 float4 per leaf
+  int* d_leaf_off = nullptr;
+  long long total_leaves = 0;
   explicit apd_cloudset_s(const std::shared_ptr<Pool>& pool) {
-    for (DevBuf* b : {&pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &inv0, &tables}) b->pool = pool;
+    for (DevBuf* b : {&pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &inv0, &tables, &lbox}) b->pool = pool;
     for (int l = 0; l < kCoarseLevels; l++)
       for (DevBuf* b : {&c_spts[l], &c_cells[l], &c_grid[l]}) b->pool = pool;
   }
@@ -144,6 +148,8 @@ struct apd_cloudset_s {
     v.cov1 = cov1.as<double2>();
     v.cov2 = cov2.as<double2>();
     v.inv0 = inv0.as<int>();
+    v.lbox = staged ? lbox.as<float4>() : nullptr;
+    v.leaf_off = d_leaf_off;
     for (int l = 0; l < kCoarseLevels; l++) {
       v.coarse[l].spts = c_spts[l].as<float4>();
       v.coarse[l].cells = c_cells[l].as<unsigned>();
@@ -275,54 +281,41 @@ int stage_upload(apd_handle h, int slot, size_t bytes, Fill fill, void* dst) {
   return APD_OK;
 }
 
-// Build the device-side description of a ragged batch: offsets, per-cloud cell budgets, tile lists.
-int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
+// Build the device-side description of a ragged batch: offsets, per-cloud cell budgets (grid mode) or leaf offsets (leaf mode), tile lists.
+// force_grid: the caller needs the voxel grid whatever the size (the pre-processing filters count neighbours on it).
+int cloudset_layout(apd_handle h, apd_cloudset_s* cs, bool force_grid = false) {
   const int nc = cs->n_clouds;
   std::vector<int> cap(nc);
   std::vector<long long> cell_off(nc + 1);
-  const size_t budget = staging_budget(h);
-  bool staged = !h->force_unstaged;
-  size_t need_max = 0;
   cs->max_n = 0;
   cs->min_n = nc ? INT32_MAX : 0;
   for (int c = 0; c < nc; c++) {
     const int n = cs->h_off[c + 1] - cs->h_off[c];
     cs->max_n = std::max(cs->max_n, n);
     cs->min_n = std::min(cs->min_n, n);
-    long long want = std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n));
-    want = std::min<long long>(want, 1ll << 28);
-    cap[c] = (int)want;
   }
-  // staging needs 16 B per point + 2 B per cell entry, and local indices that fit 16 bits
-  if (staged) {
-    for (int c = 0; c < nc && staged; c++) {
-      const long long n = cs->h_off[c + 1] - cs->h_off[c];
-      if (n >= 65535 || (size_t)(16 * n + 2 * (2 * n + 2) + 32) > budget) { staged = false; break; }
-      const long long room = ((long long)budget - 16 * n - 32) / 2 - 1;
-      cap[c] = (int)std::min<long long>(cap[c], room);
-      need_max = std::max(need_max, (size_t)(16 * n + 2 * ((long long)cap[c] + 1) + 16));
-    }
-  }
-  if (!staged) {  // undo any clamping done while probing
-    for (int c = 0; c < nc; c++) {
-      const int n = cs->h_off[c + 1] - cs->h_off[c];
-      long long want = std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n));
-      cap[c] = (int)std::min<long long>(want, 1ll << 28);
-    }
-    need_max = 0;
+  // LEAF mode (apd_leaf.cuh): every cloud of the set, staged as 32-point leaves, fits the shared memory of both the align kernel
+  // (staged target + its static state) and the kNN kernel (staged cloud + per-lane pending lists)
+  const size_t stage_bytes = (size_t)((cs->max_n + kLeaf - 1) / kLeaf) * (kLeaf * 16 + 32);
+  const bool leaf = nc > 0 && !force_grid && !h->force_unstaged && cs->max_n <= kLeafMaxPoints && stage_bytes + align_static_smem() + 1024 <= h->smem_optin &&
+                    knn_leaf_smem_bytes(cs->max_n) + 1024 <= h->smem_optin;
+  cs->staged = leaf;
+  cs->staged_smem = leaf ? ((stage_bytes + 15) & ~(size_t)15) : 0;
+  for (int c = 0; c < nc; c++) {
+    const int n = cs->h_off[c + 1] - cs->h_off[c];
+    long long want = leaf ? 1 : std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n));
+    cap[c] = (int)std::min<long long>(want, 1ll << 28);
   }
   cs->max_cap = 0;
   for (int c = 0; c < nc; c++) cs->max_cap = std::max(cs->max_cap, cap[c]);
-  cs->staged = staged && nc > 0;
-  cs->staged_smem = (need_max + 15) & ~(size_t)15;
   long long off = 0;
   for (int c = 0; c < nc; c++) {
     cell_off[c] = off;
-    off += ((long long)cap[c] + 1 + 3) & ~3ll;  // 16-byte aligned tables (stage_grid reads them as uint4)
+    off += leaf ? 0 : (((long long)cap[c] + 1 + 3) & ~3ll);  // 16-byte aligned tables
   }
   cell_off[nc] = off;
   cs->total_cells = off;
-  // coarse pyramid levels: 64x and 4096x fewer cells than the (unclamped) fine budget
+  // coarse pyramid levels (grid mode): 64x and 4096x fewer cells than the fine budget
   std::vector<int> ccap[kCoarseLevels];
   std::vector<long long> ccell_off[kCoarseLevels];
   for (int l = 0; l < kCoarseLevels; l++) {
@@ -334,28 +327,40 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
       const long long fine = std::min<long long>(std::max<long long>(64, (long long)std::llround(h->cells_per_point * (double)n)), 1ll << 28);
       ccap[l][c] = (int)std::max<long long>(8, fine >> (6 * (l + 1)));
       ccell_off[l][c] = o;
-      o += (long long)ccap[l][c] + 1;
+      o += leaf ? 0 : (long long)ccap[l][c] + 1;
     }
     ccell_off[l][nc] = o;
     cs->c_total_cells[l] = o;
   }
+  // leaf offsets (leaf mode)
+  std::vector<int> leaf_off(nc + 1, 0);
+  for (int c = 0; c < nc; c++) leaf_off[c + 1] = leaf_off[c] + (leaf ? (cs->h_off[c + 1] - cs->h_off[c] + kLeaf - 1) / kLeaf : 0);
+  cs->total_leaves = leaf_off[nc];
 
-  // tiles for the per-point build kernels: 1024 points per CTA
+  // tiles for the per-point build kernels (grid mode): 1024 points per CTA
   std::vector<int4> tb;
-  for (int c = 0; c < nc; c++) {
-    const int n = cs->h_off[c + 1] - cs->h_off[c];
-    for (int s = 0; s < n; s += 1024) tb.push_back(int4{c, s, std::min(1024, n - s), 0});
-  }
-  // tiles for kNN + covariance: whole clouds per CTA when the batch alone fills the GPU, otherwise
-  // split so that about two waves of CTAs exist
+  if (!leaf)
+    for (int c = 0; c < nc; c++) {
+      const int n = cs->h_off[c + 1] - cs->h_off[c];
+      for (int s = 0; s < n; s += 1024) tb.push_back(int4{c, s, std::min(1024, n - s), 0});
+    }
+  // tiles for kNN + covariance: whole clouds per CTA when the batch alone fills the GPU, otherwise split so that one wave of CTAs
+  // exists. Grid mode: (cloud, first query, queries); leaf mode: (cloud, first leaf, leaves).
   std::vector<int4> tk;
   const long long target_ctas = h->sm_count;  // one CTA per SM fits (shared memory): a single wave
-  // (a tile smaller than the CTA is spread over all its warps, a few queries per warp: knn_cov_kernel)
-  long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 16);
-  tile_q = std::max<long long>(tile_q, 1);
-  for (int c = 0; c < nc; c++) {
-    const int n = cs->h_off[c + 1] - cs->h_off[c];
-    for (long long s = 0; s < n; s += tile_q) tk.push_back(int4{c, (int)s, (int)std::min<long long>(tile_q, n - s), 0});
+  if (leaf) {
+    const long long per = nc >= target_ctas ? (1ll << 30) : std::max<long long>((cs->total_leaves + target_ctas - 1) / std::max<long long>(target_ctas, 1), 1);
+    for (int c = 0; c < nc; c++) {
+      const int nl = leaf_off[c + 1] - leaf_off[c];
+      for (long long s = 0; s < nl; s += per) tk.push_back(int4{c, (int)s, (int)std::min<long long>(per, nl - s), 0});
+    }
+  } else {
+    long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 16);
+    tile_q = std::max<long long>(tile_q, 1);
+    for (int c = 0; c < nc; c++) {
+      const int n = cs->h_off[c + 1] - cs->h_off[c];
+      for (long long s = 0; s < n; s += tile_q) tk.push_back(int4{c, (int)s, (int)std::min<long long>(tile_q, n - s), 0});
+    }
   }
   cs->n_tiles_build = (int)tb.size();
   cs->n_tiles_knn = (int)tk.size();
@@ -363,7 +368,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   // one device block for the small tables, one copy from the handle's pinned staging buffer: a dozen synchronous
   // copies from pageable vectors plus a stream synchronisation cost ~50 us per cloud set, most of setInputSource
   struct Part { const void* src; size_t bytes; size_t off; };
-  Part parts[5 + 2 * kCoarseLevels];
+  Part parts[6 + 2 * kCoarseLevels];
   int np_ = 0;
   size_t off_b = 0;
   auto add = [&](const void* src, size_t bytes) {
@@ -376,6 +381,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   const int i_cc = add(cap.data(), sizeof(int) * nc);
   const int i_tb = add(tb.data(), sizeof(int4) * tb.size());
   const int i_tk = add(tk.data(), sizeof(int4) * tk.size());
+  const int i_lf = add(leaf_off.data(), sizeof(int) * (nc + 1));
   int i_lo[kCoarseLevels], i_lc[kCoarseLevels];
   for (int l = 0; l < kCoarseLevels; l++) {
     i_lo[l] = add(ccell_off[l].data(), sizeof(long long) * (nc + 1));
@@ -388,6 +394,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
   cs->d_cell_cap = reinterpret_cast<int*>(dbase + parts[i_cc].off);
   cs->d_tiles_build = reinterpret_cast<int4*>(dbase + parts[i_tb].off);
   cs->d_tiles_knn = reinterpret_cast<int4*>(dbase + parts[i_tk].off);
+  cs->d_leaf_off = reinterpret_cast<int*>(dbase + parts[i_lf].off);
   for (int l = 0; l < kCoarseLevels; l++) {
     cs->d_c_cell_off[l] = reinterpret_cast<long long*>(dbase + parts[i_lo[l]].off);
     cs->d_c_cell_cap[l] = reinterpret_cast<int*>(dbase + parts[i_lc[l]].off);
@@ -397,16 +404,21 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs) {
       if (parts[i].bytes) memcpy(host + parts[i].off, parts[i].src, parts[i].bytes);
   }, dbase);
   if (rc_stage) return rc_stage;
+  const size_t np1 = (size_t)std::max<long long>(cs->total, 1);
   CK(cs->grid.reserve(sizeof(GridParams) * std::max(nc, 1)));
-  CK(cs->pts.reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
-  CK(cs->spts.reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
-  CK(cs->cov0.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
-  CK(cs->cov1.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
-  CK(cs->cov2.reserve(sizeof(double2) * std::max<long long>(cs->total, 1)));
+  CK(cs->pts.reserve(sizeof(float4) * np1));
+  CK(cs->spts.reserve(sizeof(float4) * np1));
+  CK(cs->cov0.reserve(sizeof(double2) * np1));
+  CK(cs->cov1.reserve(sizeof(double2) * np1));
+  CK(cs->cov2.reserve(sizeof(double2) * np1));
+  CK(cs->inv0.reserve(sizeof(int) * np1));
+  if (leaf) {
+    CK(cs->lbox.reserve(sizeof(float4) * 2 * (size_t)std::max<long long>(cs->total_leaves, 1)));
+    return APD_OK;  // no cell tables, no pyramid
+  }
   CK(cs->cells.reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->total_cells, 1)));
-  CK(cs->inv0.reserve(sizeof(int) * std::max<long long>(cs->total, 1)));
   for (int l = 0; l < kCoarseLevels; l++) {
-    CK(cs->c_spts[l].reserve(sizeof(float4) * std::max<long long>(cs->total, 1)));
+    CK(cs->c_spts[l].reserve(sizeof(float4) * np1));
     CK(cs->c_cells[l].reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->c_total_cells[l], 1)));
     CK(cs->c_grid[l].reserve(sizeof(GridParams) * std::max(nc, 1)));
   }
@@ -445,6 +457,11 @@ constexpr int kFusedBuildMaxPoints = 16384;  // clouds up to this size are built
 
 int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
   if (cs->grid_built || cs->n_clouds == 0) { cs->grid_built = true; return APD_OK; }
+  if (cs->staged) {  // leaf mode: Hilbert order + leaf boxes, one CTA per cloud
+    CK(launch_leaf_build(cs->view(), cs->max_n, h->stream, &h->stats));
+    cs->grid_built = true;
+    return APD_OK;
+  }
   if (cs->max_n <= kFusedBuildMaxPoints && !h->no_fused_build) {
     // one launch for every level of every cloud
     const size_t np = (size_t)std::max<long long>(cs->total, 1);
@@ -495,14 +512,16 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
   DeviceParams dp = device_params(h->prm);
   dp.knn_packed = h->knn_packed;
   dp.knn_fine_rings = h->knn_fine_rings;
-  CK(launch_knn_cov(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->staged, cs->staged_smem, dp, knn_out, h->stream, &h->stats));
+  if (cs->staged) CK(launch_knn_cov_leaf(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->max_n, dp, knn_out, h->stream, &h->stats));
+  else CK(launch_knn_cov(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, false, 0, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
   cs->cov_reg = h->prm.regularization;
   return APD_OK;
 }
 
-int make_cloudset(apd_handle h, const float* xyz, int stride_bytes, const int32_t* offsets, int n_clouds, int mem, std::shared_ptr<apd_cloudset_s>* out) {
+int make_cloudset(apd_handle h, const float* xyz, int stride_bytes, const int32_t* offsets, int n_clouds, int mem, std::shared_ptr<apd_cloudset_s>* out,
+                  bool force_grid = false) {
   if (n_clouds < 0 || (n_clouds > 0 && !offsets)) return fail(h, APD_ERR_INVALID, "bad cloud offsets");
   if (stride_bytes < 12 || stride_bytes % 4) return fail(h, APD_ERR_INVALID, "stride_bytes must be a multiple of 4 and at least 12");
   auto cs = std::make_shared<apd_cloudset_s>(h->pool);
@@ -514,7 +533,7 @@ int make_cloudset(apd_handle h, const float* xyz, int stride_bytes, const int32_
   }
   cs->total = cs->h_off[n_clouds];
   if (cs->total > 0 && !xyz) return fail(h, APD_ERR_INVALID, "null point pointer");
-  int rc = cloudset_layout(h, cs.get());
+  int rc = cloudset_layout(h, cs.get(), force_grid);
   if (rc) return rc;
   const float* first = xyz ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(xyz) + (size_t)(n_clouds ? offsets[0] : 0) * stride_bytes) : nullptr;
   rc = cloudset_fill(h, cs.get(), first, stride_bytes, mem);
@@ -1607,7 +1626,7 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
       // neighbour counting on the same uniform grid the scan matcher searches
       const int32_t off[2] = {0, m};
       std::shared_ptr<apd_cloudset_s> cs;
-      rc = make_cloudset(h, reinterpret_cast<const float*>(cur), 16, off, 1, APD_MEM_DEVICE, &cs);
+      rc = make_cloudset(h, reinterpret_cast<const float*>(cur), 16, off, 1, APD_MEM_DEVICE, &cs, /*force_grid=*/true);
       if (rc) return rc;
       rc = cloudset_build_grid(h, cs.get());
       if (rc) return rc;

@@ -37,6 +37,10 @@ struct CloudSetView {
   double2* cov2;              //               (yz, zz)
   int* inv0;                  // original local index -> position in spts
   CoarseLevel coarse[kCoarseLevels];
+  // leaf mode (apd_leaf.cuh; every cloud of the set fits shared memory): spts is in Hilbert order, cut into leaves of 32 points;
+  // there is no cell table and no pyramid. lbox == nullptr: grid mode.
+  float4* lbox;               // 2 float4 per leaf (lo, hi)
+  const int* leaf_off;        // [n_clouds+1] offsets into lbox / 2 (cloud c owns ceil(n_c / 32) leaves)
 };
 
 #ifdef __CUDACC__
@@ -183,6 +187,10 @@ cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, 
 // all pyramid levels of every cloud in ONE launch (clouds small enough for one CTA per cloud and level)
 cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap[1 + kCoarseLevels], int* const cellid[1 + kCoarseLevels],
                                     unsigned* const cursor[1 + kCoarseLevels], size_t smem_bytes /*0: global-memory version*/, cudaStream_t stream, LaunchStats* st);
+// Hilbert order + leaf boxes of every cloud of a leaf-mode set (one CTA per cloud)
+cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out /*nullable*/, cudaStream_t stream,
+                                LaunchStats* st);
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,
@@ -214,6 +222,7 @@ cudaError_t launch_pack_xyzi(const float* raw, int stride_floats, int intensity_
 cudaError_t launch_unpack_xyzi(const float4* in, const int* n_dev, int n_max, int stride_floats, int intensity_offset, float* raw, cudaStream_t stream, LaunchStats* st);
 
 size_t align_static_smem();
+size_t knn_leaf_smem_bytes(int max_n);  // dynamic shared memory of the leaf-mode kNN kernel for clouds up to max_n points
 int align_max_teams(int team_kind, int team_size, bool stage_target, size_t smem_bytes);
 
 }  // namespace apd

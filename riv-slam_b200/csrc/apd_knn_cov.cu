@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "apd_internal.h"
+#include "apd_leaf.cuh"
 
 namespace apd {
 
@@ -243,6 +244,254 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
   }
 }
 
+// ======================================================================================================================
+// Leaf-mode kNN + covariance (clouds that fit shared memory; apd_leaf.cuh). A warp owns the 32 queries of one leaf.
+//
+// Candidate bookkeeping. Round 1 inserted every candidate that passed the gate into a sorted register list at once: a
+// 48-instruction min/max network executed by the 7 lanes (of 32) that happened to pass. Here a lane that passes only
+// APPENDS a packed 32-bit key ((top 19 bits of d2) << 13 | slot) to its own pending list in shared memory (one
+// predicated store); the lists are merged into the sorted register list by ALL lanes together at warp-uniform points
+// (before a leaf scan that could overflow a list, and at the end), so the network runs converged. The gate only tightens
+// at a merge; a stale gate costs a few extra appends, never correctness.
+// The packed order is a filter (quantised distance), exactly as in TopKPacked: the list keeps K + 4 entries, proves its own
+// completeness (bucket of entry K+3 strictly beyond the bucket of entry K-1), then the exact 64-bit keys
+// (d2 bits, original index) of its entries are recomputed from the staged points and sorted; a crowded bucket (lattice
+// data, duplicates) falls back to a bounded exact scan. Either way the result is the exact (d2, index)-ordered top-k.
+constexpr int kKnnLeafThreads = 640;
+constexpr int kPendCap = 40;  // pending keys per lane; a leaf scan appends at most 32
+
+template <int K, int M>
+struct LeafTopK {
+  unsigned a[M];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < M; i++) a[i] = 0xFFFFFFFFu;
+  }
+  __device__ __forceinline__ void insert(unsigned key) {
+#pragma unroll
+    for (int j = M - 1; j > 0; j--) a[j] = umin32(a[j], umax32(a[j - 1], key));
+    a[0] = umin32(a[0], key);
+  }
+  // upper edge of the K-th entry's distance bucket; an empty slot (all ones) decodes to a NaN = "no bound yet"
+  __device__ __forceinline__ float bound2() const {
+    constexpr int sh = kLeafPosBits - 1;
+    return __uint_as_float(((a[K - 1] >> kLeafPosBits) << sh) | ((1u << sh) - 1u));
+  }
+  __device__ __forceinline__ bool complete() const { return a[K - 1] == 0xFFFFFFFFu || (a[M - 1] >> kLeafPosBits) > (a[K - 1] >> kLeafPosBits); }
+};
+
+__device__ __forceinline__ unsigned leaf_pack_key(float d2, int pos) { return ((__float_as_uint(d2) >> (kLeafPosBits - 1)) << kLeafPosBits) | (unsigned)pos; }
+
+// exact 64-bit key of a staged slot: (d2 bits) << 32 | original index << 13 | slot  (original index < 8192 in leaf mode)
+__device__ __forceinline__ unsigned long long leaf_exact_key(const LeafView& L, int pos, float qx, float qy, float qz) {
+  const float4 t = leaf_point(L, pos);
+  const float d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
+  return ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)__float_as_uint(t.w) << kLeafPosBits) | (unsigned)pos;
+}
+
+// Rare path (crowded distance bucket): exact top-K of one lane by a scan of every staged point inside `bound2`.
+template <int K>
+__device__ __noinline__ void knn_leaf_exact(LeafView L, float qx, float qy, float qz, float bound2, unsigned long long* out) {
+  TopK<K> tk;
+  tk.init();
+  const int npad = L.nleaf * kLeaf;
+  for (int p = 0; p < npad; p++) {
+    const float4 t = leaf_point(L, p);
+    const float d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
+    if (d2 <= bound2) {
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)__float_as_uint(t.w) << kLeafPosBits) | (unsigned)p;
+      if (key < tk.key[K - 1]) {
+        tk.key[K - 1] = key;
+#pragma unroll
+        for (int j = K - 1; j > 0; j--) {
+          const unsigned long long x = tk.key[j - 1], y = tk.key[j];
+          const bool sw = y < x;
+          tk.key[j - 1] = sw ? y : x;
+          tk.key[j] = sw ? x : y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < K; j++) out[j] = tk.key[j];
+}
+
+template <int K>
+__global__ void __launch_bounds__(kKnnLeafThreads, 1)
+knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out) {
+  constexpr int M = K + 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_next;
+  const int4 tile = tiles[blockIdx.x];  // (cloud, first leaf, leaves, -)
+  if (threadIdx.x == 0) s_next = 0;
+  const int c = tile.x;
+  const int base = cs.pt_off[c];
+  const int n = cs.pt_off[c + 1] - base;
+  LeafView L;
+  L.n = n;
+  L.nleaf = (n + kLeaf - 1) / kLeaf;
+  float4* sP = reinterpret_cast<float4*>(smem_raw);
+  float4* sbox = sP + (size_t)L.nleaf * kLeaf;
+  unsigned* s_list = reinterpret_cast<unsigned*>(sbox + 2 * (size_t)L.nleaf);
+  leaf_stage(sP, sbox, cs.spts + base, cs.lbox + 2 * (size_t)cs.leaf_off[c], n);
+  L.P = sP;
+  L.box = sbox;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NT = 32;  // every warp owns its own region: entry j of lane l at [j * 32 + l] (conflict-free)
+  unsigned* lst = s_list + warp * 32 * kPendCap + lane;
+  // after the search the warp's region holds the K neighbour slots of its lanes (16-bit entries, entry j at nbr[j * 32])
+  uint16_t* nbr = reinterpret_cast<uint16_t*>(s_list + warp * 32 * kPendCap) + lane;
+  const double inv_div = (double)k;
+
+  for (;;) {
+    int k0 = 0;
+    if (lane == 0) k0 = atomicAdd(&s_next, 1);
+    k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+    if (k0 >= tile.z) break;
+    const int g = tile.y + (tile.z - 1 - k0);  // from the end of the curve first (no particular reason beyond determinism)
+    const int q = g * kLeaf + lane;
+    const float4 p = leaf_point(L, q);      // padding slots: NaN
+    const bool valid = q < n && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    const f32x2_t qx2 = f2_pack(p.x, p.x), qy2 = f2_pack(p.y, p.y), qz2 = f2_pack(p.z, p.z);
+
+    LeafTopK<K, M> tk;
+    tk.init();
+    float gate = valid ? FLT_MAX : -1.f;   // a distance above it cannot belong to the result
+    int cnt = 0;
+
+    auto merge = [&]() {
+      const int maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
+      for (int j = 0; j < maxc; j++) tk.insert(j < cnt ? lst[j * NT] : 0xFFFFFFFFu);
+      cnt = 0;
+      if (valid) gate = fminf(tk.bound2(), FLT_MAX);  // NaN (list not full) -> FLT_MAX
+    };
+    auto scan = [&](int leaf) {
+      const ulonglong2* P = reinterpret_cast<const ulonglong2*>(L.P) + leaf * kLeaf;
+#pragma unroll 4
+      for (int j = 0; j < kLeaf / 2; j++) {
+        const ulonglong2 A = P[2 * j], B = P[2 * j + 1];
+        float d0, d1;
+        leaf_pair_d2(qx2, qy2, qz2, A, B.x, d0, d1);
+        const bool p0 = d0 <= gate, p1 = d1 <= gate;  // NaN (padding, non-finite points) fails
+        if (__any_sync(0xFFFFFFFFu, p0 || p1)) {
+          if (p0) { lst[cnt * NT] = leaf_pack_key(d0, leaf * kLeaf + 2 * j); cnt++; }
+          if (p1) { lst[cnt * NT] = leaf_pack_key(d1, leaf * kLeaf + 2 * j + 1); cnt++; }
+        }
+      }
+    };
+
+    if (__any_sync(0xFFFFFFFFu, valid)) {
+      // the query's own leaf first: it fills the list (32 points >= K) and gives every lane a first bound
+      scan(g);
+      merge();
+      float glo[3], ghi[3];
+      leaf_group_box(p.x, p.y, p.z, valid, glo, ghi);
+      LeafSchedule S;
+      S.init(L, glo, ghi, g);
+      for (;;) {
+        const float G = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, valid ? __float_as_uint(gate) : 0u));
+        const int l = S.next(G);
+        if (l < 0) break;
+        const float dl = leaf_point_box2(p.x, p.y, p.z, L.box[2 * l], L.box[2 * l + 1]);
+        if (!__any_sync(0xFFFFFFFFu, valid && dl <= gate)) continue;
+        if (__any_sync(0xFFFFFFFFu, cnt > kPendCap - kLeaf)) merge();
+        scan(l);
+      }
+      if (__any_sync(0xFFFFFFFFu, cnt > 0)) merge();
+    }
+
+    // exact (d2, original index) keys of the K + 4 survivors, sorted; or the bounded exact scan when the packed list cannot
+    // prove that it holds the whole K-th bucket
+    unsigned long long k64[M];
+    if (tk.complete()) {
+#pragma unroll
+      for (int j = 0; j < M; j++) k64[j] = tk.a[j] != 0xFFFFFFFFu ? leaf_exact_key(L, (int)(tk.a[j] & ((1u << kLeafPosBits) - 1u)), p.x, p.y, p.z) : APD_KEY_INF;
+      bool swapped = true;
+      while (swapped) {
+        swapped = false;
+#pragma unroll
+        for (int j = 0; j + 1 < M; j += 2) {
+          const unsigned long long x = k64[j], y = k64[j + 1];
+          const bool sw = y < x;
+          k64[j] = sw ? y : x; k64[j + 1] = sw ? x : y;
+          swapped |= sw;
+        }
+#pragma unroll
+        for (int j = 1; j + 1 < M; j += 2) {
+          const unsigned long long x = k64[j], y = k64[j + 1];
+          const bool sw = y < x;
+          k64[j] = sw ? y : x; k64[j + 1] = sw ? x : y;
+          swapped |= sw;
+        }
+      }
+    } else {
+      unsigned long long fb[K];
+      knn_leaf_exact<K>(L, p.x, p.y, p.z, fminf(tk.bound2(), FLT_MAX), fb);
+#pragma unroll
+      for (int j = 0; j < K; j++) k64[j] = fb[j];
+    }
+    __syncwarp();  // the pending lists are dead from here on: their memory now holds the neighbour slots
+#pragma unroll
+    for (int j = 0; j < K; j++) nbr[j * NT] = (k64[j] >> 32) >= 0x7F800000ull ? (uint16_t)0xFFFFu : (uint16_t)(k64[j] & ((1u << kLeafPosBits) - 1u));
+    // (0xFFFF marks "no neighbour": a non-finite query, or fewer than k finite points in the cloud)
+
+    if (q < n) {
+      // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324), in (d2, index) order from shared memory
+      double mx = 0.0, my = 0.0, mz = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < k; j++) {
+        int s = nbr[j * NT];
+        if (s == 0xFFFF) s = q;
+        const float4 nb = leaf_point(L, s);
+        mx = dadd(mx, (double)nb.x);
+        my = dadd(my, (double)nb.y);
+        mz = dadd(mz, (double)nb.z);
+      }
+      mx = mx / inv_div; my = my / inv_div; mz = mz / inv_div;
+      Sym3 cov{0, 0, 0, 0, 0, 0};
+#pragma unroll 4
+      for (int j = 0; j < k; j++) {
+        int s = nbr[j * NT];
+        if (s == 0xFFFF) s = q;
+        const float4 nb = leaf_point(L, s);
+        const double dx = dsub((double)nb.x, mx), dy = dsub((double)nb.y, my), dz = dsub((double)nb.z, mz);
+        cov.xx = dadd(cov.xx, dmul(dx, dx));
+        cov.xy = dadd(cov.xy, dmul(dx, dy));
+        cov.xz = dadd(cov.xz, dmul(dx, dz));
+        cov.yy = dadd(cov.yy, dmul(dy, dy));
+        cov.yz = dadd(cov.yz, dmul(dy, dz));
+        cov.zz = dadd(cov.zz, dmul(dz, dz));
+      }
+      cov.xx /= inv_div; cov.xy /= inv_div; cov.xz /= inv_div; cov.yy /= inv_div; cov.yz /= inv_div; cov.zz /= inv_div;
+      const Sym3 r = regularize(cov, method);
+      cs.cov0[base + q] = make_double2(r.xx, r.xy);
+      cs.cov1[base + q] = make_double2(r.xz, r.yy);
+      cs.cov2[base + q] = make_double2(r.yz, r.zz);
+      if (knn_out) {
+        int* row = knn_out + ((size_t)base + __float_as_uint(p.w)) * k;
+#pragma unroll 1
+        for (int j = 0; j < k; j++) {
+          const int s = nbr[j * NT];
+          row[j] = s == 0xFFFF ? -1 : (int)__float_as_uint(leaf_point(L, s).w);
+        }
+      }
+    }
+    __syncwarp();  // the next group's pending lists reuse the neighbour slots
+  }
+}
+
+template <int K>
+cudaError_t launch_k_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out, cudaStream_t stream) {
+  const int nleaf = (max_n + kLeaf - 1) / kLeaf;
+  const size_t total = (size_t)nleaf * (kLeaf * 16 + 32) + sizeof(unsigned) * kPendCap * kKnnLeafThreads;
+  cudaError_t e = cudaFuncSetAttribute(knn_cov_leaf_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+  if (e != cudaSuccess) return e;
+  knn_cov_leaf_kernel<K><<<n_tiles, kKnnLeafThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
+  return cudaGetLastError();
+}
+
 template <int K>
 cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm, int* knn_out,
                      cudaStream_t stream) {
@@ -263,6 +512,21 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
 }
 
 }  // namespace
+
+size_t knn_leaf_smem_bytes(int max_n) { return (size_t)((max_n + kLeaf - 1) / kLeaf) * (kLeaf * 16 + 32) + sizeof(unsigned) * kPendCap * kKnnLeafThreads; }
+
+cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out, cudaStream_t stream,
+                                LaunchStats* st) {
+  if (n_tiles == 0) return cudaSuccess;
+  if (st) st->launches++;
+  const int k = prm.k;
+  if (k <= 8) return launch_k_leaf<8>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
+  if (k <= 10) return launch_k_leaf<10>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
+  if (k <= 15) return launch_k_leaf<15>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
+  if (k <= 20) return launch_k_leaf<20>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
+  if (k <= 32) return launch_k_leaf<32>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
+  return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm, int* knn_out,
                            cudaStream_t stream, LaunchStats* st) {
