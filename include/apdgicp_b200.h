@@ -185,7 +185,8 @@ int apd_synchronize(apd_handle h);
  *   "knn_packed"       1 = kNN collects candidates in the packed 32-bit list first (default), 0 = exact list only
  *   "fitness_max_range" max_range of the getFitnessScore the batched calls fill into apd_result.fitness (default DBL_MAX)
  *   "fused_build"      1 = small clouds are gridded by one launch for all levels (default), 0 = the multi-kernel pipeline
- *   "knn_fine_rings"   kNN: rings searched on one level of the grid pyramid before restarting on the next coarser one */
+ *   "knn_fine_rings"   kNN: rings searched on one level of the grid pyramid before restarting on the next coarser one
+ *   "timeline"         1 = the align kernel stamps its phases for apd_get_timeline (profiling aid) */
 int apd_set_option(apd_handle h, const char* name, double value);
 
 /* Batched calc_fitness_score over cloud sets (one launch for a sliding window of keyframe pairs): scores[i] for cloud src_idx[i]
@@ -243,6 +244,13 @@ int apd_odometry_align(apd_handle h, const float* pts, const int32_t* offsets /*
                        const float* guesses, apd_result* out);
 
 /* ---- introspection for benchmarks ---- */
+/* Profiling aid: with apd_set_option(h, "timeline", 1) the align kernel records (phase, %globaltimer ns) stamps for the first pair of a
+ * launch: 0 kernel entered, 1 target staged, 2 iteration starts, 3 correspondences done, 4 H/b reduced, 5 LM trial done, 6 fitness done. */
+int apd_get_timeline(apd_handle h, uint64_t* phase_ns /* 2 values per stamp */, int max_stamps, int* n_stamps);
+/* Same option: counters of the leaf-mode correspondence searches of the last align launch, [0..7] first (unseeded) pass, [8..15] seeded
+ * passes: warp groups, leaves taken from the schedule, broadcast scans, transposed turns, most turns in one group, most leaves in one
+ * group, queries. */
+int apd_get_debug_counters(apd_handle h, uint64_t out[16]);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches claim). */
 int apd_get_launch_count(apd_handle h, int64_t* n);
 /* Iteration counters of the last apd_align_pairs call, summed over pairs: outer iterations (linearize

@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libapdgicp_b200.so")
 HASH_PATH = LIB_PATH + ".srchash"
 SOURCES = ["apd_build.cu", "apd_knn_cov.cu", "apd_align.cu", "apd_preprocess.cu", "apd_capi.cu"]
-HEADERS = ["apd_internal.h", "apd_grid.cuh", "apd_leaf.cuh", "apd_math.cuh", os.path.join("..", "..", "include", "apdgicp_b200.h")]
+HEADERS = ["apd_internal.h", "apd_grid.cuh", "apd_leaf.cuh", "apd_merge_net.cuh", "apd_math.cuh", os.path.join("..", "..", "include", "apdgicp_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -50,6 +50,7 @@ struct AlignShared {
   int pair;
   int staged_target;  // cloud index currently staged, -1 none
   int next;           // next unclaimed source point of the running search pass (dynamic chunks)
+  float4 qslot[kAlignThreads / 32][32];  // leaf mode: every warp's 32 queries (x, y, z, bits of the best d2) for the transposed scans
 };
 
 template <int TEAM>
@@ -90,15 +91,20 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
     return;
   }
   team_sync<TEAM>();
-  if (threadIdx.x < NV) {
+  // Cross-CTA sum, one warp per value: lane l adds the partials of ranks l, l + 32, ... (ascending), then a fixed butterfly.
+  // (One thread per value walking all ranks cost 148 dependent L2 round trips per reduction on a grid team: 30 us of a
+  // 65 us iteration.) The order is the same in every CTA, so all of them end up with identical bits.
+  for (int i = warp; i < NV; i += kAlignThreads / 32) {
     double v = 0.0;
     if (TEAM == TEAM_CLUSTER) {
       cg::cluster_group cl = cg::this_cluster();
-      for (int r = 0; r < tc.size; r++) v += *cl.map_shared_rank(&S.part[tc.buf][threadIdx.x], r);
+      for (int r = lane; r < tc.size; r += 32) v += *cl.map_shared_rank(&S.part[tc.buf][i], r);
     } else {
-      for (int r = 0; r < tc.size; r++) v += __ldcg(&tc.grid_partials[((size_t)tc.buf * tc.size + r) * kNRed + threadIdx.x]);
+      for (int r = lane; r < tc.size; r += 32) v += __ldcg(&tc.grid_partials[((size_t)tc.buf * tc.size + r) * kNRed + i]);
     }
-    S.red[threadIdx.x] = v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) S.red[i] = v;
   }
   tc.buf ^= 1;
   __syncthreads();
@@ -109,30 +115,51 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
 // round-robin 14 % of the kernel's samples sat at the next barrier waiting for the slowest warp (round-1 ncu).
 // The passes only write per-point results, so the assignment does not influence any sum. A CTA with fewer
 // points than threads (cluster and grid teams) spreads them thinly over all its warps.
-struct ChunkPlan {
-  int chunk, lane, begin_, end_;
+// Which source points a CTA of a team owns: blocks of 32 consecutive sorted points dealt round-robin over the team's CTAs
+// (a contiguous split gave one CTA the dense near-range points and another the sparse clutter, whose searches take
+// several times longer: the whole cluster then waited for it at every reduction). A CTA addresses its points by a LOCAL
+// index j in [0, n_local); map(j) is the point, or >= ns past the end of the cloud. Team of one CTA: the identity.
+struct Own {
+  int size, rank, ns, n_local;
+  __device__ __forceinline__ int map(int j) const { return (((j >> 5) * size + rank) << 5) | (j & 31); }
 };
-__device__ __forceinline__ ChunkPlan chunk_begin(AlignShared& S, int begin, int end) {
+__device__ __forceinline__ Own make_own(int ns, int size, int rank) {
+  Own o;
+  o.size = size; o.rank = rank; o.ns = ns;
+  const int blocks = (ns + 31) >> 5;
+  o.n_local = blocks > rank ? ((blocks - rank + size - 1) / size) << 5 : 0;
+  return o;
+}
+
+struct ChunkPlan {
+  int chunk, lane, n_local;
+};
+__device__ __forceinline__ ChunkPlan chunk_begin(AlignShared& S, const Own& own) {
   __syncthreads();
-  if (threadIdx.x == 0) S.next = begin;
+  if (threadIdx.x == 0) S.next = 0;
   __syncthreads();
   const int n_warps = blockDim.x >> 5;
   ChunkPlan c;
-  c.chunk = max(1, min(32, (end - begin + n_warps - 1) / n_warps));
+  // a power of two: a group must not straddle two of the CTA's 32-point blocks (with a team they are far apart in space)
+  const int want = max(1, min(32, (own.n_local + n_warps - 1) / n_warps));
+  c.chunk = 1 << (31 - __clz(want));
   c.lane = threadIdx.x & 31;
-  c.begin_ = begin;
-  c.end_ = end;
+  c.n_local = own.n_local;
   return c;
 }
 // returns false when the pass is over; otherwise i is this lane's point or -1 (idle lane of the chunk)
-__device__ __forceinline__ bool chunk_next(AlignShared& S, const ChunkPlan& c, int end, int& i) {
+__device__ __forceinline__ bool chunk_next(AlignShared& S, const ChunkPlan& c, const Own& own, int& i) {
   int i0 = 0;
   if (c.lane == 0) i0 = atomicAdd(&S.next, c.chunk);
   i0 = __shfl_sync(0xFFFFFFFFu, i0, 0);
-  if (i0 >= end) return false;
-  // handed out from the end of the cell-sorted order: the sparse high-z cells, whose searches are the long ones, go first
-  const int j = c.end_ - 1 - (i0 - c.begin_) - c.lane;
-  i = (c.lane < c.chunk && j >= c.begin_) ? j : -1;
+  if (i0 >= c.n_local) return false;
+  // handed out from the end of the sorted order first
+  const int j = c.n_local - 1 - i0 - c.lane;
+  i = -1;
+  if (c.lane < c.chunk && j >= 0) {
+    const int g = own.map(j);
+    if (g < own.ns) i = g;
+  }
   return true;
 }
 
@@ -215,6 +242,20 @@ struct TargetView {
   int cloud;                          // index in B.tgt (for the coarse pyramid levels)
 };
 
+// profiling aid (apd_set_option "timeline"): nanosecond stamps of the phases of the first pair, read back by apd_get_timeline
+__device__ __forceinline__ void stamp(const AlignBatch& B, int phase) {
+  if (B.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long n = B.timeline[0];
+    if (n < 250) {
+      B.timeline[1 + 2 * n] = (unsigned long long)phase;
+      B.timeline[2 + 2 * n] = t;
+      B.timeline[0] = n + 1;
+    }
+  }
+}
+
 // covariances of a matched pair -> Mahalanobis matrix of the point (fast_apdgicp_impl.hpp:159-192)
 template <typename CellT>
 __device__ __forceinline__ void store_mahalanobis(const AlignBatch& B, const AlignShared& S, const TargetView<CellT>& T, const double2* __restrict__ c0,
@@ -237,15 +278,15 @@ __device__ __forceinline__ void store_mahalanobis(const AlignBatch& B, const Ali
 template <typename CellT>
 __device__ __forceinline__ void correspondence_pass_leaf(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts,
                                                          const double2* __restrict__ c0, const double2* __restrict__ c1, const double2* __restrict__ c2,
-                                                         int begin, int end, size_t sbase, bool seeded) {
+                                                         const Own& own, size_t sbase, bool seeded) {
   const float* Tf = S.Tf;
   const float r00 = Tf[0], r01 = Tf[1], r02 = Tf[2], t0 = Tf[3];
   const float r10 = Tf[4], r11 = Tf[5], r12 = Tf[6], t1 = Tf[7];
   const float r20 = Tf[8], r21 = Tf[9], r22 = Tf[10], t2 = Tf[11];
   const float inf = __int_as_float(0x7f800000);
   const bool gated = B.prm.corr_limit2 < 3.0e38f;
-  const ChunkPlan cp = chunk_begin(S, begin, end);
-  for (int i; chunk_next(S, cp, end, i);) {   // warp-uniform: every lane of the warp gets a point or -1
+  const ChunkPlan cp = chunk_begin(S, own);
+  for (int i; chunk_next(S, cp, own, i);) {   // warp-uniform: every lane of the warp gets a point or -1
     const bool act = i >= 0;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (act) a = sspts[i];
@@ -254,41 +295,43 @@ __device__ __forceinline__ void correspondence_pass_leaf(const AlignBatch& B, Al
     const float qz = xform_row_rn(r20, r21, r22, t2, a.x, a.y, a.z);
     const bool finite = isfinite(qx) && isfinite(qy) && isfinite(qz);  // a non-finite query finds nothing (NaN distances)
     const int prev = (seeded && act) ? B.scratch.corr[sbase + i] : -2;
-    LeafTop1 v;
-    v.idx = 0xFFFFFFFFu;
-    v.pos = -1;
-    v.d2 = inf;
+    float bound = inf;
     bool search = act && finite, full_ring = false, anchored = false;
     float unexplored = 0.f;
     if (prev >= 0) {
       // the previous correspondence bounds the nearest neighbour (capped by the gate: beyond it nothing can match)
       const float4 t = leaf_point(T.L, prev);
-      v.d2 = fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2);
+      bound = fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2);
     } else if (prev == -1 && gated) {
       // ANCHOR of a point that had no correspondence: where it was searched and how far every target point is from there at
       // least. If it has moved by less than the slack between that bound and the gate, nothing can have come inside the gate.
       const float4 an = B.scratch.anchor[sbase + i];
       const float moved = sqrtf(sqdist_rn(qx, qy, qz, an.x, an.y, an.z));
       if (an.w * 0.99999f - moved * 1.00001f - 1e-3f > sqrtf(B.prm.corr_limit2) * 1.00001f) { search = false; anchored = true; }
-      v.d2 = B.prm.corr_limit2;
+      bound = B.prm.corr_limit2;
       unexplored = sqrtf(B.prm.corr_limit2);  // everything inside the gate radius is examined
       full_ring = true;
     } else if (gated) {
       // first pass: a little beyond the gate, so that a point without correspondence learns how far the target really is
-      v.d2 = B.prm.corr_wide2;
+      bound = B.prm.corr_wide2;
       unexplored = sqrtf(B.prm.corr_wide2);
       full_ring = true;
     }
-    leaf_nn1(T.L, qx, qy, qz, search, v);
+    LeafTop1 v;
+    v.init(bound);
+    stamp(B, 10);
+    leaf_nn1(T.L, qx, qy, qz, search, v, S.qslot[threadIdx.x >> 5], B.timeline ? B.timeline + 600 + (seeded ? 8 : 0) : nullptr);
+    stamp(B, 11);
     if (!act) continue;
     if (anchored) {
       B.scratch.sqd[sbase + i] = inf;
       continue;  // corr stays -1, the anchor stays valid
     }
-    const bool found = search && v.pos >= 0;
-    const float d2 = found ? v.d2 : inf;
+    const bool found = search && v.found();
+    const float d2 = found ? v.d2() : inf;
     const bool ok = found && (double)d2 < B.prm.corr_thr2;
-    B.scratch.corr[sbase + i] = ok ? v.pos : -1;
+    const int vpos = v.pos();
+    B.scratch.corr[sbase + i] = ok ? vpos : -1;
     B.scratch.sqd[sbase + i] = d2;
     if (!ok) {
       // anchor: every target point is at least min(nearest found, radius that was examined) away; after a seeded search that
@@ -297,19 +340,22 @@ __device__ __forceinline__ void correspondence_pass_leaf(const AlignBatch& B, Al
       B.scratch.anchor[sbase + i] = make_float4(qx, qy, qz, lb);
       continue;
     }
-    store_mahalanobis(B, S, T, c0, c1, c2, i, v.pos, sbase, qx, qy, qz);
+    store_mahalanobis(B, S, T, c0, c1, c2, i, vpos, sbase, qx, qy, qz);
+    stamp(B, 12);
   }
+  stamp(B, 13);
   __syncthreads();
+  stamp(B, 14);
 }
 
 // pcl::Registration::getFitnessScore on a LEAF-mode target: per-point squared 1-NN distances (the fixed-order sum follows in fitness_pass)
 template <typename CellT>
-__device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
+__device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, const Own& own,
                                                     size_t sbase, bool seeded) {
   const float* Tf = S.Tf;
   const float inf = __int_as_float(0x7f800000);
-  const ChunkPlan cp = chunk_begin(S, begin, end);
-  for (int i; chunk_next(S, cp, end, i);) {
+  const ChunkPlan cp = chunk_begin(S, own);
+  for (int i; chunk_next(S, cp, own, i);) {
     const bool act = i >= 0;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (act) a = sspts[i];
@@ -318,16 +364,15 @@ __device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignSh
     const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
     const bool finite = isfinite(qx) && isfinite(qy) && isfinite(qz);
     const int prev = (seeded && act) ? B.scratch.corr[sbase + i] : -1;
-    LeafTop1 v;
-    v.idx = 0xFFFFFFFFu;
-    v.pos = -1;
-    v.d2 = inf;
+    float bound = inf;
     if (prev >= 0) {  // seeded by the correspondence of the last linearization
       const float4 t = leaf_point(T.L, prev);
-      v.d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
+      bound = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
     }
-    leaf_nn1(T.L, qx, qy, qz, act && finite, v);
-    if (act) B.scratch.fit[sbase + i] = (finite && v.pos >= 0) ? v.d2 : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
+    LeafTop1 v;
+    v.init(bound);
+    leaf_nn1(T.L, qx, qy, qz, act && finite, v, S.qslot[threadIdx.x >> 5]);
+    if (act) B.scratch.fit[sbase + i] = (finite && v.found()) ? v.d2() : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
   }
   __syncthreads();
 }
@@ -336,13 +381,13 @@ __device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignSh
 template <typename CellT>
 __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts,
                                                     const double2* __restrict__ c0, const double2* __restrict__ c1, const double2* __restrict__ c2,
-                                                    int begin, int end, size_t sbase, bool seeded) {
+                                                    const Own& own, size_t sbase, bool seeded) {
   const float* Tf = S.Tf;
   const float r00 = Tf[0], r01 = Tf[1], r02 = Tf[2], t0 = Tf[3];
   const float r10 = Tf[4], r11 = Tf[5], r12 = Tf[6], t1 = Tf[7];
   const float r20 = Tf[8], r21 = Tf[9], r22 = Tf[10], t2 = Tf[11];
-  const ChunkPlan cp = chunk_begin(S, begin, end);
-  for (int i; chunk_next(S, cp, end, i);) {
+  const ChunkPlan cp = chunk_begin(S, own);
+  for (int i; chunk_next(S, cp, own, i);) {
     if (i < 0) continue;
     const float4 a = sspts[i];
     const float qx = xform_row_rn(r00, r01, r02, t0, a.x, a.y, a.z);
@@ -402,11 +447,14 @@ __device__ __forceinline__ void correspondence_pass(const AlignBatch& B, AlignSh
 
 // H/b/error accumulation (FULL, fast_apdgicp_impl.hpp:221-258) or error only (:278-296) at pose x
 template <bool FULL, bool LEAF, typename CellT>
-__device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const double* x, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
+__device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const double* x, const TargetView<CellT>& T, const float4* __restrict__ sspts, const Own& own,
                                                 size_t sbase, double (&acc)[kNRed]) {
   const double R00 = x[0], R01 = x[1], R02 = x[2], R10 = x[3], R11 = x[4], R12 = x[5], R20 = x[6], R21 = x[7], R22 = x[8];
   const double tx = x[9], ty = x[10], tz = x[11];
-  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+  // fixed point-to-thread order (whatever warp searched a point): the sums are deterministic for a launch shape
+  for (int j = threadIdx.x; j < own.n_local; j += blockDim.x) {
+    const int i = own.map(j);
+    if (i >= own.ns) continue;
     const int c = B.scratch.corr[sbase + i];
     if (c < 0) continue;
     const float4 a = sspts[i];
@@ -449,14 +497,14 @@ __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const doubl
 
 // pcl::Registration::getFitnessScore(max_range): mean squared 1-NN distance of the transformed source
 template <bool LEAF, typename CellT>
-__device__ __forceinline__ void fitness_pass(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, int begin, int end,
+__device__ __forceinline__ void fitness_pass(const AlignBatch& B, AlignShared& S, const TargetView<CellT>& T, const float4* __restrict__ sspts, const Own& own,
                                              size_t sbase, bool seeded, double (&acc)[kNRed]) {
   const float* Tf = S.Tf;
   if (LEAF) {
-    fitness_search_leaf(B, S, T, sspts, begin, end, sbase, seeded);
+    fitness_search_leaf(B, S, T, sspts, own, sbase, seeded);
   } else {
-    const ChunkPlan cp = chunk_begin(S, begin, end);
-    for (int i; chunk_next(S, cp, end, i);) {
+    const ChunkPlan cp = chunk_begin(S, own);
+    for (int i; chunk_next(S, cp, own, i);) {
       if (i < 0) continue;
       const float4 a = sspts[i];
       const float qx = xform_row_rn(Tf[0], Tf[1], Tf[2], Tf[3], a.x, a.y, a.z);
@@ -476,7 +524,9 @@ __device__ __forceinline__ void fitness_pass(const AlignBatch& B, AlignShared& S
     __syncthreads();
   }
   // the sum runs in a fixed point-to-thread order, whatever warp searched the point
-  for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+  for (int j = threadIdx.x; j < own.n_local; j += blockDim.x) {
+    const int i = own.map(j);
+    if (i >= own.ns) continue;
     const float d2 = B.scratch.fit[sbase + i];
     if ((double)d2 <= B.max_range) {
       acc[0] += (double)d2;
@@ -508,6 +558,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
   __syncthreads();
 
   int pair = tc.id;
+  stamp(B, 0);  // kernel entered
   for (;;) {
     if (TEAM == TEAM_CTA) {
       __syncthreads();
@@ -549,8 +600,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       T.G.cells = reinterpret_cast<const CellT*>(B.tgt.cells + B.tgt.cell_off[t]);
     }
 
-    const int begin = (int)((long long)ns * tc.rank / tc.size);
-    const int end = (int)((long long)ns * (tc.rank + 1) / tc.size);
+    stamp(B, 1);  // target staged
+    const Own own = make_own(ns, tc.size, tc.rank);
 
     if (threadIdx.x == 0) {
       // x0 = Isometry3d(guess.cast<double>())  (lsq_registration_impl.hpp:56)
@@ -589,7 +640,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       // ---- compute_error(x0) alone: stale correspondences and Mahalanobis of the last linearize (fast_apdgicp_impl.hpp:275-298) ----
 #pragma unroll
       for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-      accumulate_pass<false, STAGED>(B, S.x0, T, sspts, begin, end, sbase, acc);
+      accumulate_pass<false, STAGED>(B, S.x0, T, sspts, own, sbase, acc);
       acc[0] = acc[27];
       team_reduce<TEAM, 1>(acc, S, tc);
       last_y0 = S.red[0];
@@ -598,12 +649,15 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     for (int it = 0; have_input && it < (B.mode == 1 ? 1 : (B.mode >= 2 ? 0 : P.max_iterations)); it++) {
       iterations = it;
       // ---- linearize(x0) ----
-      if (STAGED) correspondence_pass_leaf(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
-      else correspondence_pass(B, S, T, sspts, c0, c1, c2, begin, end, sbase, it > 0);
+      stamp(B, 2);  // iteration starts
+      if (STAGED) correspondence_pass_leaf(B, S, T, sspts, c0, c1, c2, own, sbase, it > 0);
+      else correspondence_pass(B, S, T, sspts, c0, c1, c2, own, sbase, it > 0);
+      stamp(B, 3);  // correspondences + Mahalanobis done
 #pragma unroll
       for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-      accumulate_pass<true, STAGED>(B, S.x0, T, sspts, begin, end, sbase, acc);
+      accumulate_pass<true, STAGED>(B, S.x0, T, sspts, own, sbase, acc);
       team_reduce<TEAM, 29>(acc, S, tc);
+      stamp(B, 4);  // H, b reduced
       if (threadIdx.x == 0) unpack_record(S);
       if (leader) atomicAdd(&B.counters[0], 1ull);
       __syncthreads();
@@ -654,9 +708,10 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
           // ---- compute_error(xi): stale correspondences and Mahalanobis ----
 #pragma unroll
           for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-          accumulate_pass<false, STAGED>(B, S.xi, T, sspts, begin, end, sbase, acc);
+          accumulate_pass<false, STAGED>(B, S.xi, T, sspts, own, sbase, acc);
           acc[0] = acc[27];
           team_reduce<TEAM, 1>(acc, S, tc);
+          stamp(B, 5);  // LM solve + error pass reduced
           if (leader) atomicAdd(&B.counters[1], 1ull);
           if (threadIdx.x == 0) {
             const double yi = S.red[0];
@@ -707,8 +762,9 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
     // ---- final_transformation_ = x0.cast<float>() (:78) and getFitnessScore ----
 #pragma unroll
     for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
-    if (have_input && B.mode != 1 && B.mode != 3) fitness_pass<STAGED>(B, S, T, sspts, begin, end, sbase, B.mode == 0 && P.max_iterations > 0, acc);
+    if (have_input && B.mode != 1 && B.mode != 3) fitness_pass<STAGED>(B, S, T, sspts, own, sbase, B.mode == 0 && P.max_iterations > 0, acc);
     team_reduce<TEAM, 2>(acc, S, tc);
+    stamp(B, 6);  // fitness done
     if (leader) {
       apd_result r;
       for (int i = 0; i < 3; i++) {
@@ -875,6 +931,7 @@ __global__ void __launch_bounds__(256) fitness_leaf_kernel(CloudSetView src, int
                                                            double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double ws[8][2];
+  __shared__ float4 qslot[8][32];
   const int tb = tgt.pt_off[t], nt = tgt.pt_off[t + 1] - tb;
   const int sb = src.pt_off[s], ns = src.pt_off[s + 1] - sb;
   LeafView L;
@@ -899,12 +956,10 @@ __global__ void __launch_bounds__(256) fitness_leaf_kernel(CloudSetView src, int
       const float qz = xform_row_rn(Tf[8], Tf[9], Tf[10], Tf[11], a.x, a.y, a.z);
       const bool valid = act && isfinite(qx) && isfinite(qy) && isfinite(qz);
       LeafTop1 v;
-      v.d2 = __int_as_float(0x7f800000);
-      v.idx = 0xFFFFFFFFu;
-      v.pos = -1;
-      leaf_nn1(L, qx, qy, qz, valid, v);
-      if (valid && v.pos >= 0 && (strict ? (double)v.d2 < max_range : (double)v.d2 <= max_range)) {
-        sum += (double)v.d2;
+      v.init(__int_as_float(0x7f800000));
+      leaf_nn1(L, qx, qy, qz, valid, v, qslot[warp]);
+      if (valid && v.found() && (strict ? (double)v.d2() < max_range : (double)v.d2() <= max_range)) {
+        sum += (double)v.d2();
         cnt += 1.0;
       }
     }

@@ -181,9 +181,10 @@ struct apd_context {
   int no_smem_build = 0;
   double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
+  int timeline_opt = 0;  // profiling aid: the align kernel stamps its phases (apd_get_timeline)
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, sc_fit, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
-      counters, grid_partials, misc, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
+      counters, grid_partials, misc, timeline, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
   int scratch_slots = 0, scratch_max_src = 0;
   // last single-pair alignment
   bool has_last = false;
@@ -580,12 +581,19 @@ int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tg
     // a CTA pass handles kAlignThreads points at a time: no point in more CTAs than that
     while (size > 1 && (long long)src->max_n < (long long)(size / 2) * kAlignThreads) size /= 2;
   }
-  if (!p.staged && h->team_size <= 0 && n_pairs == 1 && src->max_n > 16 * kAlignThreads * 2) {
+  const bool force_grid_team = h->team_size >= 1000;  // option team_size = 1000 + n: a cooperative grid of up to n CTAs on one pair (experiments)
+  if (force_grid_team) size = 1;
+  // One pair: a cooperative grid. Measured on a 5000-point pair (scripts/latency_probe.py): 16-CTA cluster 147 us, grid of 74 CTAs 118 us,
+  // of 148 CTAs 123 us per align; a warp then owns a handful of queries and the transposed leaf scan costs what those queries need.
+  const bool single_staged = p.staged && h->team_size <= 0 && n_pairs == 1 && plan_for_pairs <= 1 && src->max_n >= 256;
+  if ((force_grid_team && n_pairs == 1) || single_staged || (!p.staged && h->team_size <= 0 && n_pairs == 1 && src->max_n > 16 * kAlignThreads * 2)) {
     // large source against a large target: the whole GPU on one pair
-    const int max_blocks = align_max_teams(TEAM_GRID, 0, false, 0);
+    const int max_blocks = align_max_teams(TEAM_GRID, 0, p.staged, p.smem);
     if (max_blocks >= 2) {
       p.kind = TEAM_GRID;
       p.size = std::min(max_blocks, (src->max_n + kAlignThreads - 1) / kAlignThreads);
+      if (force_grid_team) p.size = std::max(2, std::min(max_blocks, h->team_size - 1000));
+      else if (single_staged) p.size = std::max(2, std::min(max_blocks, (src->max_n + 63) / 64));  // ~64 points per CTA: 4 queries per warp
       p.teams = 1;
       *plan = p;
       return APD_OK;
@@ -704,6 +712,11 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   b.scratch.anchor = h->sc_anchor.as<float4>();
   b.scratch.fit = h->sc_fit.as<float>();
   b.prm = device_params(h->prm);
+  if (h->timeline_opt) {
+    CK(h->timeline.reserve(sizeof(unsigned long long) * 1024));
+    CK(cudaMemsetAsync(h->timeline.p, 0, sizeof(unsigned long long) * 1024, h->stream));
+    b.timeline = h->timeline.as<unsigned long long>();
+  }
   b.mode = c.mode;
   b.min_points = c.min_points;
   b.max_range = c.max_range;
@@ -864,6 +877,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "smem_build") h->no_smem_build = value == 0;
   else if (n == "fitness_max_range") h->fitness_max_range = value;
   else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
+  else if (n == "timeline") h->timeline_opt = value != 0;
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
 }
@@ -1726,6 +1740,30 @@ int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which,
 int apd_synchronize(apd_handle h) {
   if (!h) return APD_ERR_INVALID;
   DeviceGuard guard(h->device);
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_get_timeline(apd_handle h, uint64_t* phase_ns /* 2 per stamp */, int max_stamps, int* n_stamps) {
+  if (!h || !n_stamps) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  *n_stamps = 0;
+  if (!h->timeline.p) return APD_OK;
+  unsigned long long buf[512];
+  CK(cudaMemcpyAsync(buf, h->timeline.p, sizeof(buf), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int n = (int)std::min<unsigned long long>(buf[0], 250);
+  *n_stamps = n;
+  if (phase_ns) memcpy(phase_ns, buf + 1, sizeof(unsigned long long) * 2 * std::min(n, max_stamps));
+  return APD_OK;
+}
+
+int apd_get_debug_counters(apd_handle h, uint64_t out[16]) {
+  if (!h || !out) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  memset(out, 0, sizeof(uint64_t) * 16);
+  if (!h->timeline.p) return APD_OK;
+  CK(cudaMemcpyAsync(out, h->timeline.as<unsigned long long>() + 600, sizeof(uint64_t) * 16, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return APD_OK;
 }

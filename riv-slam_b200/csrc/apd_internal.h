@@ -169,6 +169,7 @@ struct AlignBatch {
                            // 3 = compute_error only at the given pose, with the correspondences and Mahalanobis matrices the
                            //     last linearize left in the slot (fast_apdgicp_impl.hpp:275-298): out->error
   double max_range;        // fitness gate (getFitnessScore max_range)
+  unsigned long long* timeline;  // nullable (option "timeline"): thread 0 of team 0's first CTA stamps %globaltimer at phase boundaries, [0] = count
 };
 
 struct LaunchStats {

@@ -12,6 +12,7 @@
 
 #include "apd_internal.h"
 #include "apd_leaf.cuh"
+#include "apd_merge_net.cuh"
 
 namespace apd {
 
@@ -282,11 +283,11 @@ struct LeafTopK {
 
 __device__ __forceinline__ unsigned leaf_pack_key(float d2, int pos) { return ((__float_as_uint(d2) >> (kLeafPosBits - 1)) << kLeafPosBits) | (unsigned)pos; }
 
-// exact 64-bit key of a staged slot: (d2 bits) << 32 | original index << 13 | slot  (original index < 8192 in leaf mode)
+// exact 64-bit key of a staged slot: (d2 bits) << 32 | tag, tag = original index << 13 | slot (apd_leaf.cuh)
 __device__ __forceinline__ unsigned long long leaf_exact_key(const LeafView& L, int pos, float qx, float qy, float qz) {
   const float4 t = leaf_point(L, pos);
   const float d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
-  return ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)__float_as_uint(t.w) << kLeafPosBits) | (unsigned)pos;
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(t.w);
 }
 
 // Rare path (crowded distance bucket): exact top-K of one lane by a scan of every staged point inside `bound2`.
@@ -299,7 +300,7 @@ __device__ __noinline__ void knn_leaf_exact(LeafView L, float qx, float qy, floa
     const float4 t = leaf_point(L, p);
     const float d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
     if (d2 <= bound2) {
-      const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | ((unsigned long long)__float_as_uint(t.w) << kLeafPosBits) | (unsigned)p;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(t.w);
       if (key < tk.key[K - 1]) {
         tk.key[K - 1] = key;
 #pragma unroll
@@ -361,9 +362,20 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
     float gate = valid ? FLT_MAX : -1.f;   // a distance above it cannot belong to the result
     int cnt = 0;
 
+    // Merge the pending keys of every lane into its sorted list, all lanes together. Batches of 8 go through a sorting network
+    // and a pruned Batcher merge (apd_merge_net.cuh: 158 min/max per 8 keys); a remainder of one or two keys is inserted one at
+    // a time (48 min/max each). A lane with fewer pending keys than the busiest lane merges empty slots (all ones).
     auto merge = [&]() {
       const int maxc = __reduce_max_sync(0xFFFFFFFFu, cnt);
-      for (int j = 0; j < maxc; j++) tk.insert(j < cnt ? lst[j * NT] : 0xFFFFFFFFu);
+      int j = 0;
+      for (; maxc - j >= 3; j += 8) {
+        unsigned b[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) b[t] = (j + t < cnt) ? lst[(j + t) * NT] : 0xFFFFFFFFu;
+        sort8_net(b);
+        MergeNet8<M>::run(tk.a, b);
+      }
+      for (; j < maxc; j++) tk.insert(j < cnt ? lst[j * NT] : 0xFFFFFFFFu);
       cnt = 0;
       if (valid) gate = fminf(tk.bound2(), FLT_MAX);  // NaN (list not full) -> FLT_MAX
     };
@@ -383,23 +395,30 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
     };
 
     if (__any_sync(0xFFFFFFFFu, valid)) {
-      // the query's own leaf first: it fills the list (32 points >= K) and gives every lane a first bound
-      scan(g);
-      merge();
-      float glo[3], ghi[3];
-      leaf_group_box(p.x, p.y, p.z, valid, glo, ghi);
+      // The query's own leaf first (it fills the list: 32 points >= K, and gives every lane a first bound), then the other
+      // leaves nearest first. ONE scan site and ONE merge site: the two are the bulk of the loop's instruction footprint.
       LeafSchedule S;
-      S.init(L, glo, ghi, g);
+      int l = g;
+      bool first = true;
       for (;;) {
-        const float G = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, valid ? __float_as_uint(gate) : 0u));
-        const int l = S.next(G);
+        if (l >= 0) scan(l);
+        // merge when the next scan (up to 32 appends) could overflow a list, after the own leaf, and at the very end
+        if (first || __any_sync(0xFFFFFFFFu, l < 0 ? cnt > 0 : cnt > kPendCap - kLeaf)) merge();
         if (l < 0) break;
-        const float dl = leaf_point_box2(p.x, p.y, p.z, L.box[2 * l], L.box[2 * l + 1]);
-        if (!__any_sync(0xFFFFFFFFu, valid && dl <= gate)) continue;
-        if (__any_sync(0xFFFFFFFFu, cnt > kPendCap - kLeaf)) merge();
-        scan(l);
+        if (first) {
+          float glo[3], ghi[3];
+          leaf_group_box(p.x, p.y, p.z, valid, glo, ghi);
+          S.init(L, glo, ghi, g);
+          first = false;
+        }
+        for (;;) {  // the nearest unvisited leaf that some lane's bound reaches
+          const float G = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, valid ? __float_as_uint(gate) : 0u));
+          l = S.next(G);
+          if (l < 0) break;
+          const float dl = leaf_point_box2(p.x, p.y, p.z, L.box[2 * l], L.box[2 * l + 1]);
+          if (__any_sync(0xFFFFFFFFu, valid && dl <= gate)) break;
+        }
       }
-      if (__any_sync(0xFFFFFFFFu, cnt > 0)) merge();
     }
 
     // exact (d2, original index) keys of the K + 4 survivors, sorted; or the bounded exact scan when the packed list cannot
@@ -470,11 +489,11 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       cs.cov1[base + q] = make_double2(r.xz, r.yy);
       cs.cov2[base + q] = make_double2(r.yz, r.zz);
       if (knn_out) {
-        int* row = knn_out + ((size_t)base + __float_as_uint(p.w)) * k;
+        int* row = knn_out + ((size_t)base + leaf_tag_index(p.w)) * k;
 #pragma unroll 1
         for (int j = 0; j < k; j++) {
           const int s = nbr[j * NT];
-          row[j] = s == 0xFFFF ? -1 : (int)__float_as_uint(leaf_point(L, s).w);
+          row[j] = s == 0xFFFF ? -1 : (int)leaf_tag_index(leaf_point(L, s).w);
         }
       }
     }

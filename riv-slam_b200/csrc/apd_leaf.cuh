@@ -28,6 +28,7 @@ constexpr int kLeaf = 32;              // points per leaf = lanes per warp
 constexpr int kLeafMaxPoints = 8192;   // 13-bit positions in packed keys; 256 leaves = 8 rounds of cached box distances
 constexpr int kLeafPosBits = 13;
 constexpr int kLeafMaxRounds = kLeafMaxPoints / kLeaf / 32;
+constexpr int kLeafTransposeMax = 20;  // 1-NN: up to this many queries needing a leaf take turns (transposed scan); more: one broadcast scan
 
 #ifdef __CUDACC__
 
@@ -75,7 +76,9 @@ __device__ __forceinline__ void leaf_pair_d2(f32x2_t qx2, f32x2_t qy2, f32x2_t q
 }
 
 // A staged cloud: candidate pairs in shared memory, NEGATED so that a difference is one packed add:
-//   pair j = points 2j, 2j+1:  P[2j] = (-x0, -x1, -y0, -y1)   P[2j+1] = (-z0, -z1, orig0, orig1)   (orig = original index bits)
+//   pair j = points 2j, 2j+1:  P[2j] = (-x0, -x1, -y0, -y1)   P[2j+1] = (-z0, -z1, tag0, tag1)
+//   tag = original index << 13 | slot: the low word of a candidate's exact 64-bit key (d2 bits << 32 | tag), whose unsigned order
+//   IS the (d2, original index) order of the results (original indices are below 8192 in leaf mode)
 // Slots beyond n (the last leaf is padded to 32) hold NaN coordinates: every distance to them is NaN and fails every
 // `<=` test. Non-finite input points behave the same way and are sorted to the end of the cloud by the build.
 struct LeafView {
@@ -97,20 +100,21 @@ __device__ __forceinline__ void leaf_stage(float4* __restrict__ sP, float4* __re
   const float qnan = __int_as_float(0x7fc00000);
   for (int j = threadIdx.x; j < npairs; j += blockDim.x) {
     const int i0 = 2 * j, i1 = 2 * j + 1;
-    float4 a = make_float4(qnan, qnan, qnan, __uint_as_float(0xFFFFFFFFu)), b = a;
+    float4 a = make_float4(qnan, qnan, qnan, __uint_as_float(0x7FFFFu)), b = a;
     if (i0 < n) a = gspts[i0];
     if (i1 < n) b = gspts[i1];
     sP[2 * j] = make_float4(-a.x, -b.x, -a.y, -b.y);
-    sP[2 * j + 1] = make_float4(-a.z, -b.z, a.w, b.w);
+    sP[2 * j + 1] = make_float4(-a.z, -b.z, __uint_as_float(__float_as_uint(a.w) << kLeafPosBits | (unsigned)i0), __uint_as_float(__float_as_uint(b.w) << kLeafPosBits | (unsigned)i1));
   }
   for (int j = threadIdx.x; j < 2 * nleaf; j += blockDim.x) sbox[j] = gbox[j];
 }
 
-// the point in slot `pos` of a staged cloud: (x, y, z, original index bits)
+// the point in slot `pos` of a staged cloud: (x, y, z, tag bits); tag >> 13 = original index
 __device__ __forceinline__ float4 leaf_point(const LeafView& L, int pos) {
   const float4 A = L.P[2 * (pos >> 1)], B = L.P[2 * (pos >> 1) + 1];
   return (pos & 1) ? make_float4(-A.y, -A.w, -B.y, B.w) : make_float4(-A.x, -A.z, -B.x, B.z);
 }
+__device__ __forceinline__ unsigned leaf_tag_index(float w) { return __float_as_uint(w) >> kLeafPosBits; }
 
 // squared distance from a point to a box (0 inside), as a lower bound of the distance to every point of the box;
 // scaled down so that float rounding of this bound itself can never exclude a candidate (same 0.99999 as the grid search)
@@ -174,14 +178,19 @@ __device__ __forceinline__ void leaf_group_box(float qx, float qy, float qz, boo
 }
 
 // ---- 1-NN (update_correspondences, getFitnessScore) ----
-// Per-lane state of an exact nearest-neighbour search ordered by (d2, original index).
+// Per-lane state of an exact nearest-neighbour search: the smallest 64-bit key (d2 bits << 32 | original index << 13 | slot)
+// seen so far. Unsigned order of the key = (d2, original index) order, so ties break by index like the oracle.
+// Before anything is found the low word is all ones and the high word is the search bound: a candidate AT the bound still wins.
 struct LeafTop1 {
-  float d2;       // best squared distance so far; also the lane's search bound
-  unsigned idx;   // original index of the best (tie-break)
-  int pos;        // its slot in the staged (sorted) target, -1 = none
+  unsigned long long key;
+  __device__ __forceinline__ void init(float bound2) { key = ((unsigned long long)__float_as_uint(bound2) << 32) | 0xFFFFFFFFull; }
+  __device__ __forceinline__ float d2() const { return __uint_as_float((unsigned)(key >> 32)); }  // best distance, or the bound while nothing is found
+  __device__ __forceinline__ bool found() const { return (unsigned)key != 0xFFFFFFFFu; }
+  __device__ __forceinline__ int pos() const { return found() ? (int)((unsigned)key & ((1u << kLeafPosBits) - 1u)) : -1; }
 };
 
-// Scan one leaf for all 32 lanes: candidates are broadcast, two per packed instruction.
+// Scan one leaf for all 32 lanes: candidates are broadcast, two per packed instruction. The update (a 64-bit unsigned minimum)
+// sits behind a warp vote: once the first candidates are in, most pairs improve nobody's result.
 __device__ __forceinline__ void leaf_scan_top1(const LeafView& L, int leaf, f32x2_t qx2, f32x2_t qy2, f32x2_t qz2, LeafTop1& v) {
   const ulonglong2* P = reinterpret_cast<const ulonglong2*>(L.P) + leaf * kLeaf;  // 2 x 16 bytes per pair, 16 pairs
 #pragma unroll 4
@@ -189,36 +198,104 @@ __device__ __forceinline__ void leaf_scan_top1(const LeafView& L, int leaf, f32x
     const ulonglong2 A = P[2 * j], B = P[2 * j + 1];
     float d0, d1;
     leaf_pair_d2(qx2, qy2, qz2, A, B.x, d0, d1);
-    // (d2, index) lexicographic minimum; NaN (padding, non-finite points) compares false
-    if (d0 <= v.d2) {
-      const unsigned i = (unsigned)(B.y & 0xFFFFFFFFull);
-      if (d0 < v.d2 || i < v.idx) { v.d2 = d0; v.idx = i; v.pos = leaf * kLeaf + 2 * j; }
-    }
-    if (d1 <= v.d2) {
-      const unsigned i = (unsigned)(B.y >> 32);
-      if (d1 < v.d2 || i < v.idx) { v.d2 = d1; v.idx = i; v.pos = leaf * kLeaf + 2 * j + 1; }
+    const float best = v.d2();
+    // NaN distances (padding, non-finite points) compare false; an invalid lane's key is 0 (best = +0, and its distances are NaN)
+    if (__any_sync(0xFFFFFFFFu, d0 <= best || d1 <= best)) {
+      const unsigned long long k0 = ((unsigned long long)__float_as_uint(d0) << 32) | (B.y & 0xFFFFFFFFull);
+      const unsigned long long k1 = ((unsigned long long)__float_as_uint(d1) << 32) | (B.y >> 32);
+      const unsigned long long k = k0 < k1 ? k0 : k1;  // NaN bit patterns are above +inf: they never win
+      if (k < v.key) v.key = k;
     }
   }
 }
 
-// Exact nearest neighbour of every lane's query among the staged target, inside the lane's initial bound v.d2
-// (+inf: unbounded; a seed candidate may already sit in v). valid == false lanes take no part. Warp-collective.
-__device__ __forceinline__ void leaf_nn1(const LeafView& L, float qx, float qy, float qz, bool valid, LeafTop1& v) {
+// The same leaf, TRANSPOSED: every lane holds one CANDIDATE of the leaf, and the queries that need the leaf (bit mask `need`)
+// take turns. One turn = broadcast the query from the warp's shared-memory slots, 32 distances in parallel, one REDUX for the
+// minimum; only when that minimum reaches the query's current best is anything updated. A turn costs ~15 instructions, so the
+// transposed form wins whenever fewer than about 20 of the 32 queries need the leaf - the normal case once a search is seeded
+// (a query's ball touches 2-3 leaf boxes, the group's 32 balls together touch 7-8).
+// qslot: the warp's 32 x float4 (qx, qy, qz, bits of the query's best d2 / bound), kept current by the owning lane.
+__device__ __forceinline__ void leaf_scan_top1_transposed(const LeafView& L, int leaf, unsigned need, float4* __restrict__ qslot, LeafTop1& v) {
+  const int lane = threadIdx.x & 31;
+  const float4 c = leaf_point(L, leaf * kLeaf + lane);  // this lane's candidate (NaN coordinates in padding slots)
+  const unsigned ctag = __float_as_uint(c.w);
+  // Two queries per turn: the loads, the distance chains and the two reductions of a pair are independent, which halves the
+  // dependent latency a lone warp sees (single-pair latency mode: one or two groups per warp, nothing else to hide it).
+  while (need) {
+    const int q0 = __ffs(need) - 1;
+    need &= need - 1;
+    const int q1 = need ? __ffs(need) - 1 : q0;
+    need &= need - 1;
+    const float4 Q0 = qslot[q0], Q1 = qslot[q1];
+    const unsigned d0 = __float_as_uint(sqdist_rn(Q0.x, Q0.y, Q0.z, c.x, c.y, c.z));
+    const unsigned d1 = __float_as_uint(sqdist_rn(Q1.x, Q1.y, Q1.z, c.x, c.y, c.z));
+    const unsigned m0 = __reduce_min_sync(0xFFFFFFFFu, d0);  // d2 >= +0: bit order is value order; NaN patterns are above +inf
+    const unsigned m1 = __reduce_min_sync(0xFFFFFFFFu, d1);
+    const bool h0 = m0 <= __float_as_uint(Q0.w), h1 = q1 != q0 && m1 <= __float_as_uint(Q1.w);  // warp-uniform
+    if (h0 || h1) {
+      // lowest tag (= lowest original index) among the candidates at that distance, then the 64-bit (d2, index) comparison
+      if (h0) {
+        const unsigned wtag = __reduce_min_sync(0xFFFFFFFFu, d0 == m0 ? ctag : 0xFFFFFFFFu);
+        const unsigned long long nk = ((unsigned long long)m0 << 32) | wtag;
+        if (lane == q0 && nk < v.key) { v.key = nk; qslot[q0].w = __uint_as_float(m0); }
+      }
+      if (h1) {
+        const unsigned wtag = __reduce_min_sync(0xFFFFFFFFu, d1 == m1 ? ctag : 0xFFFFFFFFu);
+        const unsigned long long nk = ((unsigned long long)m1 << 32) | wtag;
+        if (lane == q1 && nk < v.key) { v.key = nk; qslot[q1].w = __uint_as_float(m1); }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Exact nearest neighbour of every lane's query among the staged target, inside the bound v was initialised with
+// (+inf: unbounded). valid == false lanes take no part. Warp-collective. qslot: 32 float4 of shared memory owned by this warp.
+__device__ __forceinline__ void leaf_nn1(const LeafView& L, float qx, float qy, float qz, bool valid, LeafTop1& v, float4* __restrict__ qslot,
+                                         unsigned long long* dbg = nullptr) {
   if (!__any_sync(0xFFFFFFFFu, valid)) return;
+  unsigned n_next = 0, n_bcast = 0, n_turns = 0;
   float glo[3], ghi[3];
   leaf_group_box(qx, qy, qz, valid, glo, ghi);
   LeafSchedule S;
   S.init(L, glo, ghi, -1);
+  // an invalid lane must neither win a candidate nor hold the group's bound up: NaN coordinates, key 0
+  const float nanq = __int_as_float(0x7fc00000);
+  if (!valid) { qx = nanq; qy = nanq; qz = nanq; v.key = 0ull; }
   const f32x2_t qx2 = f2_pack(qx, qx), qy2 = f2_pack(qy, qy), qz2 = f2_pack(qz, qz);
-  if (!valid) v.d2 = -1.f;  // nothing passes `<= -1`
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  qslot[lane] = make_float4(qx, qy, qz, __uint_as_float((unsigned)(v.key >> 32)));
+  __syncwarp();
   for (;;) {
-    // the largest bound of the group (bit patterns of non-negative floats order like the values; -1 counts as 0)
-    const float G = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, valid ? __float_as_uint(v.d2) : 0u));
+    // the largest bound of the group (bit patterns of non-negative floats order like the values)
+    const float G = __uint_as_float(__reduce_max_sync(0xFFFFFFFFu, (unsigned)(v.key >> 32)));
     const int l = S.next(G);
     if (l < 0) break;
-    const float dl = leaf_point_box2(qx, qy, qz, L.box[2 * l], L.box[2 * l + 1]);
-    if (!__any_sync(0xFFFFFFFFu, valid && dl <= v.d2)) continue;
-    leaf_scan_top1(L, l, qx2, qy2, qz2, v);
+    n_next++;
+    const float dl = leaf_point_box2(qx, qy, qz, L.box[2 * l], L.box[2 * l + 1]);  // NaN for an invalid lane: compares false
+    // (valid: fmaxf drops the NaN of an invalid lane's box distance, so that lane must be masked explicitly)
+    const unsigned need = __ballot_sync(0xFFFFFFFFu, valid && dl <= v.d2());
+    if (need == 0u) continue;
+    if (__popc(need) > kLeafTransposeMax) {
+      leaf_scan_top1(L, l, qx2, qy2, qz2, v);
+      qslot[lane].w = __uint_as_float((unsigned)(v.key >> 32));
+      __syncwarp();
+      n_bcast++;
+    } else {
+      leaf_scan_top1_transposed(L, l, need, qslot, v);
+      n_turns += __popc(need);
+    }
+  }
+  const unsigned n_valid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+  if (dbg && lane == 0) {  // profiling aid: groups, leaves popped, broadcast scans, transposed turns, worst group
+    atomicAdd(dbg + 0, 1ull);
+    atomicAdd(dbg + 1, (unsigned long long)n_next);
+    atomicAdd(dbg + 2, (unsigned long long)n_bcast);
+    atomicAdd(dbg + 3, (unsigned long long)n_turns);
+    atomicMax(dbg + 4, (unsigned long long)n_turns);
+    atomicMax(dbg + 5, (unsigned long long)n_next);
+    atomicAdd(dbg + 6, (unsigned long long)n_valid);
   }
 }
 

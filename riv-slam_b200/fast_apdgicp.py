@@ -118,6 +118,8 @@ _PROTOTYPES = {
     "apd_odometry_align": (C.c_int, [C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_int, _fp, C.c_void_p]),
     "apd_synchronize": (C.c_int, [C.c_void_p]),
     "apd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "apd_get_timeline": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, _ip]),
+    "apd_get_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "apd_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "apd_get_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
@@ -211,6 +213,18 @@ class Handle:
         n = C.c_int64(0)
         self.check(self.L.apd_get_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def timeline(self):
+        """(phase, ns) stamps of the last align launch's first pair (option "timeline")."""
+        n = C.c_int32(0)
+        buf = (C.c_uint64 * 500)()
+        self.check(self.L.apd_get_timeline(self.h, buf, 250, C.byref(n)))
+        return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n.value)]
+
+    def debug_counters(self):
+        buf = (C.c_uint64 * 16)()
+        self.check(self.L.apd_get_debug_counters(self.h, buf))
+        return [int(x) for x in buf]
 
     def work_counters(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)

@@ -32,3 +32,17 @@ names = ["setInputTarget(cached)", "setInputSource(upload)", "grid+knn+cov", "al
 for nm, m, p in zip(names, np.median(r, 0), np.percentile(r, 95, 0)):
     print(f"{nm:26s} p50 {m:7.3f} ms   p95 {p:7.3f} ms")
 print(f"{'total':26s} p50 {np.median(r.sum(1)):7.3f} ms   iterations {reg.nr_iterations()} launches/pair {H.launch_count() / n:.1f}")
+# in-kernel timeline of one more align (phase stamps from %globaltimer)
+reg.setOption("timeline", 1)
+reg.setInputTarget(clouds[0], cache_key=1001); reg.setInputSource(clouds[1], cache_key=1002)
+reg.computeCovariances()
+reg.align(None, want_output=False)
+tl = H.timeline()
+names = {0: "enter", 1: "staged", 2: "iter", 3: "corr", 4: "H/b", 5: "LM trial", 6: "fitness", 10: "nn1>", 11: "<nn1", 12: "mahal", 13: "passend", 14: "synced"}
+if tl:
+    t0 = tl[0][1]
+    print("timeline (us):", " ".join(f"{names.get(p, p)}@{(t - t0) / 1e3:.1f}" for p, t in tl))
+dc = H.debug_counters()
+for nm, c in (("first pass", dc[:8]), ("seeded passes", dc[8:])):
+    if c[0]:
+        print(f"{nm}: groups {c[0]} queries/group {c[6] / c[0]:.1f} leaves popped/group {c[1] / c[0]:.1f} broadcast scans/group {c[2] / c[0]:.2f} turns/group {c[3] / c[0]:.1f} max turns {c[4]} max leaves {c[5]}")
