@@ -160,29 +160,79 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = min(args.pairs, args.cpu_sample)
-    scans, order = make_workload(args.pairs, args.unique, 0, args.workers)
     cores = host_cores()
     rates = []
-    for s in range(args.warmup + args.steps):
-        rate, done, cores, per = cpu_registrations(scans, order, n_sample, cores, args.cpu_budget)
-        if s >= args.warmup:
-            rates.append((rate, done, per))
+    if args.config == "c4":
+        from oracle.oracle import Oracle
+        from riv_slam_b200 import datagen
+        n_sample = min(args.c4_pairs, args.cpu_sample)
+        uniq = max(1, min(args.unique, args.c4_pairs))
+        base = [datagen.make_pair(4, i, n_src=N_POINTS) for i in range(min(uniq, n_sample))]
+        o = Oracle(num_threads=cores, **LAUNCH_PARAMS)
+        for s in range(args.warmup + args.steps):
+            per, t_start = [], time.perf_counter()
+            for i in range(n_sample):
+                sec, Tc, conv, it, fit = o.timed_registration(base[i % len(base)][0], base[i % len(base)][1])
+                per.append(sec)
+                if time.perf_counter() - t_start > args.cpu_budget:
+                    break
+            if s >= args.warmup:
+                rates.append((len(per) / sum(per), len(per), per))
+        workload = f"C4 batched loop-closure candidate verification, {args.c4_pairs} independent pairs x {N_POINTS} pts (bounded sample)"
+        sample = f"first {rates[0][1]} of {args.c4_pairs} independent pairs per step, both clouds new every pair"
+    else:
+        n_sample = min(args.pairs, args.cpu_sample)
+        scans, order = make_workload(args.pairs, args.unique, 0, args.workers)
+        for s in range(args.warmup + args.steps):
+            rate, done, cores, per = cpu_registrations(scans, order, n_sample, cores, args.cpu_budget)
+            if s >= args.warmup:
+                rates.append((rate, done, per))
+        workload = f"C2 sequential scan-to-scan odometry, {args.pairs} pairs x {N_POINTS} pts (bounded sample)"
+        sample = f"first {rates[0][1]} of {args.pairs} pairs of the C2 drive per step, covariances reused scan to scan"
     total_pairs = sum(d for _, d, _ in rates)
     total_time = sum(sum(p) for _, _, p in rates)
     value = total_pairs / total_time
     allper = np.concatenate([np.asarray(p) for _, _, p in rates])
-    sample = f"first {rates[0][1]} of {args.pairs} pairs of the C2 drive per step, covariances reused scan to scan"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total_time / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * total_time / max(1, args.steps), "higher_is_better": True, "scaling": "strong" if args.config == "c4" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "p50_align_latency_ms": float(np.median(allper) * 1e3),
-        "config": {"workload": f"C2 sequential scan-to-scan odometry, {args.pairs} pairs x {N_POINTS} pts (bounded sample)", "params": "launch file"},
+        "config": {"workload": workload, "params": "launch file"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+KERNEL_NOTES = {
+    "pack_points": "pcl::PointXYZI records (32 B, 12 used) -> float4: 48 B/pt",
+    "build": "Hilbert order + leaf boxes (K1 of SURVEY.md 8d): 36 B/pt",
+    "knn_cov": "kNN(k) + covariance + regularisation (K2): 48 B/pt; compute-bound, see dist_evals",
+    "align": "persistent align + fitness kernel: N * (148 * linearize + 84 * error + 32 * pairs) B (K3, K4, K6)",
+}
+
+
+def kernel_rooflines(ms, launches, alg_bytes, peak, traffic, dist_evals, clock_mhz):
+    """One roofline entry per hot kernel from the library's own CUDA-event timings (apd_get_kernel_times)."""
+    out = {}
+    lane_peak = 148 * 128 * (clock_mhz or 1965.0) * 1e6   # fp32 lane-issue slots per second
+    for k in ("pack_points", "build", "knn_cov", "align"):
+        if launches.get(k, 0) == 0 or ms.get(k, 0.0) <= 0:
+            continue
+        per_launch_ms = ms[k] / launches[k]
+        b = alg_bytes[k]
+        ach = b / (per_launch_ms * 1e-3) / 1e9
+        e = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(k), "launch_ms": per_launch_ms,
+             "launches": launches[k], "algorithmic_bytes_per_launch": int(b), "what": KERNEL_NOTES[k]}
+        if k in dist_evals and dist_evals[k]:
+            ev = dist_evals[k] / launches[k] / (per_launch_ms * 1e-3)
+            # one evaluation = 5 issue slots per lane (3 FADD2 + 3 FMUL2 + 4 FADD per candidate PAIR): stated, not hidden
+            e["dist_evals_per_s"] = ev
+            e["dist_eval_lane_issue_frac"] = ev * 5.0 / lane_peak
+            e["lane_issue_peak_per_s"] = lane_peak
+        out[k] = e
+    return out
 
 
 def main():
@@ -191,12 +241,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=1000, help="scan pairs per step per GPU")
-    ap.add_argument("--unique", type=int, default=96, help="distinct scans generated (replayed forth and back)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"], help="c2: scan-to-scan odometry, --pairs per GPU (weak scaling); "
+                    "c4: --c4-pairs independent pairs in total, sharded over the GPUs (strong scaling)")
+    ap.add_argument("--pairs", type=int, default=1000, help="scan pairs per step per GPU (c2)")
+    ap.add_argument("--c4-pairs", type=int, default=4096, help="independent pairs per step in total (c4)")
+    ap.add_argument("--unique", type=int, default=96, help="distinct scans (c2) / pairs (c4) generated, then replayed")
+    ap.add_argument("--same-workload", action="store_true", help="c2: every rank drives segment 0 (a homogeneous weak-scaling figure)")
     ap.add_argument("--workers", type=int, default=0, help="processes for data generation (0 = host cores)")
     ap.add_argument("--cpu-sample", type=int, default=200)
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--latency-pairs", type=int, default=100)
+    ap.add_argument("--streaming-points", type=int, default=1000000, help="size of the streaming-kernel section (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="name=value tuning option for apd_set_option")
     args = ap.parse_args()
@@ -211,10 +266,31 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    P = args.pairs
-    # synthetic scans first: the generator forks worker processes, which must happen before this process owns a CUDA context
-    scans, order = make_workload(P, args.unique, rank, max(1, args.workers // max(1, min(world, 8))))   # each rank drives its own segment
-    host_np, off = to_pointxyzi(scans, order)
+    c4 = args.config == "c4"
+    # synthetic data first: the generator forks worker processes, which must happen before this process owns a CUDA context
+    workers = max(1, args.workers // max(1, min(world, 8)))
+    if c4:
+        from riv_slam_b200 import datagen, sharding
+        lo, hi = sharding.shard_range(args.c4_pairs, rank, world)   # contiguous block of ceil(P/R) pairs
+        P = hi - lo
+        uniq = max(1, min(args.unique, args.c4_pairs))
+        base = [datagen.make_pair(4, i, n_src=N_POINTS) for i in sorted({g % uniq for g in range(lo, hi)})]
+        idx = {u: k for k, u in enumerate(sorted({g % uniq for g in range(lo, hi)}))}
+        scans = None
+        def blk(clouds):
+            out = np.zeros((len(clouds) * N_POINTS, 8), dtype=np.float32)
+            for i, c in enumerate(clouds):
+                b = out[i * N_POINTS:(i + 1) * N_POINTS]
+                b[:, :3] = c[:, :3]; b[:, 3] = 1.0; b[:, 4] = c[:, 3]
+            return out
+        src_np = blk([base[idx[g % uniq]][0] for g in range(lo, hi)])
+        tgt_np = blk([base[idx[g % uniq]][1] for g in range(lo, hi)])
+        off = (np.arange(P + 1) * N_POINTS).astype(np.int32)
+        host_np = np.concatenate([src_np, tgt_np])
+    else:
+        P = args.pairs
+        scans, order = make_workload(P, args.unique, 0 if args.same_workload else rank, workers)   # each rank drives its own segment
+        host_np, off = to_pointxyzi(scans, order)
 
     import torch
     import torch.distributed as dist
@@ -241,31 +317,48 @@ def main():
 
     host = torch.from_numpy(host_np).pin_memory()
     dev_pts = host.to(dev, non_blocking=False)
-    res_dev = torch.zeros(P * 96, dtype=torch.uint8, device=dev)
-    res_host = torch.zeros(P * 96, dtype=torch.uint8).pin_memory()
-    gathered = torch.zeros(world * P * 96, dtype=torch.uint8, device=dev) if world > 1 else None
+    res_dev = torch.zeros(max(P, 1) * 96, dtype=torch.uint8, device=dev)
+    res_host = torch.zeros(max(P, 1) * 96, dtype=torch.uint8).pin_memory()
+    # c4 shards can differ by one pair: gather buffers are sized for the largest shard
+    Pmax = -(-args.c4_pairs // world) if c4 else P
+    gather_in = torch.zeros(Pmax * 96, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * Pmax * 96, dtype=torch.uint8, device=dev) if world > 1 else None
     src_idx = np.arange(1, P + 1, dtype=np.int32)
     tgt_idx = np.arange(0, P, dtype=np.int32)
     ip = C.POINTER(C.c_int32)
+    n_scans_step = 2 * P if c4 else P + 1
 
     def step(pts_tensor, mem, out_host):
-        """One pass of the hot path. Returns (cloudset handle to destroy, event pairs)."""
-        cs = C.c_void_p()
+        """One pass of the hot path. Returns (cloud-set handles to destroy, events)."""
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        sets = []
         with torch.cuda.stream(stream):
             ev[0].record(stream)
-            H.check(L.apd_cloudset_create(H.h, C.c_void_p(pts_tensor.data_ptr()), 32, off.ctypes.data_as(ip), P + 1, mem, C.byref(cs)))
-            H.check(L.apd_cloudset_prepare(H.h, cs))
-            ev[1].record(stream)
-            H.check(L.apd_align_pairs(H.h, cs, cs, src_idx.ctypes.data_as(ip), tgt_idx.ctypes.data_as(ip), None, P,
-                                      C.c_void_p(res_dev.data_ptr()), F.MEM_DEVICE))
+            if c4:
+                cs_s, cs_t = C.c_void_p(), C.c_void_p()
+                H.check(L.apd_cloudset_create(H.h, C.c_void_p(pts_tensor.data_ptr()), 32, off.ctypes.data_as(ip), P, mem, C.byref(cs_s)))
+                H.check(L.apd_cloudset_create(H.h, C.c_void_p(pts_tensor.data_ptr() + P * N_POINTS * 32), 32, off.ctypes.data_as(ip), P, mem, C.byref(cs_t)))
+                H.check(L.apd_cloudset_prepare(H.h, cs_s))
+                H.check(L.apd_cloudset_prepare(H.h, cs_t))
+                ev[1].record(stream)
+                H.check(L.apd_align_pairs(H.h, cs_s, cs_t, None, None, None, P, C.c_void_p(res_dev.data_ptr()), F.MEM_DEVICE))
+                sets = [cs_s, cs_t]
+            else:
+                cs = C.c_void_p()
+                H.check(L.apd_cloudset_create(H.h, C.c_void_p(pts_tensor.data_ptr()), 32, off.ctypes.data_as(ip), P + 1, mem, C.byref(cs)))
+                H.check(L.apd_cloudset_prepare(H.h, cs))
+                ev[1].record(stream)
+                H.check(L.apd_align_pairs(H.h, cs, cs, src_idx.ctypes.data_as(ip), tgt_idx.ctypes.data_as(ip), None, P,
+                                          C.c_void_p(res_dev.data_ptr()), F.MEM_DEVICE))
+                sets = [cs]
             ev[2].record(stream)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, res_dev)
+                gather_in[:P * 96].copy_(res_dev[:P * 96], non_blocking=True)
+                dist.all_gather_into_tensor(gathered, gather_in)
             if out_host:
                 res_host.copy_(res_dev, non_blocking=True)
             ev[3].record(stream)
-        return cs, ev
+        return sets, ev
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -277,14 +370,15 @@ def main():
         barrier()
         t_wall0 = time.perf_counter()
         tot = prep = align = 0.0
-        # steps run back to back; each step's cloud set is freed after its results are complete
+        # steps run back to back; each step's cloud sets are freed after its results are complete
         for _ in range(steps):
-            cs, ev = step(pts_tensor, mem, out_host)
+            sets, ev = step(pts_tensor, mem, out_host)
             ev[3].synchronize()
             tot += ev[0].elapsed_time(ev[3])
             prep += ev[0].elapsed_time(ev[1])
             align += ev[1].elapsed_time(ev[2])
-            L.apd_cloudset_destroy(H.h, cs)
+            for cs in sets:
+                L.apd_cloudset_destroy(H.h, cs)
         barrier()
         wall = time.perf_counter() - t_wall0
         return tot * 1e-3, prep * 1e-3, align * 1e-3, wall
@@ -293,21 +387,30 @@ def main():
     timed(dev_pts, F.MEM_DEVICE, False, max(args.warmup, 1))
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = H.launch_count()
+    H.set_option("kernel_timing", 1)    # the library brackets its own launches with CUDA events on the launch stream
+    H.kernel_times(); H.search_counters()
     t0 = time.perf_counter()
     tot, prep, align, wall = timed(dev_pts, F.MEM_DEVICE, False, args.steps)
     t1 = time.perf_counter()
+    k_ms, k_n = H.kernel_times()
+    knn_evals, nn1_evals = H.search_counters()
+    H.set_option("kernel_timing", 0)
     launches = H.launch_count() - launches0
     lin, err, _ = H.work_counters()   # of the last step (all steps do identical work)
 
     # ---- end to end: pinned host PointXYZI buffers in, host results out, through the public call a user makes ----
-    # apd_odometry_align uploads every scan from (pinned) host memory, builds grids + covariances, aligns
-    # all pairs and writes the 96-byte records to host memory; it pipelines chunks over two streams.
-    res_np = np.zeros(P, dtype=F.RESULT_DTYPE)
+    # apd_odometry_align / apd_batch_align upload every scan from (pinned) host memory, build leaves + covariances, align all pairs and
+    # write the 96-byte records to host memory; they pipeline chunks over two streams.
+    res_np = np.zeros(max(P, 1), dtype=F.RESULT_DTYPE)
     res_pin = torch.from_numpy(res_np.view(np.uint8).reshape(-1)).pin_memory()
     res_view = np.frombuffer(memoryview(res_pin.numpy()), dtype=F.RESULT_DTYPE)
 
     def e2e_step():
-        H.check(L.apd_odometry_align(H.h, C.c_void_p(host.data_ptr()), off.ctypes.data_as(ip), P + 1, 32, None, C.c_void_p(res_pin.data_ptr())))
+        if c4:
+            H.check(L.apd_batch_align(H.h, C.c_void_p(host.data_ptr()), off.ctypes.data_as(ip), C.c_void_p(host.data_ptr() + P * N_POINTS * 32),
+                                      off.ctypes.data_as(ip), 32, None, P, C.c_void_p(res_pin.data_ptr())))
+        else:
+            H.check(L.apd_odometry_align(H.h, C.c_void_p(host.data_ptr()), off.ctypes.data_as(ip), P + 1, 32, None, C.c_void_p(res_pin.data_ptr())))
 
     def e2e_timed(steps):
         barrier()
@@ -316,19 +419,22 @@ def main():
         with torch.cuda.stream(stream):
             e0.record(stream)
             for _ in range(steps):
-                e2e_step()          # returns when the results are in host memory
+                if P > 0:
+                    e2e_step()          # returns when the results are in host memory
                 if world > 1:
-                    dist.all_gather_into_tensor(gathered, res_dev)
+                    dist.all_gather_into_tensor(gathered, gather_in)
             e1.record(stream)
+        torch.cuda.synchronize(dev)
+        mine = time.perf_counter() - t0
         barrier()
-        return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0
+        return e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0, mine
 
     e2e_timed(max(args.warmup, 1))
-    e_tot, e_wall = e2e_timed(args.steps)
+    e_tot, e_wall, e_mine = e2e_timed(args.steps)
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if sampler else None   # samples cover both timed regions (device-resident and end to end)
     e_tot = max(e_tot, e_wall)    # the helper stream's work is not on `stream`: the host clock bounds the region
-    results = res_view.copy()
+    results = res_view[:P].copy()
 
     def allmax(x):
         if world == 1:
@@ -337,79 +443,140 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def allgather_row(row):
+        """per-rank figures on rank 0 (names the straggler of a multi-GPU run)"""
+        t = torch.tensor(row, dtype=torch.float64, device=dev)
+        if world == 1:
+            return [row]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [[float(v) for v in o.tolist()] for o in out]
+
     tot_m, e_m, align_m, prep_m = allmax(tot), allmax(e_tot), allmax(align), allmax(prep)
-    # e2e uses the larger of the device-event time and the host wall clock around the same region
-    e_m = max(e_m, 0.0)
-    e_wall_m = allmax(e_wall)
+    per_rank = allgather_row([1e3 * prep / args.steps, 1e3 * align / args.steps, 1e3 * tot / args.steps, 1e3 * e_mine / args.steps,
+                              host_np.nbytes / max(e_mine / args.steps, 1e-12) / 1e9, float(P)])
+    if world > 1:
+        dist.barrier()   # every rank is done measuring: ranks > 0 leave now instead of spinning in NCCL while rank 0 runs the CPU leg
 
     # ---- single-pair latency through the reference-shaped object (setInputTarget/Source + align + fitness) ----
-    lat = []
-    reg = F.FastAPDGICP(local_rank)
-    reg.handle().set_params(**LAUNCH_PARAMS)
-    n_lat = min(args.latency_pairs, P)
-    clouds = [np.ascontiguousarray(host_np[i * N_POINTS:(i + 1) * N_POINTS]) for i in range(n_lat + 1)]
-    guess = np.eye(4, dtype=np.float32)
-    for i in range(n_lat):
-        ta = time.perf_counter()
-        reg.setInputTarget(clouds[i], cache_key=i + 1)        # the previous source: device data reused
-        reg.setInputSource(clouds[i + 1], cache_key=i + 2)
-        reg.align(guess, want_output=False)
-        reg.getFitnessScore()
-        lat.append(time.perf_counter() - ta)
-    p50 = float(np.median(lat[3:]) * 1e3) if len(lat) > 3 else None
+    p50 = None
+    seq_rate = None
+    if rank == 0 and args.latency_pairs > 0:
+        lat = []
+        reg = F.FastAPDGICP(local_rank)
+        reg.handle().set_params(**LAUNCH_PARAMS)
+        for kv in args.option:
+            k, v = kv.split("=")
+            reg.handle().set_option(k, float(v))
+        n_lat = min(args.latency_pairs, max(n_scans_step - 1, 1))
+        clouds = [np.ascontiguousarray(host_np[i * N_POINTS:(i + 1) * N_POINTS]) for i in range(n_lat + 1)]
+        guess = np.eye(4, dtype=np.float32)
+        if c4:   # independent pairs: both clouds are new every time
+            tg = [np.ascontiguousarray(host_np[(P + i) * N_POINTS:(P + i + 1) * N_POINTS]) for i in range(n_lat)]
+        for i in range(n_lat):
+            ta = time.perf_counter()
+            if c4:
+                reg.setInputTarget(tg[i], cache_key=1000 + i)
+                reg.setInputSource(clouds[i], cache_key=5000 + i)
+            else:
+                reg.setInputTarget(clouds[i], cache_key=i + 1)        # the previous source: device data reused
+                reg.setInputSource(clouds[i + 1], cache_key=i + 2)
+            reg.align(guess, want_output=False)
+            reg.getFitnessScore()
+            lat.append(time.perf_counter() - ta)
+        p50 = float(np.median(lat[3:]) * 1e3) if len(lat) > 3 else None
+        if not c4:
+            # truly sequential odometry (scan_matching_odometry_nodelet.cpp:461-468): the guess of pair t is the result of pair t-1,
+            # so pairs cannot be batched; one stream of dependent registrations
+            g = np.eye(4, dtype=np.float32)
+            ta = time.perf_counter()
+            for i in range(n_lat):
+                reg.setInputTarget(clouds[i], cache_key=i + 1)
+                reg.setInputSource(clouds[i + 1], cache_key=i + 2)
+                reg.align(g, want_output=False)
+                reg.getFitnessScore()
+                g = reg.getFinalTransformation()
+            seq_rate = n_lat / (time.perf_counter() - ta)
 
     if rank != 0:
         if world > 1:
-            dist.barrier()
             dist.destroy_process_group()
         return
 
-    value = world * P * args.steps / tot_m
-    e2e_value = world * P * args.steps / max(e_m, 1e-12)
-    # roofline of the dominant kernel (align): algorithmic bytes of one launch / its measured duration
-    align_bytes = N_POINTS * (B_LINEARIZE * lin + B_ERROR * err + B_FITNESS * P)
-    align_s = align_m / args.steps
+    total_pairs = (args.c4_pairs if c4 else world * P)
+    value = total_pairs * args.steps / tot_m
+    e2e_value = total_pairs * args.steps / max(e_m, 1e-12)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
     else:
         peak, peak_src = 6650.0, "fallback"
-    achieved = align_bytes / align_s / 1e9
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one align launch at this shape, from the committed ncu capture
+    # algorithmic bytes per launch (SURVEY.md 8d per-unit figures x the units one launch processes; DESIGN.md section 4)
+    n_pts_step = n_scans_step * N_POINTS
+    launches_per_step = {k: max(1, v // max(args.steps, 1)) for k, v in k_n.items()}
+    alg = {"pack_points": 48.0 * n_pts_step / launches_per_step.get("pack_points", 1), "build": 36.0 * n_pts_step / launches_per_step.get("build", 1),
+           "knn_cov": 48.0 * n_pts_step / launches_per_step.get("knn_cov", 1), "align": float(N_POINTS * (B_LINEARIZE * lin + B_ERROR * err + B_FITNESS * P))}
+    traffic = {}
     try:
-        if P == 1000:
-            traffic = int(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))["align_kernel"]["dram_bytes_per_launch"])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+        if tj.get("pairs") == P and tj.get("config") == args.config:
+            traffic = {k: int(v["dram_bytes_per_launch"]) for k, v in tj["kernels"].items()}
     except Exception:
-        traffic = None
-    prep_bytes = (P + 1) * N_POINTS * B_PREPARE
+        traffic = {}
+    kr = kernel_rooflines(k_ms, k_n, alg, peak, traffic, {"knn_cov": knn_evals, "align": nn1_evals}, clocks["sm_mhz"] if clocks else None)
+    dominant = max(kr, key=lambda k: kr[k]["launch_ms"] * kr[k]["launches"]) if kr else None
+    roof = dict(kr[dominant], kernel=dominant, peak_source=peak_src, linearize_passes=int(lin), error_passes=int(err),
+                note="dominant kernel by summed CUDA-event time over the timed region; all hot kernels under roofline_kernels") if dominant else None
+    stream_sec = None
+    if args.streaming_points > 0:
+        sres = H.bench_streaming(args.streaming_points, 5)
+        stream_sec = {"points": args.streaming_points, "l2": "flushed (256 MB memset) before every repetition",
+                      "kernels": {k: {"achieved": g, "peak": peak, "unit": "GB/s", "frac": g / peak, "launch_ms": m} for k, (g, m) in sres.items()}}
+    workload = (f"C4 batched loop-closure candidate verification: {args.c4_pairs} independent pairs x {N_POINTS} pts, identity guess, sharded over {world} GPU(s)"
+                if c4 else f"C2 sequential scan-to-scan odometry: {P} pairs x {N_POINTS} pts per GPU per step (scan t+1 -> scan t, identity guess)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_m / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": f"synthetic ({len(scans)} generated 4D-radar scans of one drive, replayed forth and back to {P + 1} scans per GPU)",
-        "config": {"workload": f"C2 sequential scan-to-scan odometry: {P} pairs x {N_POINTS} pts per GPU per step (scan t+1 -> scan t, identity guess)",
+        "ms_per_step": 1e3 * tot_m / args.steps, "higher_is_better": True, "scaling": "strong" if c4 else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": (f"synthetic ({min(args.unique, args.c4_pairs)} generated 4D-radar scan pairs, replayed to {args.c4_pairs})" if c4 else
+                                f"synthetic ({len(scans)} generated 4D-radar scans of one drive, replayed forth and back to {P + 1} scans per GPU)"),
+        "config": {"workload": workload,
                    "params": "launch file (k=20, dmax=2.0, eps 0.1/2e-3, 64 iters, vars 0.86/1.0/1.0, PLANE)",
-                   "l2": "inputs larger than L2 (per-step working set ~0.6 GB per GPU)", "parallelism": f"pair-sharded x{world}"},
+                   "l2": f"inputs larger than L2 (per-step working set ~{n_pts_step * 100 / 1e9:.1f} GB per GPU)", "parallelism": f"pair-sharded x{world}",
+                   "segments": "same on every rank" if args.same_workload else "one drive segment per rank"},
         "p50_align_latency_ms": p50,
+        "sequential_chained_reg_per_s": seq_rate,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_np.nbytes), "d2h_bytes_per_step": int(P * 96),
-                "ms_per_step": 1e3 * e_m / args.steps, "wall_ms_per_step": 1e3 * e_wall_m / args.steps},
+                "ms_per_step": 1e3 * e_m / args.steps, "wall_ms_per_step": 1e3 * allmax(e_wall) / args.steps if world == 1 else 1e3 * e_m / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "align_kernel<TEAM_CTA,staged>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(align_bytes), "launch_ms": 1e3 * align_s,
-                     "linearize_passes": int(lin), "error_passes": int(err)},
-        "phases_ms_per_step": {"upload_or_copy+grid+knn_cov": 1e3 * prep_m / args.steps, "align+fitness": 1e3 * align_m / args.steps,
-                               "prepare_algorithmic_GBps": prep_bytes / (prep_m / args.steps) / 1e9},
+        "roofline": roof,
+        "roofline_kernels": kr,
+        "streaming_kernels": stream_sec,
+        "phases_ms_per_step": {"upload_or_copy+build+knn_cov": 1e3 * prep_m / args.steps, "align+fitness": 1e3 * align_m / args.steps},
+        "per_rank": {"columns": ["prepare_ms", "align_ms", "step_ms", "e2e_ms", "e2e_h2d_GBps", "pairs"], "rows": per_rank},
         "results": {"converged_frac": float(np.mean(results["converged"] != 0)), "mean_iterations": float(np.mean(results["iterations"])),
                     "mean_fitness": float(np.mean(results["fitness"])), "status_ok_frac": float(np.mean(results["status"] == 0))},
     }
     if not args.no_cpu:
-        rate, done, cores, per = cpu_registrations(scans, order, min(P, args.cpu_sample), 0, args.cpu_budget)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"first {done} of {P} pairs of the same drive, covariances reused scan to scan",
-                                "p50_latency_ms": float(np.median(per) * 1e3)}
+        if c4:
+            from oracle.oracle import Oracle
+            o = Oracle(num_threads=host_cores(), **LAUNCH_PARAMS)
+            per, t_start = [], time.perf_counter()
+            for i in range(min(P, args.cpu_sample)):
+                s_np = src_np[i * N_POINTS:(i + 1) * N_POINTS, :3]
+                t_np = tgt_np[i * N_POINTS:(i + 1) * N_POINTS, :3]
+                sec, Tc, conv, it, fit = o.timed_registration(s_np, t_np)
+                per.append(sec)
+                if time.perf_counter() - t_start > args.cpu_budget:
+                    break
+            rate, done, cores = len(per) / sum(per), len(per), host_cores()
+            sample = f"first {done} of {args.c4_pairs} independent pairs, both clouds new every pair"
+        else:
+            rate, done, cores, per = cpu_registrations(scans, order, min(P, args.cpu_sample), 0, args.cpu_budget)
+            sample = f"first {done} of {P} pairs of the same drive, covariances reused scan to scan"
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "p50_latency_ms": float(np.median(per) * 1e3)}
     print(json.dumps(line))
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
 
 

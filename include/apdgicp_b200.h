@@ -186,7 +186,8 @@ int apd_synchronize(apd_handle h);
  *   "fitness_max_range" max_range of the getFitnessScore the batched calls fill into apd_result.fitness (default DBL_MAX)
  *   "fused_build"      1 = small clouds are gridded by one launch for all levels (default), 0 = the multi-kernel pipeline
  *   "knn_fine_rings"   kNN: rings searched on one level of the grid pyramid before restarting on the next coarser one
- *   "timeline"         1 = the align kernel stamps its phases for apd_get_timeline (profiling aid) */
+ *   "timeline"         1 = the align kernel stamps its phases for apd_get_timeline (profiling aid)
+ *   "kernel_timing"    1 = CUDA events around the hot launches (apd_get_kernel_times) */
 int apd_set_option(apd_handle h, const char* name, double value);
 
 /* Batched calc_fitness_score over cloud sets (one launch for a sliding window of keyframe pairs): scores[i] for cloud src_idx[i]
@@ -244,6 +245,19 @@ int apd_odometry_align(apd_handle h, const float* pts, const int32_t* offsets /*
                        const float* guesses, apd_result* out);
 
 /* ---- introspection for benchmarks ---- */
+/* The streaming kernels of the path at n_points, each timed `reps` times with CUDA events on the handle's stream, L2 flushed (a 256 MB
+ * memset) before every repetition: [0] pack_points (pcl::PointXYZI records -> float4), [1] transform_points (the output cloud,
+ * lsq_registration_impl.hpp:79), [2] cov_export (getSource/TargetCovariances), [3] cov_import (setSource/TargetCovariances).
+ * gbps = algorithmic bytes (48 / 28 / 192 / 192 per point) / time; ms (may be NULL) = time per launch. */
+int apd_bench_streaming(apd_handle h, int n_points, int reps, double gbps[4], double ms[4]);
+/* Point-to-point distance evaluations executed by the leaf-mode searches since the last call (and reset): kNN + covariance kernel,
+ * and the 1-NN searches of the align kernel (correspondences + fitness). Every lane of a warp counts: a broadcast leaf scan is
+ * 32 queries x 32 candidates, a transposed turn 32 candidates of one query. */
+int apd_get_search_counters(apd_handle h, int64_t* knn_evals, int64_t* nn1_evals);
+/* With apd_set_option(h, "kernel_timing", 1) every hot launch is bracketed by CUDA events on the stream it is launched on; this call
+ * synchronises, returns the summed durations since the last call (ms) and the launch counts per kind - 0 pack_points, 1 grid / leaf
+ * build, 2 kNN + covariance, 3 align (+ fitness) - and clears them. Chunks of a pipelined call that ran on the helper stream are included. */
+int apd_get_kernel_times(apd_handle h, double ms[4], int64_t launches[4]);
 /* Profiling aid: with apd_set_option(h, "timeline", 1) the align kernel records (phase, %globaltimer ns) stamps for the first pair of a
  * launch: 0 kernel entered, 1 target staged, 2 iteration starts, 3 correspondences done, 4 H/b reduced, 5 LM trial done, 6 fitness done. */
 int apd_get_timeline(apd_handle h, uint64_t* phase_ns /* 2 values per stamp */, int max_stamps, int* n_stamps);

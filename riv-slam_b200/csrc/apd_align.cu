@@ -320,7 +320,7 @@ __device__ __forceinline__ void correspondence_pass_leaf(const AlignBatch& B, Al
     LeafTop1 v;
     v.init(bound);
     stamp(B, 10);
-    leaf_nn1(T.L, qx, qy, qz, search, v, S.qslot[threadIdx.x >> 5], B.timeline ? B.timeline + 600 + (seeded ? 8 : 0) : nullptr);
+    leaf_nn1(T.L, qx, qy, qz, search, v, S.qslot[threadIdx.x >> 5], B.timeline ? B.timeline + 600 + (seeded ? 8 : 0) : nullptr, B.nn1_evals);
     stamp(B, 11);
     if (!act) continue;
     if (anchored) {
@@ -371,7 +371,7 @@ __device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignSh
     }
     LeafTop1 v;
     v.init(bound);
-    leaf_nn1(T.L, qx, qy, qz, act && finite, v, S.qslot[threadIdx.x >> 5]);
+    leaf_nn1(T.L, qx, qy, qz, act && finite, v, S.qslot[threadIdx.x >> 5], nullptr, B.nn1_evals);
     if (act) B.scratch.fit[sbase + i] = (finite && v.found()) ? v.d2() : __int_as_float(0x7fc00000);  // NaN: no neighbour at all
   }
   __syncthreads();

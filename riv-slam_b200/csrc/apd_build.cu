@@ -507,6 +507,11 @@ __global__ void transform_points_kernel(const float4* __restrict__ pts, int n, c
   o[2] = xform_row_rn(T[8], T[9], T[10], T[11], a.x, a.y, a.z);
 }
 
+__global__ void iota_w_kernel(float4* __restrict__ pts, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pts[i].w = __uint_as_float((unsigned)i);
+}
+
 // sorted 6-double covariances -> Eigen::Matrix4d layout (16 doubles, symmetric so row/column order is moot) in original order
 __global__ void cov_export_kernel(CloudSetView cs, int cloud, double* __restrict__ out16) {
   const int n = cs.pt_off[cloud + 1] - cs.pt_off[cloud];
@@ -838,6 +843,13 @@ cudaError_t launch_pack_points(const float* xyz, int stride_floats, long long n,
 cudaError_t launch_transform_points(const float4* pts, int n, const float* T16, float* out, int out_stride_floats, cudaStream_t stream, LaunchStats* st) {
   if (n == 0) return cudaSuccess;
   transform_points_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n, T16, out, out_stride_floats);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_iota_w(float4* pts, int n, cudaStream_t stream, LaunchStats* st) {
+  if (n == 0) return cudaSuccess;
+  iota_w_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pts, n);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -182,9 +182,14 @@ struct apd_context {
   double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
   int timeline_opt = 0;  // profiling aid: the align kernel stamps its phases (apd_get_timeline)
+  // kernel timing (option "kernel_timing"): CUDA events around the hot launches, on the stream they are launched on
+  int kernel_timing = 0;
+  struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
+  std::vector<TimedLaunch> timed;
+  std::vector<cudaEvent_t> event_pool;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, sc_fit, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
-      counters, grid_partials, misc, timeline, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
+      counters, search_counters, grid_partials, misc, timeline, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
   int scratch_slots = 0, scratch_max_src = 0;
   // last single-pair alignment
   bool has_last = false;
@@ -228,6 +233,27 @@ struct DeviceGuard {
     else prev = -1;
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// Brackets one hot launch with CUDA events on the handle's stream when kernel timing is on (bench.py's per-kernel figures).
+// kind: 0 pack_points, 1 grid / leaf build, 2 kNN + covariance, 3 align (+ fitness)
+struct KernelTimer {
+  apd_handle h;
+  int slot = -1;
+  KernelTimer(apd_handle h_, int kind) : h(h_) {
+    if (!h->kernel_timing) return;
+    cudaEvent_t ev[2];
+    for (auto& e : ev) {
+      if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+      else if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+    }
+    cudaEventRecord(ev[0], h->stream);
+    h->timed.push_back({kind, ev[0], ev[1]});
+    slot = (int)h->timed.size() - 1;
+  }
+  ~KernelTimer() {
+    if (slot >= 0) cudaEventRecord(h->timed[slot].e1, h->stream);
+  }
 };
 
 DeviceParams device_params(const apd_params& p) {
@@ -450,6 +476,7 @@ int cloudset_fill(apd_handle h, apd_cloudset_s* cs, const float* xyz, int stride
     }
     dev_xyz = h->raw_upload.as<float>();
   }
+  KernelTimer kt(h, 0);
   CK(launch_pack_points(dev_xyz, stride_bytes / 4, n, cs->pts.as<float4>(), h->stream, &h->stats));
   return APD_OK;
 }
@@ -458,6 +485,7 @@ constexpr int kFusedBuildMaxPoints = 16384;  // clouds up to this size are built
 
 int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
   if (cs->grid_built || cs->n_clouds == 0) { cs->grid_built = true; return APD_OK; }
+  KernelTimer kt(h, 1);
   if (cs->staged) {  // leaf mode: Hilbert order + leaf boxes, one CTA per cloud
     CK(launch_leaf_build(cs->view(), cs->max_n, h->stream, &h->stats));
     cs->grid_built = true;
@@ -513,7 +541,12 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
   DeviceParams dp = device_params(h->prm);
   dp.knn_packed = h->knn_packed;
   dp.knn_fine_rings = h->knn_fine_rings;
-  if (cs->staged) CK(launch_knn_cov_leaf(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->max_n, dp, knn_out, h->stream, &h->stats));
+  KernelTimer kt(h, 2);
+  if (!h->search_counters.p) {
+    CK(h->search_counters.reserve(sizeof(unsigned long long) * 4));
+    CK(cudaMemsetAsync(h->search_counters.p, 0, sizeof(unsigned long long) * 4, h->stream));
+  }
+  if (cs->staged) CK(launch_knn_cov_leaf(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->max_n, dp, knn_out, h->search_counters.as<unsigned long long>(), h->stream, &h->stats));
   else CK(launch_knn_cov(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, false, 0, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
@@ -712,6 +745,11 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   b.scratch.anchor = h->sc_anchor.as<float4>();
   b.scratch.fit = h->sc_fit.as<float>();
   b.prm = device_params(h->prm);
+  if (!h->search_counters.p) {
+    CK(h->search_counters.reserve(sizeof(unsigned long long) * 4));
+    CK(cudaMemsetAsync(h->search_counters.p, 0, sizeof(unsigned long long) * 4, h->stream));
+  }
+  b.nn1_evals = h->search_counters.as<unsigned long long>() + 1;
   if (h->timeline_opt) {
     CK(h->timeline.reserve(sizeof(unsigned long long) * 1024));
     CK(cudaMemsetAsync(h->timeline.p, 0, sizeof(unsigned long long) * 1024, h->stream));
@@ -720,7 +758,10 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   b.mode = c.mode;
   b.min_points = c.min_points;
   b.max_range = c.max_range;
-  CK(launch_align(b, plan.kind, plan.size, plan.teams, plan.staged, plan.smem, h->stream, &h->stats));
+  {
+    KernelTimer kt(h, 3);
+    CK(launch_align(b, plan.kind, plan.size, plan.teams, plan.staged, plan.smem, h->stream, &h->stats));
+  }
   if (used) *used = b;
   if (used_plan) *used_plan = plan;
   return APD_OK;
@@ -833,6 +874,8 @@ int apd_destroy(apd_handle h) {
     if (h->stage_host[i]) cudaFreeHost(h->stage_host[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
   }
+  for (auto& t : h->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+  for (auto& e : h->event_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return APD_OK;
@@ -878,6 +921,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "fitness_max_range") h->fitness_max_range = value;
   else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
   else if (n == "timeline") h->timeline_opt = value != 0;
+  else if (n == "kernel_timing") h->kernel_timing = value != 0;
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
 }
@@ -1457,6 +1501,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->knn_packed = h->knn_packed;
   x->no_fused_build = h->no_fused_build;
   x->no_smem_build = h->no_smem_build;
+  x->kernel_timing = h->kernel_timing;
   x->fitness_max_range = h->fitness_max_range;
   x->knn_fine_rings = h->knn_fine_rings;
   *out = x;
@@ -1755,6 +1800,104 @@ int apd_get_timeline(apd_handle h, uint64_t* phase_ns /* 2 per stamp */, int max
   const int n = (int)std::min<unsigned long long>(buf[0], 250);
   *n_stamps = n;
   if (phase_ns) memcpy(phase_ns, buf + 1, sizeof(unsigned long long) * 2 * std::min(n, max_stamps));
+  return APD_OK;
+}
+
+// Streaming kernels of the path at a given size, timed with CUDA events on the handle's stream (bench.py "streaming" section): the only
+// kernels whose roofline is HBM bandwidth by construction. Algorithmic bytes per point: pack_points 32 (one pcl::PointXYZI record) + 16;
+// transform_points 16 + 12; cov_export 16 + 48 + 128; cov_import 128 + 16 + 48.
+int apd_bench_streaming(apd_handle h, int n_points, int reps, double gbps[4], double ms[4]) {
+  if (!h || !gbps || n_points <= 0 || reps <= 0) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  const size_t n = (size_t)n_points;
+  DevBuf raw, cov16, out3, flush;
+  for (DevBuf* b : {&raw, &cov16, &out3, &flush}) b->pool = h->pool;
+  CK(raw.reserve(32 * n));
+  CK(cov16.reserve(128 * n));
+  CK(out3.reserve(12 * n));
+  const size_t flush_bytes = 256u << 20;  // larger than the 126 MB L2: every timed repetition starts cold
+  CK(flush.reserve(flush_bytes));
+  CK(cudaMemsetAsync(raw.p, 0x3c, 32 * n, h->stream));
+  CK(cudaMemsetAsync(cov16.p, 0, 128 * n, h->stream));
+  const int32_t off[2] = {0, n_points};
+  std::shared_ptr<apd_cloudset_s> cs;
+  const int saved_unstaged = h->force_unstaged;
+  int rc = make_cloudset(h, raw.as<float>(), 32, off, 1, APD_MEM_DEVICE, &cs, /*force_grid=*/true);
+  if (rc) return rc;
+  h->force_unstaged = saved_unstaged;
+  // spts.w must hold a permutation for the export / import kernels: the identity is as good as any (the grid is not built here)
+  CK(cudaMemcpyAsync(cs->spts.p, cs->pts.p, sizeof(float4) * n, cudaMemcpyDeviceToDevice, h->stream));
+  CK(launch_iota_w(cs->spts.as<float4>(), n_points, h->stream, &h->stats));
+  CK(h->misc.reserve(sizeof(float) * 16 + 64));
+  const float T[16] = {0.99f, -0.1f, 0.f, 0.3f, 0.1f, 0.99f, 0.f, -0.2f, 0.f, 0.f, 1.f, 0.05f, 0.f, 0.f, 0.f, 1.f};
+  CK(cudaMemcpyAsync(h->misc.p, T, sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const double bytes[4] = {48.0, 28.0, 192.0, 192.0};
+  for (int k = 0; k < 4; k++) {
+    double total = 0.0;
+    for (int r = -1; r < reps; r++) {  // r = -1: warm-up
+      CK(cudaMemsetAsync(flush.p, r & 0xff, flush_bytes, h->stream));
+      CK(cudaEventRecord(e0, h->stream));
+      if (k == 0) CK(launch_pack_points(raw.as<float>(), 8, (long long)n, cs->pts.as<float4>(), h->stream, &h->stats));
+      else if (k == 1) CK(launch_transform_points(cs->pts.as<float4>(), n_points, h->misc.as<float>(), out3.as<float>(), 3, h->stream, &h->stats));
+      else if (k == 2) CK(launch_cov_export(cs->view(), 0, cov16.as<double>(), h->stream, &h->stats));
+      else CK(launch_cov_import(cs->view(), 0, cov16.as<double>(), h->stream, &h->stats));
+      CK(cudaEventRecord(e1, h->stream));
+      CK(cudaEventSynchronize(e1));
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, e0, e1));
+      if (r >= 0) total += t;
+    }
+    const double per = total / reps;
+    if (ms) ms[k] = per;
+    gbps[k] = bytes[k] * (double)n / (per * 1e-3) / 1e9;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CK(cudaStreamSynchronize(h->stream));
+  return APD_OK;
+}
+
+int apd_get_search_counters(apd_handle h, int64_t* knn_evals, int64_t* nn1_evals) {
+  if (!h) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  long long k = 0, n = 0;
+  for (apd_handle x : {h, h->helper}) {
+    if (!x || !x->search_counters.p) continue;
+    unsigned long long c[2] = {0, 0};
+    CK(cudaMemcpyAsync(c, x->search_counters.p, sizeof(c), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemsetAsync(x->search_counters.p, 0, sizeof(unsigned long long) * 4, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    k += (long long)c[0];
+    n += (long long)c[1];
+  }
+  if (knn_evals) *knn_evals = k;
+  if (nn1_evals) *nn1_evals = n;
+  return APD_OK;
+}
+
+int apd_get_kernel_times(apd_handle h, double ms[4], int64_t launches[4]) {
+  if (!h || !ms) return APD_ERR_INVALID;
+  DeviceGuard guard(h->device);
+  for (int k = 0; k < 4; k++) { ms[k] = 0.0; if (launches) launches[k] = 0; }
+  for (apd_handle x : {h, h->helper}) {
+    if (!x) continue;
+    CK(cudaStreamSynchronize(x->stream));
+    for (auto& t : x->timed) {
+      float e = 0.f;
+      if (cudaEventElapsedTime(&e, t.e0, t.e1) == cudaSuccess && t.kind >= 0 && t.kind < 4) {
+        ms[t.kind] += (double)e;
+        if (launches) launches[t.kind]++;
+      } else {
+        cudaGetLastError();
+      }
+      x->event_pool.push_back(t.e0);
+      x->event_pool.push_back(t.e1);
+    }
+    x->timed.clear();
+  }
   return APD_OK;
 }
 

@@ -169,6 +169,7 @@ struct AlignBatch {
                            // 3 = compute_error only at the given pose, with the correspondences and Mahalanobis matrices the
                            //     last linearize left in the slot (fast_apdgicp_impl.hpp:275-298): out->error
   double max_range;        // fitness gate (getFitnessScore max_range)
+  unsigned long long* nn1_evals;  // nullable: += distance evaluations of the leaf-mode 1-NN searches (bench.py)
   unsigned long long* timeline;  // nullable (option "timeline"): thread 0 of team 0's first CTA stamps %globaltimer at phase boundaries, [0] = count
 };
 
@@ -190,8 +191,8 @@ cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap
                                     unsigned* const cursor[1 + kCoarseLevels], size_t smem_bytes /*0: global-memory version*/, cudaStream_t stream, LaunchStats* st);
 // Hilbert order + leaf boxes of every cloud of a leaf-mode set (one CTA per cloud)
 cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st);
-cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out /*nullable*/, cudaStream_t stream,
-                                LaunchStats* st);
+cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out /*nullable*/,
+                                unsigned long long* evals /*nullable: += distance evaluations*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,
@@ -203,6 +204,7 @@ cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& t
 cudaError_t launch_count_below(const float* d2, int n, double thr, double* out /*device [1]*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_pack_points(const float* xyz, int stride_floats, long long n, float4* out, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_transform_points(const float4* pts, int n, const float* T16 /*device*/, float* out, int out_stride_floats, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_iota_w(float4* pts, int n, cudaStream_t stream, LaunchStats* st);  // pts[i].w = bits(i)
 // gather/scatter between original and sorted order for the covariance getters / setters
 cudaError_t launch_cov_export(const CloudSetView& cs, int cloud, double* out16 /*device n*16*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_cov_import(const CloudSetView& cs, int cloud, const double* in16 /*device n*16*/, cudaStream_t stream, LaunchStats* st);

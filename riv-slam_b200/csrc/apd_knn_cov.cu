@@ -319,7 +319,7 @@ __device__ __noinline__ void knn_leaf_exact(LeafView L, float qx, float qy, floa
 
 template <int K>
 __global__ void __launch_bounds__(kKnnLeafThreads, 1)
-knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out) {
+knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out, unsigned long long* __restrict__ evals) {
   constexpr int M = K + 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
@@ -400,8 +400,9 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       LeafSchedule S;
       int l = g;
       bool first = true;
+      unsigned n_scanned = 0;
       for (;;) {
-        if (l >= 0) scan(l);
+        if (l >= 0) { scan(l); n_scanned++; }
         // merge when the next scan (up to 32 appends) could overflow a list, after the own leaf, and at the very end
         if (first || __any_sync(0xFFFFFFFFu, l < 0 ? cnt > 0 : cnt > kPendCap - kLeaf)) merge();
         if (l < 0) break;
@@ -419,6 +420,8 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
           if (__any_sync(0xFFFFFFFFu, valid && dl <= gate)) break;
         }
       }
+      // distance evaluations executed by this group: every lane computes every candidate of every scanned leaf (bench.py's figure)
+      if (evals && lane == 0) atomicAdd(evals, (unsigned long long)n_scanned * (kLeaf * 32));
     }
 
     // exact (d2, original index) keys of the K + 4 survivors, sorted; or the bounded exact scan when the packed list cannot
@@ -502,12 +505,13 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
 }
 
 template <int K>
-cudaError_t launch_k_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out, cudaStream_t stream) {
+cudaError_t launch_k_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out, unsigned long long* evals,
+                          cudaStream_t stream) {
   const int nleaf = (max_n + kLeaf - 1) / kLeaf;
   const size_t total = (size_t)nleaf * (kLeaf * 16 + 32) + sizeof(unsigned) * kPendCap * kKnnLeafThreads;
   cudaError_t e = cudaFuncSetAttribute(knn_cov_leaf_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
   if (e != cudaSuccess) return e;
-  knn_cov_leaf_kernel<K><<<n_tiles, kKnnLeafThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out);
+  knn_cov_leaf_kernel<K><<<n_tiles, kKnnLeafThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out, evals);
   return cudaGetLastError();
 }
 
@@ -534,16 +538,16 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
 
 size_t knn_leaf_smem_bytes(int max_n) { return (size_t)((max_n + kLeaf - 1) / kLeaf) * (kLeaf * 16 + 32) + sizeof(unsigned) * kPendCap * kKnnLeafThreads; }
 
-cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out, cudaStream_t stream,
-                                LaunchStats* st) {
+cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out,
+                                unsigned long long* evals, cudaStream_t stream, LaunchStats* st) {
   if (n_tiles == 0) return cudaSuccess;
   if (st) st->launches++;
   const int k = prm.k;
-  if (k <= 8) return launch_k_leaf<8>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
-  if (k <= 10) return launch_k_leaf<10>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
-  if (k <= 15) return launch_k_leaf<15>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
-  if (k <= 20) return launch_k_leaf<20>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
-  if (k <= 32) return launch_k_leaf<32>(cs, tiles, n_tiles, max_n, prm, knn_out, stream);
+  if (k <= 8) return launch_k_leaf<8>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
+  if (k <= 10) return launch_k_leaf<10>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
+  if (k <= 15) return launch_k_leaf<15>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
+  if (k <= 20) return launch_k_leaf<20>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
+  if (k <= 32) return launch_k_leaf<32>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -252,7 +252,7 @@ __device__ __forceinline__ void leaf_scan_top1_transposed(const LeafView& L, int
 // Exact nearest neighbour of every lane's query among the staged target, inside the bound v was initialised with
 // (+inf: unbounded). valid == false lanes take no part. Warp-collective. qslot: 32 float4 of shared memory owned by this warp.
 __device__ __forceinline__ void leaf_nn1(const LeafView& L, float qx, float qy, float qz, bool valid, LeafTop1& v, float4* __restrict__ qslot,
-                                         unsigned long long* dbg = nullptr) {
+                                         unsigned long long* dbg = nullptr, unsigned long long* evals = nullptr) {
   if (!__any_sync(0xFFFFFFFFu, valid)) return;
   unsigned n_next = 0, n_bcast = 0, n_turns = 0;
   float glo[3], ghi[3];
@@ -287,6 +287,7 @@ __device__ __forceinline__ void leaf_nn1(const LeafView& L, float qx, float qy, 
       n_turns += __popc(need);
     }
   }
+  if (evals && lane == 0) atomicAdd(evals, (unsigned long long)n_bcast * (kLeaf * 32) + (unsigned long long)n_turns * 32);
   const unsigned n_valid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
   if (dbg && lane == 0) {  // profiling aid: groups, leaves popped, broadcast scans, transposed turns, worst group
     atomicAdd(dbg + 0, 1ull);

@@ -120,6 +120,9 @@ _PROTOTYPES = {
     "apd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "apd_get_timeline": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, _ip]),
     "apd_get_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "apd_get_kernel_times": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_int64)]),
+    "apd_bench_streaming": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp]),
+    "apd_get_search_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "apd_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "apd_get_work_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
@@ -220,6 +223,28 @@ class Handle:
         buf = (C.c_uint64 * 500)()
         self.check(self.L.apd_get_timeline(self.h, buf, 250, C.byref(n)))
         return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n.value)]
+
+    def kernel_times(self):
+        """({kind: ms}, {kind: launches}) since the last call (option "kernel_timing"): pack, build, knn_cov, align."""
+        ms = (C.c_double * 4)()
+        n = (C.c_int64 * 4)()
+        self.check(self.L.apd_get_kernel_times(self.h, ms, n))
+        names = ("pack_points", "build", "knn_cov", "align")
+        return {k: float(v) for k, v in zip(names, ms)}, {k: int(v) for k, v in zip(names, n)}
+
+    def bench_streaming(self, n_points: int, reps: int = 5):
+        """{kernel: (GB/s algorithmic, ms)} of the streaming kernels at n_points (apd_bench_streaming)."""
+        g = (C.c_double * 4)()
+        m = (C.c_double * 4)()
+        self.check(self.L.apd_bench_streaming(self.h, int(n_points), int(reps), g, m))
+        names = ("pack_points", "transform_points", "cov_export", "cov_import")
+        return {k: (float(a), float(b)) for k, a, b in zip(names, g, m)}
+
+    def search_counters(self):
+        """(kNN distance evaluations, 1-NN distance evaluations) since the last call."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.check(self.L.apd_get_search_counters(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_counters(self):
         buf = (C.c_uint64 * 16)()
