@@ -245,8 +245,8 @@ int apd_odometry_align(apd_handle h, const float* pts, const int32_t* offsets /*
                        const float* guesses, apd_result* out);
 
 /* ---- introspection for benchmarks ---- */
-/* The streaming kernels of the path at n_points, each timed `reps` times with CUDA events on the handle's stream, L2 flushed (a 256 MB
- * memset) before every repetition: [0] pack_points (pcl::PointXYZI records -> float4), [1] transform_points (the output cloud,
+/* The streaming kernels of the path at n_points, each timed `reps` times with CUDA events on the handle's stream, L2 evicted (a 256 MB
+ * read) before every repetition: [0] pack_points (pcl::PointXYZI records -> float4), [1] transform_points (the output cloud,
  * lsq_registration_impl.hpp:79), [2] cov_export (getSource/TargetCovariances), [3] cov_import (setSource/TargetCovariances).
  * gbps = algorithmic bytes (48 / 28 / 192 / 192 per point) / time; ms (may be NULL) = time per launch. */
 int apd_bench_streaming(apd_handle h, int n_points, int reps, double gbps[4], double ms[4]);

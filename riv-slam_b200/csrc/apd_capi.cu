@@ -1818,6 +1818,7 @@ int apd_bench_streaming(apd_handle h, int n_points, int reps, double gbps[4], do
   const size_t flush_bytes = 256u << 20;  // larger than the 126 MB L2: every timed repetition starts cold
   CK(flush.reserve(flush_bytes));
   CK(cudaMemsetAsync(raw.p, 0x3c, 32 * n, h->stream));
+  CK(cudaMemsetAsync(flush.p, 0, flush_bytes, h->stream));
   CK(cudaMemsetAsync(cov16.p, 0, 128 * n, h->stream));
   const int32_t off[2] = {0, n_points};
   std::shared_ptr<apd_cloudset_s> cs;
@@ -1838,7 +1839,7 @@ int apd_bench_streaming(apd_handle h, int n_points, int reps, double gbps[4], do
   for (int k = 0; k < 4; k++) {
     double total = 0.0;
     for (int r = -1; r < reps; r++) {  // r = -1: warm-up
-      CK(cudaMemsetAsync(flush.p, r & 0xff, flush_bytes, h->stream));
+      CK(launch_l2_flush(flush.p, flush_bytes, out3.as<float>(), h->stream));  // clean eviction: every repetition starts cold
       CK(cudaEventRecord(e0, h->stream));
       if (k == 0) CK(launch_pack_points(raw.as<float>(), 8, (long long)n, cs->pts.as<float4>(), h->stream, &h->stats));
       else if (k == 1) CK(launch_transform_points(cs->pts.as<float4>(), n_points, h->misc.as<float>(), out3.as<float>(), 3, h->stream, &h->stats));

@@ -204,6 +204,7 @@ cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& t
 cudaError_t launch_count_below(const float* d2, int n, double thr, double* out /*device [1]*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_pack_points(const float* xyz, int stride_floats, long long n, float4* out, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_transform_points(const float4* pts, int n, const float* T16 /*device*/, float* out, int out_stride_floats, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_l2_flush(const void* buf, size_t bytes, float* sink, cudaStream_t stream);  // evict L2 by READING a large buffer
 cudaError_t launch_iota_w(float4* pts, int n, cudaStream_t stream, LaunchStats* st);  // pts[i].w = bits(i)
 // gather/scatter between original and sorted order for the covariance getters / setters
 cudaError_t launch_cov_export(const CloudSetView& cs, int cloud, double* out16 /*device n*16*/, cudaStream_t stream, LaunchStats* st);

@@ -381,15 +381,18 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
     };
     auto scan = [&](int leaf) {
       const ulonglong2* P = reinterpret_cast<const ulonglong2*>(L.P) + leaf * kLeaf;
-#pragma unroll 4
-      for (int j = 0; j < kLeaf / 2; j++) {
-        const ulonglong2 A = P[2 * j], B = P[2 * j + 1];
-        float d0, d1;
-        leaf_pair_d2(qx2, qy2, qz2, A, B.x, d0, d1);
-        const bool p0 = d0 <= gate, p1 = d1 <= gate;  // NaN (padding, non-finite points) fails
-        if (__any_sync(0xFFFFFFFFu, p0 || p1)) {
-          if (p0) { lst[cnt * NT] = leaf_pack_key(d0, leaf * kLeaf + 2 * j); cnt++; }
-          if (p1) { lst[cnt * NT] = leaf_pack_key(d1, leaf * kLeaf + 2 * j + 1); cnt++; }
+#pragma unroll 2
+      for (int j = 0; j < kLeaf / 2; j += 2) {   // four candidates per vote
+        const ulonglong2 A0 = P[2 * j], B0 = P[2 * j + 1], A1 = P[2 * j + 2], B1 = P[2 * j + 3];
+        float d0, d1, d2, d3;
+        leaf_pair_d2(qx2, qy2, qz2, A0, B0.x, d0, d1);
+        leaf_pair_d2(qx2, qy2, qz2, A1, B1.x, d2, d3);
+        // NaN (padding, non-finite points) fails every test (fminf drops it)
+        if (__any_sync(0xFFFFFFFFu, fminf(fminf(d0, d1), fminf(d2, d3)) <= gate)) {
+          if (d0 <= gate) { lst[cnt * NT] = leaf_pack_key(d0, leaf * kLeaf + 2 * j); cnt++; }
+          if (d1 <= gate) { lst[cnt * NT] = leaf_pack_key(d1, leaf * kLeaf + 2 * j + 1); cnt++; }
+          if (d2 <= gate) { lst[cnt * NT] = leaf_pack_key(d2, leaf * kLeaf + 2 * j + 2); cnt++; }
+          if (d3 <= gate) { lst[cnt * NT] = leaf_pack_key(d3, leaf * kLeaf + 2 * j + 3); cnt++; }
         }
       }
     };

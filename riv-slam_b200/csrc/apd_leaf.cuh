@@ -25,7 +25,7 @@
 namespace apd {
 
 constexpr int kLeaf = 32;              // points per leaf = lanes per warp
-constexpr int kLeafMaxPoints = 8192;   // 13-bit positions in packed keys; 256 leaves = 8 rounds of cached box distances
+constexpr int kLeafMaxPoints = 6144;   // 13-bit positions in packed keys; 192 leaves = 6 rounds of cached box distances
 constexpr int kLeafPosBits = 13;
 constexpr int kLeafMaxRounds = kLeafMaxPoints / kLeaf / 32;
 constexpr int kLeafTransposeMax = 20;  // 1-NN: up to this many queries needing a leaf take turns (transposed scan); more: one broadcast scan
@@ -193,17 +193,21 @@ struct LeafTop1 {
 // sits behind a warp vote: once the first candidates are in, most pairs improve nobody's result.
 __device__ __forceinline__ void leaf_scan_top1(const LeafView& L, int leaf, f32x2_t qx2, f32x2_t qy2, f32x2_t qz2, LeafTop1& v) {
   const ulonglong2* P = reinterpret_cast<const ulonglong2*>(L.P) + leaf * kLeaf;  // 2 x 16 bytes per pair, 16 pairs
-#pragma unroll 4
-  for (int j = 0; j < kLeaf / 2; j++) {
-    const ulonglong2 A = P[2 * j], B = P[2 * j + 1];
-    float d0, d1;
-    leaf_pair_d2(qx2, qy2, qz2, A, B.x, d0, d1);
+#pragma unroll 2
+  for (int j = 0; j < kLeaf / 2; j += 2) {   // four candidates per vote
+    const ulonglong2 A0 = P[2 * j], B0 = P[2 * j + 1], A1 = P[2 * j + 2], B1 = P[2 * j + 3];
+    float d0, d1, d2, d3;
+    leaf_pair_d2(qx2, qy2, qz2, A0, B0.x, d0, d1);
+    leaf_pair_d2(qx2, qy2, qz2, A1, B1.x, d2, d3);
     const float best = v.d2();
     // NaN distances (padding, non-finite points) compare false; an invalid lane's key is 0 (best = +0, and its distances are NaN)
-    if (__any_sync(0xFFFFFFFFu, d0 <= best || d1 <= best)) {
-      const unsigned long long k0 = ((unsigned long long)__float_as_uint(d0) << 32) | (B.y & 0xFFFFFFFFull);
-      const unsigned long long k1 = ((unsigned long long)__float_as_uint(d1) << 32) | (B.y >> 32);
-      const unsigned long long k = k0 < k1 ? k0 : k1;  // NaN bit patterns are above +inf: they never win
+    if (__any_sync(0xFFFFFFFFu, fminf(fminf(d0, d1), fminf(d2, d3)) <= best)) {
+      const unsigned long long k0 = ((unsigned long long)__float_as_uint(d0) << 32) | (B0.y & 0xFFFFFFFFull);
+      const unsigned long long k1 = ((unsigned long long)__float_as_uint(d1) << 32) | (B0.y >> 32);
+      const unsigned long long k2 = ((unsigned long long)__float_as_uint(d2) << 32) | (B1.y & 0xFFFFFFFFull);
+      const unsigned long long k3 = ((unsigned long long)__float_as_uint(d3) << 32) | (B1.y >> 32);
+      const unsigned long long ka = k0 < k1 ? k0 : k1, kb = k2 < k3 ? k2 : k3;  // NaN bit patterns are above +inf: they never win
+      const unsigned long long k = ka < kb ? ka : kb;
       if (k < v.key) v.key = k;
     }
   }
