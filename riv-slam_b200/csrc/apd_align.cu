@@ -67,16 +67,53 @@ __device__ __forceinline__ void team_sync() {
   else __syncthreads();
 }
 
+// Warp-wide sums of NV <= 32 per-lane values in 31 shuffles instead of 5 * NV: a reduce-scatter. In the step with offset o every
+// lane keeps the half of its values whose index has bit o equal to its own lane bit and hands the other half to lane ^ o, so the
+// value count halves with every step and lane l ends up with the warp total of value l. (Shuffles issue at one warp per clock per
+// SM: the 29 butterflies of a linearization cost 16 warps x 290 SHFL = 2.4 us per reduction, a third of a single-pair iteration.)
+// The order of the additions is fixed by the lane numbers, so the result is deterministic.
+template <int NV>
+__device__ __forceinline__ double warp_reduce_scatter(const double (&acc)[kNRed]) {
+  const int lane = threadIdx.x & 31;
+  double a[16];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const double lo = j < NV ? acc[j] : 0.0, hi = j + 16 < NV ? acc[j + 16] : 0.0;
+      const double recv = __shfl_xor_sync(0xFFFFFFFFu, up ? lo : hi, 16);
+      a[j] = (up ? hi : lo) + recv;
+    }
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    const bool up = lane & o;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (j < o) {
+        const double recv = __shfl_xor_sync(0xFFFFFFFFu, up ? a[j] : a[j + o], o);
+        a[j] = (up ? a[j + o] : a[j]) + recv;
+      }
+    }
+  }
+  return a[0];
+}
+
 // acc: per-thread partial record. On return S.red holds the team-wide sums (same bits in every CTA).
 template <int TEAM, int NV>
 __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S, TeamCtx<TEAM>& tc) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (NV > 4) {
+    const double v = warp_reduce_scatter<NV>(acc);
+    if (lane < NV) S.warp_part[warp][lane] = v;
+  } else {
 #pragma unroll
-  for (int i = 0; i < NV; i++) {
-    double v = acc[i];
+    for (int i = 0; i < NV; i++) {
+      double v = acc[i];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) S.warp_part[warp][i] = v;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0) S.warp_part[warp][i] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < NV) {
@@ -91,20 +128,50 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
     return;
   }
   team_sync<TEAM>();
-  // Cross-CTA sum, one warp per value: lane l adds the partials of ranks l, l + 32, ... (ascending), then a fixed butterfly.
-  // (One thread per value walking all ranks cost 148 dependent L2 round trips per reduction on a grid team: 30 us of a
-  // 65 us iteration.) The order is the same in every CTA, so all of them end up with identical bits.
-  for (int i = warp; i < NV; i += kAlignThreads / 32) {
-    double v = 0.0;
-    if (TEAM == TEAM_CLUSTER) {
+  // Cross-CTA sum in a fixed order that is the same in every CTA, so all of them end up with identical bits.
+  if (TEAM == TEAM_CLUSTER && tc.size <= 16) {
+    // a cluster has at most 16 ranks: each HALF-warp sums one value (lane & 15 = rank), so the 16 warps cover all 29 values of a
+    // linearization in one round of remote reads instead of two
+    cg::cluster_group cl = cg::this_cluster();
+    const int r = lane & 15;
+    for (int i = 2 * warp + (lane >> 4); i < NV; i += 2 * (kAlignThreads / 32)) {
+      double v = r < tc.size ? *cl.map_shared_rank(&S.part[tc.buf][i], r) : 0.0;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (r == 0) S.red[i] = v;
+    }
+  } else if (TEAM == TEAM_GRID) {
+    // A half-warp per value, so all values of a linearization are summed in ONE round: lane s of the half adds the partials of
+    // ranks s, s + 16, ... (ascending; the loads of a batch of 8 are independent and in flight together), then a fixed butterfly.
+    // (One thread per value walking all ranks cost 148 dependent L2 round trips per reduction: 30 us of a 65 us iteration; one
+    // warp per value still paid two rounds of three dependent round trips on a 79-CTA team.)
+    const int s16 = lane & 15;
+    for (int i = 2 * warp + (lane >> 4); i < NV; i += 2 * (kAlignThreads / 32)) {
+      double v = 0.0;
+      for (int r0 = s16; r0 < tc.size; r0 += 16 * 8) {
+        double x[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+          const int r = r0 + 16 * m;
+          x[m] = r < tc.size ? __ldcg(&tc.grid_partials[((size_t)tc.buf * tc.size + r) * kNRed + i]) : 0.0;
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) v += x[m];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (s16 == 0) S.red[i] = v;
+    }
+  } else {
+    // clusters of more than 16 CTAs do not exist today; kept general: one warp per value, lane l adds ranks l, l + 32, ...
+    for (int i = warp; i < NV; i += kAlignThreads / 32) {
+      double v = 0.0;
       cg::cluster_group cl = cg::this_cluster();
       for (int r = lane; r < tc.size; r += 32) v += *cl.map_shared_rank(&S.part[tc.buf][i], r);
-    } else {
-      for (int r = lane; r < tc.size; r += 32) v += __ldcg(&tc.grid_partials[((size_t)tc.buf * tc.size + r) * kNRed + i]);
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) S.red[i] = v;
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0) S.red[i] = v;
+    }
   }
   tc.buf ^= 1;
   __syncthreads();
@@ -656,11 +723,13 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
 #pragma unroll
       for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
       accumulate_pass<true, STAGED>(B, S.x0, T, sspts, own, sbase, acc);
+      stamp(B, 20);  // H, b partials accumulated
       team_reduce<TEAM, 29>(acc, S, tc);
       stamp(B, 4);  // H, b reduced
       if (threadIdx.x == 0) unpack_record(S);
       if (leader) atomicAdd(&B.counters[0], 1ull);
       __syncthreads();
+      stamp(B, 23);  // record unpacked
       last_y0 = S.y0;
       last_inl = S.red[28];
       if (B.mode == 1) break;
@@ -669,10 +738,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       if (P.optimizer == APD_OPT_GAUSS_NEWTON) {
         // ---- step_gn (lsq_registration_impl.hpp:107-123) ----
         if (threadIdx.x == 0) {
-          double A[36], nb[6];
-          for (int i = 0; i < 36; i++) A[i] = S.H[i];
-          for (int i = 0; i < 6; i++) nb[i] = -S.b[i];
-          ldlt6_solve(A, nb, S.d);
+          ldlt6_solve(S.H, S.b, S.d, 0.0, -1.0);
           so3_exp_matrix(S.d, S.delta);
           S.delta[9] = S.d[3]; S.delta[10] = S.d[4]; S.delta[11] = S.d[5];
           pose_mul(S.delta, S.x0, S.xi);
@@ -696,20 +762,21 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
         }
         for (int li = 0; li < P.lm_max_iterations; li++) {
           if (threadIdx.x == 0) {
-            double A[36], nb[6];
-            for (int i = 0; i < 36; i++) A[i] = S.H[i];
-            for (int i = 0; i < 6; i++) { A[i * 6 + i] += S.lambda; nb[i] = -S.b[i]; }
-            ldlt6_solve(A, nb, S.d);
+            ldlt6_solve(S.H, S.b, S.d, S.lambda, -1.0);
+            stamp(B, 24);  // LDLT done
             so3_exp_matrix(S.d, S.delta);
+            stamp(B, 25);  // so3_exp done
             S.delta[9] = S.d[3]; S.delta[10] = S.d[4]; S.delta[11] = S.d[5];
             pose_mul(S.delta, S.x0, S.xi);
           }
+          stamp(B, 21);  // damped system solved
           __syncthreads();
           // ---- compute_error(xi): stale correspondences and Mahalanobis ----
 #pragma unroll
           for (int i = 0; i < kNRed; i++) acc[i] = 0.0;
           accumulate_pass<false, STAGED>(B, S.xi, T, sspts, own, sbase, acc);
           acc[0] = acc[27];
+          stamp(B, 22);  // error partials accumulated
           team_reduce<TEAM, 1>(acc, S, tc);
           stamp(B, 5);  // LM solve + error pass reduced
           if (leader) atomicAdd(&B.counters[1], 1ull);

@@ -697,7 +697,17 @@ __device__ __forceinline__ void leaf_box_of(const float4* __restrict__ pts, cons
   }
 }
 
-__global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool bitonic) {
+// profiling aid (option "timeline"): %globaltimer stamps of the build phases of cloud 0, appended to apd_get_timeline as phases 100+
+__device__ unsigned long long g_leaf_build_stamps[16];
+__device__ __forceinline__ void bstamp(bool on, int k) {
+  if (on && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_leaf_build_stamps[k] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool bitonic, bool stamps) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   __shared__ unsigned s_hist[32][256];  // per-warp digit histograms / scatter cursors
   __shared__ unsigned s_box[32][6];
@@ -708,6 +718,7 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
   const int base = cs.pt_off[c];
   const int n = cs.pt_off[c + 1] - base;
   if (n == 0) return;
+  bstamp(stamps, 0);
   const float4* pts = cs.pts + base;
   unsigned* ka = reinterpret_cast<unsigned*>(sm_raw);
   unsigned* kb = ka + n;
@@ -746,6 +757,7 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
     s_scale = ext > 0.f ? 1023.0f / ext : 0.f;  // cubic cells: the curve's locality is isotropic
   }
   __syncthreads();
+  bstamp(stamps, 1);  // bounding box
 
   // 2. Hilbert keys
   const float lox = s_lo[0], loy = s_lo[1], loz = s_lo[2], scale = s_scale;
@@ -762,6 +774,7 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
     va[i] = (uint16_t)i;
   }
   __syncthreads();
+  bstamp(stamps, 2);  // keys
 
   // 3a. few clouds (a single scan: latency matters, the GPU is otherwise idle): bitonic sort of 64-bit (key << 13 | index) words in
   //     shared memory - 91 barrier-separated steps of four compare-exchanges per thread for 8192 slots (~5 us) against ~44 us for
@@ -879,6 +892,7 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
     __syncthreads();
     unsigned* tk = ka; ka = kb; kb = tk;
     uint16_t* tv = va; va = vb; vb = tv;
+    bstamp(stamps, 3 + (shift >> 3));  // radix pass done
   }
 
   // 4. sorted points, inverse permutation, leaf boxes (finite points only)
@@ -891,7 +905,9 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
   }
   const int nleaf = (n + kLeaf - 1) / kLeaf;
   float4* box = cs.lbox + 2 * (size_t)cs.leaf_off[c];
+  bstamp(stamps, 7);  // sorted points written
   for (int l = warp; l < nleaf; l += (T >> 5)) leaf_box_of(pts, nullptr, va, n, l, lane, box);
+  bstamp(stamps, 8);  // boxes (this warp's)
 }
 
 }  // namespace
@@ -954,7 +970,9 @@ cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap
   return cudaSuccess;
 }
 
-cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st) {
+cudaError_t leaf_build_stamps(unsigned long long out[16]) { return cudaMemcpyFromSymbol(out, g_leaf_build_stamps, sizeof(unsigned long long) * 16); }
+
+cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st, bool stamps) {
   if (cs.n_clouds == 0) return cudaSuccess;
   int n2 = 64;
   while (n2 < max_n) n2 <<= 1;
@@ -965,7 +983,7 @@ cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t st
   if (bitonic) smem = std::max(smem, (size_t)n2 * sizeof(unsigned long long) + 16);
   cudaError_t e = cudaFuncSetAttribute(leaf_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  leaf_build_kernel<<<cs.n_clouds, 1024, smem, stream>>>(cs, bitonic);
+  leaf_build_kernel<<<cs.n_clouds, 1024, smem, stream>>>(cs, bitonic, stamps);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -487,7 +487,7 @@ int cloudset_build_grid(apd_handle h, apd_cloudset_s* cs) {
   if (cs->grid_built || cs->n_clouds == 0) { cs->grid_built = true; return APD_OK; }
   KernelTimer kt(h, 1);
   if (cs->staged) {  // leaf mode: Hilbert order + leaf boxes, one CTA per cloud
-    CK(launch_leaf_build(cs->view(), cs->max_n, h->stream, &h->stats));
+    CK(launch_leaf_build(cs->view(), cs->max_n, h->stream, &h->stats, h->timeline_opt != 0));
     cs->grid_built = true;
     return APD_OK;
   }
@@ -1797,8 +1797,13 @@ int apd_get_timeline(apd_handle h, uint64_t* phase_ns /* 2 per stamp */, int max
   unsigned long long buf[512];
   CK(cudaMemcpyAsync(buf, h->timeline.p, sizeof(buf), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  const int n = (int)std::min<unsigned long long>(buf[0], 250);
-  *n_stamps = n;
+  int n = (int)std::min<unsigned long long>(buf[0], 230);
+  // the last leaf build's phases (cloud 0), as phases 100 + k
+  unsigned long long bs[16];
+  CK(leaf_build_stamps(bs));
+  for (int k = 0; k < 9; k++)
+    if (bs[k]) { buf[1 + 2 * n] = 100 + k; buf[2 + 2 * n] = bs[k]; n++; }
+  *n_stamps = std::min(n, max_stamps);
   if (phase_ns) memcpy(phase_ns, buf + 1, sizeof(unsigned long long) * 2 * std::min(n, max_stamps));
   return APD_OK;
 }

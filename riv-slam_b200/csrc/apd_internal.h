@@ -190,7 +190,8 @@ cudaError_t launch_grid_build(const CloudSetView& cs, const BuildWorkspace& ws, 
 cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap[1 + kCoarseLevels], int* const cellid[1 + kCoarseLevels],
                                     unsigned* const cursor[1 + kCoarseLevels], size_t smem_bytes /*0: global-memory version*/, cudaStream_t stream, LaunchStats* st);
 // Hilbert order + leaf boxes of every cloud of a leaf-mode set (one CTA per cloud)
-cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st, bool stamps = false);
+cudaError_t leaf_build_stamps(unsigned long long out[16]);  // profiling aid
 cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out /*nullable*/,
                                 unsigned long long* evals /*nullable: += distance evaluations*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,

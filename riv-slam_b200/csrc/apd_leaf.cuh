@@ -141,11 +141,12 @@ struct LeafSchedule {
     rounds = (L.nleaf + 31) >> 5;
 #pragma unroll
     for (int t = 0; t < kLeafMaxRounds; t++) {
-      d[t] = __int_as_float(0x7f800000);
+      float v = __int_as_float(0x7f800000);
       if (t < rounds) {
         const int l = t * 32 + lane;
-        if (l < L.nleaf && l != skip_leaf) d[t] = leaf_box_box2(glo, ghi, L.box[2 * l], L.box[2 * l + 1]);
+        if (l < L.nleaf && l != skip_leaf) v = leaf_box_box2(glo, ghi, L.box[2 * l], L.box[2 * l + 1]);
       }
+      d[t] = v;
     }
   }
   // G: the largest bound any lane still has (squared). All lanes get the same answer.
@@ -159,9 +160,11 @@ struct LeafSchedule {
     if ((best & 0xFFFFFF00u) >= 0x7F800000u) return -1;  // every leaf visited (or empty: box distance +inf)
     if (!(__uint_as_float(best & 0xFFFFFF00u) <= G)) return -1;
     const int l = (int)(best & 0xFFu);
+    // (a select per slot, not a conditional store: the compiler merges conditional stores into ONE dynamically indexed
+    // store, which moves the whole array from registers to local memory)
+    const int mine = lane == (l & 31) ? (l >> 5) : -1;
 #pragma unroll
-    for (int t = 0; t < kLeafMaxRounds; t++)
-      if (t == (l >> 5) && lane == (l & 31)) d[t] = __int_as_float(0x7f800000);
+    for (int t = 0; t < kLeafMaxRounds; t++) d[t] = (t == mine) ? __int_as_float(0x7f800000) : d[t];
     return l;
   }
 };

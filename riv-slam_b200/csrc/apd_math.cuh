@@ -204,42 +204,93 @@ APD_HD Sym3 recompose(const double V[9], const double d[3]) {
 
 // LDL^T with diagonal pivoting of a symmetric 6x6 (row-major A[36], destroyed) and solve A x = rhs.
 // Zero-pivot rule of Eigen's LDLT::solve: |D_i| <= max|D| * eps contributes 0.
-APD_HD_NOINLINE void ldlt6_solve(double* A, const double* rhs, double* x) {
+// One thread of the align kernel runs this between two block barriers while the rest of the team waits, so it is written
+// for LATENCY: only the lower triangle is kept (21 entries: the algorithm never reads the upper one after it goes stale),
+// every loop is unrolled and every index is a compile-time constant (the pivot, the only dynamic quantity, selects one of at
+// most five statically indexed swap blocks), so the matrix, the permutation and the right-hand side stay in registers. The
+// rolled version indexed a local-memory 6x6 with the pivot: a few hundred dependent local loads per solve. The arithmetic,
+// its order and the pivoting rule are those of the rolled version (and of oracle/linalg.hpp).
+#ifdef __CUDACC__
+#define APD_UNROLL _Pragma("unroll")
+#else
+#define APD_UNROLL
+#endif
+#define APD_L(i, j) L[(i) * ((i) + 1) / 2 + (j)]  // i >= j
+#define APD_SWAPD(a, b) { const double t_ = a; a = b; b = t_; }
+// Solves (Ain + diag_add * I) x = rhs_sign * rhs: the damped system of step_lm (lsq_registration_impl.hpp:137) is read straight
+// from the reduced H and b without a copy.
+APD_HD_NOINLINE void ldlt6_solve(const double* Ain, const double* rhs, double* x, double diag_add = 0.0, double rhs_sign = 1.0) {
+  double L[21], y[6];
   int perm[6];
-  for (int i = 0; i < 6; i++) perm[i] = i;
+  APD_UNROLL
+  for (int i = 0; i < 6; i++) {
+    APD_UNROLL
+    for (int j = 0; j <= i; j++) APD_L(i, j) = Ain[i * 6 + j];
+    if (diag_add != 0.0) APD_L(i, i) += diag_add;
+    perm[i] = i;
+    y[i] = rhs_sign < 0.0 ? -rhs[i] : rhs[i];
+  }
+  APD_UNROLL
   for (int k = 0; k < 6; k++) {
     int piv = k;
-    double best = fabs(A[k * 6 + k]);
+    double best = fabs(APD_L(k, k));
+    APD_UNROLL
     for (int i = k + 1; i < 6; i++) {
-      const double v = fabs(A[i * 6 + i]);
+      const double v = fabs(APD_L(i, i));
       if (v > best) { best = v; piv = i; }
     }
-    if (piv != k) {
-      for (int j = 0; j < 6; j++) { const double t = A[k * 6 + j]; A[k * 6 + j] = A[piv * 6 + j]; A[piv * 6 + j] = t; }
-      for (int i = 0; i < 6; i++) { const double t = A[i * 6 + k]; A[i * 6 + k] = A[i * 6 + piv]; A[i * 6 + piv] = t; }
-      const int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
-    }
-    const double d = A[k * 6 + k];
-    if (d == 0.0) continue;
-    for (int i = k + 1; i < 6; i++) A[i * 6 + k] /= d;
-    for (int i = k + 1; i < 6; i++)
-      for (int j = k + 1; j <= i; j++) {
-        A[i * 6 + j] -= A[i * 6 + k] * d * A[j * 6 + k];
-        A[j * 6 + i] = A[i * 6 + j];
+    APD_UNROLL
+    for (int p = k + 1; p < 6; p++) {
+      if (piv == p) {  // symmetric transposition k <-> p on the lower triangle; the right-hand side moves along (y[i] = rhs[perm[i]])
+        APD_SWAPD(APD_L(k, k), APD_L(p, p))
+        APD_UNROLL
+        for (int j = 0; j < k; j++) APD_SWAPD(APD_L(k, j), APD_L(p, j))
+        APD_UNROLL
+        for (int i = k + 1; i < p; i++) APD_SWAPD(APD_L(i, k), APD_L(p, i))
+        APD_UNROLL
+        for (int i = p + 1; i < 6; i++) APD_SWAPD(APD_L(i, k), APD_L(i, p))
+        const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+        APD_SWAPD(y[k], y[p])
       }
+    }
+    const double d = APD_L(k, k);
+    if (d != 0.0) {
+      APD_UNROLL
+      for (int i = k + 1; i < 6; i++) APD_L(i, k) /= d;
+      APD_UNROLL
+      for (int i = k + 1; i < 6; i++) {
+        APD_UNROLL
+        for (int j = k + 1; j <= i; j++) APD_L(i, j) -= APD_L(i, k) * d * APD_L(j, k);
+      }
+    }
   }
   double maxd = 0.0;
-  for (int i = 0; i < 6; i++) maxd = fmax(maxd, fabs(A[i * 6 + i]));
+  APD_UNROLL
+  for (int i = 0; i < 6; i++) maxd = fmax(maxd, fabs(APD_L(i, i)));
   const double tol = fmax(maxd * DBL_EPSILON, 1.0 / DBL_MAX);
-  double y[6];
-  for (int i = 0; i < 6; i++) y[i] = rhs[perm[i]];
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < i; j++) y[i] -= A[i * 6 + j] * y[j];
-  for (int i = 0; i < 6; i++) y[i] = (fabs(A[i * 6 + i]) > tol) ? y[i] / A[i * 6 + i] : 0.0;
-  for (int i = 5; i >= 0; i--)
-    for (int j = i + 1; j < 6; j++) y[i] -= A[j * 6 + i] * y[j];
-  for (int i = 0; i < 6; i++) x[perm[i]] = y[i];
+  APD_UNROLL
+  for (int i = 0; i < 6; i++) {
+    APD_UNROLL
+    for (int j = 0; j < i; j++) y[i] -= APD_L(i, j) * y[j];
+  }
+  APD_UNROLL
+  for (int i = 0; i < 6; i++) y[i] = (fabs(APD_L(i, i)) > tol) ? y[i] / APD_L(i, i) : 0.0;
+  APD_UNROLL
+  for (int i = 5; i >= 0; i--) {
+    APD_UNROLL
+    for (int j = i + 1; j < 6; j++) y[i] -= APD_L(j, i) * y[j];
+  }
+  // x[perm[i]] = y[i] without a dynamically indexed store
+  APD_UNROLL
+  for (int o = 0; o < 6; o++) {
+    double v = 0.0;
+    APD_UNROLL
+    for (int i = 0; i < 6; i++) v = (perm[i] == o) ? y[i] : v;
+    x[o] = v;
+  }
 }
+#undef APD_L
+#undef APD_SWAPD
 
 // so3_exp (so3.hpp:59-78) followed by Quaterniond::toRotationMatrix; R row-major
 APD_HD_NOINLINE void so3_exp_matrix(const double* w, double* R) {

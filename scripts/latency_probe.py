@@ -38,10 +38,14 @@ reg.setInputTarget(clouds[0], cache_key=1001); reg.setInputSource(clouds[1], cac
 reg.computeCovariances()
 reg.align(None, want_output=False)
 tl = H.timeline()
-names = {0: "enter", 1: "staged", 2: "iter", 3: "corr", 4: "H/b", 5: "LM trial", 6: "fitness", 10: "nn1>", 11: "<nn1", 12: "mahal", 13: "passend", 14: "synced"}
+names = {0: "enter", 1: "staged", 2: "iter", 3: "corr", 4: "H/b", 5: "LM trial", 6: "fitness", 10: "nn1>", 11: "<nn1", 12: "mahal", 13: "passend", 14: "synced", 20: "acc", 21: "solved", 22: "erracc", 23: "unpacked", 24: "ldlt", 25: "so3exp"}
 if tl:
     t0 = tl[0][1]
-    print("timeline (us):", " ".join(f"{names.get(p, p)}@{(t - t0) / 1e3:.1f}" for p, t in tl))
+    print("timeline (us):", " ".join(f"{names.get(p, p)}@{(t - t0) / 1e3:.1f}" for p, t in tl if p < 100))
+    bl = [(p, t) for p, t in tl if p >= 100]
+    if bl:
+        bn = {100: "enter", 101: "bbox", 102: "keys", 103: "pass0", 104: "pass1", 105: "pass2", 106: "pass3", 107: "gather", 108: "boxes"}
+        print("leaf build (us):", " ".join(f"{bn.get(p, p)}@{(t - bl[0][1]) / 1e3:.1f}" for p, t in bl))
 dc = H.debug_counters()
 for nm, c in (("first pass", dc[:8]), ("seeded passes", dc[8:])):
     if c[0]:
