@@ -53,11 +53,27 @@ struct AlignShared {
   float4 qslot[kAlignThreads / 32][32];  // leaf mode: every warp's 32 queries (x, y, z, bits of the best d2) for the transposed scans
 };
 
+// profiling aid (apd_set_option "timeline"): nanosecond stamps of the phases of the first pair, read back by apd_get_timeline
+__device__ __forceinline__ void stamp_tl(unsigned long long* tl, int phase) {
+  if (tl && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long n = tl[0];
+    if (n < 250) {
+      tl[1 + 2 * n] = (unsigned long long)phase;
+      tl[2 + 2 * n] = t;
+      tl[0] = n + 1;
+    }
+  }
+}
+__device__ __forceinline__ void stamp(const AlignBatch& B, int phase) { stamp_tl(B.timeline, phase); }
+
 template <int TEAM>
 struct TeamCtx {
   int size, rank, id, count;
   int buf;
   double* grid_partials;
+  unsigned long long* tl;  // timeline (profiling aid), usually null
 };
 
 template <int TEAM>
@@ -116,6 +132,7 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
     }
   }
   __syncthreads();
+  if (NV > 4) stamp_tl(tc.tl, 30);  // warp sums done
   if (threadIdx.x < NV) {
     double v = 0.0;
     for (int w = 0; w < kAlignThreads / 32; w++) v += S.warp_part[w][threadIdx.x];
@@ -127,18 +144,21 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
     __syncthreads();
     return;
   }
+  if (NV > 4) stamp_tl(tc.tl, 31);  // CTA partial written
   team_sync<TEAM>();
+  if (NV > 4) stamp_tl(tc.tl, 32);  // team barrier passed
   // Cross-CTA sum in a fixed order that is the same in every CTA, so all of them end up with identical bits.
   if (TEAM == TEAM_CLUSTER && tc.size <= 16) {
     // a cluster has at most 16 ranks: each HALF-warp sums one value (lane & 15 = rank), so the 16 warps cover all 29 values of a
     // linearization in one round of remote reads instead of two
     cg::cluster_group cl = cg::this_cluster();
     const int r = lane & 15;
-    for (int i = 2 * warp + (lane >> 4); i < NV; i += 2 * (kAlignThreads / 32)) {
-      double v = r < tc.size ? *cl.map_shared_rank(&S.part[tc.buf][i], r) : 0.0;
+    for (int i0 = 2 * warp; i0 < NV; i0 += 2 * (kAlignThreads / 32)) {  // warp-uniform trip count: the shuffles below need all 32 lanes
+      const int i = i0 + (lane >> 4);
+      double v = (i < NV && r < tc.size) ? *cl.map_shared_rank(&S.part[tc.buf][i], r) : 0.0;
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if (r == 0) S.red[i] = v;
+      if (r == 0 && i < NV) S.red[i] = v;
     }
   } else if (TEAM == TEAM_GRID) {
     // A half-warp per value, so all values of a linearization are summed in ONE round: lane s of the half adds the partials of
@@ -146,21 +166,25 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
     // (One thread per value walking all ranks cost 148 dependent L2 round trips per reduction: 30 us of a 65 us iteration; one
     // warp per value still paid two rounds of three dependent round trips on a 79-CTA team.)
     const int s16 = lane & 15;
-    for (int i = 2 * warp + (lane >> 4); i < NV; i += 2 * (kAlignThreads / 32)) {
+    for (int i0 = 2 * warp; i0 < NV; i0 += 2 * (kAlignThreads / 32)) {  // warp-uniform trip count: the shuffles below need all 32 lanes
+      const int i = i0 + (lane >> 4);
       double v = 0.0;
-      for (int r0 = s16; r0 < tc.size; r0 += 16 * 8) {
-        double x[8];
+      if (i < NV) {
+        for (int r0 = s16; r0 < tc.size; r0 += 16 * 8) {
+          double x[8];
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-          const int r = r0 + 16 * m;
-          x[m] = r < tc.size ? __ldcg(&tc.grid_partials[((size_t)tc.buf * tc.size + r) * kNRed + i]) : 0.0;
+          for (int m = 0; m < 8; m++) {
+            const int r = r0 + 16 * m;
+            x[m] = r < tc.size ? __ldcg(&tc.grid_partials[((size_t)tc.buf * tc.size + r) * kNRed + i]) : 0.0;
+          }
+#pragma unroll
+          for (int m = 0; m < 8; m++) v += x[m];
         }
-#pragma unroll
-        for (int m = 0; m < 8; m++) v += x[m];
       }
+      __syncwarp();
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if (s16 == 0) S.red[i] = v;
+      if (s16 == 0 && i < NV) S.red[i] = v;
     }
   } else {
     // clusters of more than 16 CTAs do not exist today; kept general: one warp per value, lane l adds ranks l, l + 32, ...
@@ -186,15 +210,19 @@ __device__ __forceinline__ void team_reduce(double (&acc)[kNRed], AlignShared& S
 // (a contiguous split gave one CTA the dense near-range points and another the sparse clutter, whose searches take
 // several times longer: the whole cluster then waited for it at every reduction). A CTA addresses its points by a LOCAL
 // index j in [0, n_local); map(j) is the point, or >= ns past the end of the cloud. Team of one CTA: the identity.
+// A large team on a small cloud (the cooperative grid on one scan pair: ~64 points per CTA, 4 per warp) deals blocks of 8 instead:
+// with two 32-point blocks per CTA the slowest CTA's search pass took twice the average, and every CTA waited for it at the grid
+// barrier of the reduction (3.8 us of a 6 us reduction).
 struct Own {
-  int size, rank, ns, n_local;
-  __device__ __forceinline__ int map(int j) const { return (((j >> 5) * size + rank) << 5) | (j & 31); }
+  int size, rank, ns, n_local, sh;
+  __device__ __forceinline__ int map(int j) const { return (((j >> sh) * size + rank) << sh) | (j & ((1 << sh) - 1)); }
 };
 __device__ __forceinline__ Own make_own(int ns, int size, int rank) {
   Own o;
   o.size = size; o.rank = rank; o.ns = ns;
-  const int blocks = (ns + 31) >> 5;
-  o.n_local = blocks > rank ? ((blocks - rank + size - 1) / size) << 5 : 0;
+  o.sh = (size > 16 && ns <= size * 8 * (kAlignThreads / 32)) ? 3 : 5;
+  const int blocks = (ns + (1 << o.sh) - 1) >> o.sh;
+  o.n_local = blocks > rank ? ((blocks - rank + size - 1) / size) << o.sh : 0;
   return o;
 }
 
@@ -208,7 +236,7 @@ __device__ __forceinline__ ChunkPlan chunk_begin(AlignShared& S, const Own& own)
   const int n_warps = blockDim.x >> 5;
   ChunkPlan c;
   // a power of two: a group must not straddle two of the CTA's 32-point blocks (with a team they are far apart in space)
-  const int want = max(1, min(32, (own.n_local + n_warps - 1) / n_warps));
+  const int want = max(1, min(1 << own.sh, (own.n_local + n_warps - 1) / n_warps));
   c.chunk = 1 << (31 - __clz(want));
   c.lane = threadIdx.x & 31;
   c.n_local = own.n_local;
@@ -308,20 +336,6 @@ struct TargetView {
   const int* inv0;                    // original index -> sorted position (this cloud)
   int cloud;                          // index in B.tgt (for the coarse pyramid levels)
 };
-
-// profiling aid (apd_set_option "timeline"): nanosecond stamps of the phases of the first pair, read back by apd_get_timeline
-__device__ __forceinline__ void stamp(const AlignBatch& B, int phase) {
-  if (B.timeline && blockIdx.x == 0 && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    const unsigned long long n = B.timeline[0];
-    if (n < 250) {
-      B.timeline[1 + 2 * n] = (unsigned long long)phase;
-      B.timeline[2 + 2 * n] = t;
-      B.timeline[0] = n + 1;
-    }
-  }
-}
 
 // covariances of a matched pair -> Mahalanobis matrix of the point (fast_apdgicp_impl.hpp:159-192)
 template <typename CellT>
@@ -611,6 +625,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
   TeamCtx<TEAM> tc;
   tc.buf = 0;
   tc.grid_partials = B.grid_partials;
+  tc.tl = B.timeline;
   if (TEAM == TEAM_CTA) {
     tc.size = 1; tc.rank = 0; tc.id = blockIdx.x; tc.count = gridDim.x;
   } else if (TEAM == TEAM_CLUSTER) {
@@ -864,7 +879,7 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
 template <int TEAM, bool STAGED>
 cudaError_t launch_t(const AlignBatch& b, int team_size, int n_teams, size_t smem_bytes, cudaStream_t stream) {
   auto kern = align_kernel<TEAM, STAGED>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  cudaError_t e = ensure_dynamic_smem(kern, smem_bytes);
   if (e != cudaSuccess) return e;
   if (TEAM == TEAM_CTA) {
     kern<<<n_teams, kAlignThreads, smem_bytes, stream>>>(b);
@@ -897,7 +912,7 @@ cudaError_t launch_t(const AlignBatch& b, int team_size, int n_teams, size_t sme
 template <int TEAM, bool STAGED>
 int max_teams_t(int team_size, size_t smem_bytes) {
   auto kern = align_kernel<TEAM, STAGED>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+  if (ensure_dynamic_smem(kern, smem_bytes) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -1081,7 +1096,7 @@ cudaError_t launch_fitness(const CloudSetView& src, int s, const CloudSetView& t
                            int blocks, double* out, cudaStream_t stream, LaunchStats* st) {
   if (tgt.lbox) {  // leaf-mode target: staged per CTA, so few CTAs (the staging copy is the fixed cost)
     const size_t smem = (size_t)((tgt.total_points + kLeaf - 1) / kLeaf + tgt.n_clouds) * (kLeaf * 16 + 32);  // >= the largest cloud of the set
-    cudaError_t e = cudaFuncSetAttribute(fitness_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(fitness_leaf_kernel, smem);
     if (e != cudaSuccess) return e;
     fitness_leaf_kernel<<<blocks, 256, smem, stream>>>(src, s, tgt, t, T16, max_range, strict, partials);
   } else {

@@ -646,6 +646,14 @@ __global__ void corr_export_kernel(AlignBatch b, int slot, int s, int t, int* __
 // (pcl::KdTreeFLANN::convertCloudToArray leaves them out of the index). Equal keys keep their input order (the sort is
 // stable), so the layout - and with it every later summation order - is deterministic.
 
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // bit b -> bit 3b, for 10-bit v
+  v = (v | v << 16) & 0x030000FFu;
+  v = (v | v << 8) & 0x0300F00Fu;
+  v = (v | v << 4) & 0x030C30C3u;
+  v = (v | v << 2) & 0x09249249u;
+  return v;
+}
+
 // Skilling's transform: 3 x 10 bit coordinates -> 30-bit Hilbert index (consecutive indices are adjacent cells)
 __device__ __forceinline__ unsigned hilbert30(unsigned x, unsigned y, unsigned z) {
   unsigned X[3] = {x, y, z};
@@ -665,10 +673,8 @@ __device__ __forceinline__ unsigned hilbert30(unsigned x, unsigned y, unsigned z
   for (unsigned Q = 512u; Q > 1u; Q >>= 1)
     if (X[2] & Q) t ^= Q - 1u;
   X[0] ^= t; X[1] ^= t; X[2] ^= t;
-  unsigned key = 0u;
-#pragma unroll
-  for (int b = 0; b < 10; b++) key |= ((X[0] >> b) & 1u) << (3 * b + 2) | ((X[1] >> b) & 1u) << (3 * b + 1) | ((X[2] >> b) & 1u) << (3 * b);
-  return key;
+  // interleave: bit b of X[0] -> 3b + 2, of X[1] -> 3b + 1, of X[2] -> 3b (spread by magic masks: 9 operations per coordinate)
+  return spread10(X[0]) << 2 | spread10(X[1]) << 1 | spread10(X[2]);
 }
 
 // bounding box of leaf l (finite points only), by one warp; the sorted order comes either as 64-bit words (index in the low 13 bits)
@@ -719,16 +725,20 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
   const int n = cs.pt_off[c + 1] - base;
   if (n == 0) return;
   bstamp(stamps, 0);
-  const float4* pts = cs.pts + base;
-  unsigned* ka = reinterpret_cast<unsigned*>(sm_raw);
+  const float4* gpts = cs.pts + base;
+  // the cloud itself is kept in shared memory for the whole build: the key pass, the final gather and the leaf boxes read it again
+  // in sorted (random) order, which from global memory cost one exposed L2 round trip per point and thread (7 + 3 us of a 42 us build)
+  float4* pts = reinterpret_cast<float4*>(sm_raw);
+  unsigned* ka = reinterpret_cast<unsigned*>(pts + n);
   unsigned* kb = ka + n;
   uint16_t* va = reinterpret_cast<uint16_t*>(kb + n);
   uint16_t* vb = va + n;
 
-  // 1. bounding box of the finite points
+  // 1. stage the points; bounding box of the finite ones
   unsigned mn[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, mx[3] = {0u, 0u, 0u};
   for (int i = tid; i < n; i += T) {
-    const float4 p = pts[i];
+    const float4 p = gpts[i];
+    pts[i] = p;
     if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
       const unsigned e[3] = {enc_f(p.x), enc_f(p.y), enc_f(p.z)};
 #pragma unroll
@@ -781,7 +791,7 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
   //     the four radix passes below, whose histogram / scan / ranked-scatter phases are long dependent chains. Many more
   //     instructions in total, so batches keep the radix sort. Same order either way: the index breaks ties, as stability does.
   if (bitonic) {
-    unsigned long long* w = reinterpret_cast<unsigned long long*>(sm_raw);
+    unsigned long long* w = reinterpret_cast<unsigned long long*>(ka);  // behind the staged points (8-byte aligned: 16 n bytes in front)
     int n2 = 64;
     while (n2 < n) n2 <<= 1;
     __syncthreads();
@@ -837,6 +847,7 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
       if (j < n) atomicAdd(&s_hist[warp][(ka[j] >> shift) & 255u], 1u);
     }
     __syncthreads();
+    bstamp(stamps && shift == 0, 9);  // pass 0: histograms
     {  // exclusive scan of the 256 x 32 bins in (digit, warp) order: 8 consecutive bins per thread
       unsigned loc[8], sum = 0u;
 #pragma unroll
@@ -873,12 +884,21 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
       }
     }
     __syncthreads();
+    bstamp(stamps && shift == 0, 10);  // pass 0: bins ranked
     for (int r = r0; r < r1; r++) {
       const int j = (r << 5) + lane;
       const bool valid = j < n;
       const unsigned k = valid ? ka[j] : 0u;
-      const unsigned d = valid ? ((k >> shift) & 255u) : (0x10000u + (unsigned)lane);
-      const unsigned same = __match_any_sync(0xFFFFFFFFu, d);
+      const unsigned d = (k >> shift) & 255u;
+      // lanes of this row with the same digit: eight ballots (one per digit bit). __match_any_sync resolves one distinct value per
+      // step: ~1 us per row when the 32 digits of a row are all different (the low bytes of a Hilbert key), 5 of the 7 us of a pass.
+      unsigned same = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        const unsigned bit = (d >> b) & 1u;
+        const unsigned v = __ballot_sync(0xFFFFFFFFu, bit);
+        same &= bit ? v : ~v;
+      }
       const unsigned rank = __popc(same & ((1u << lane) - 1u));
       if (valid) {
         const unsigned dst = s_hist[warp][d] + rank;
@@ -895,19 +915,35 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
     bstamp(stamps, 3 + (shift >> 3));  // radix pass done
   }
 
-  // 4. sorted points, inverse permutation, leaf boxes (finite points only)
+  // 4. sorted points, inverse permutation, leaf boxes (finite points only): a warp's 32 consecutive sorted positions ARE one leaf
   float4* spts = cs.spts + base;
-  for (int i = tid; i < n; i += T) {
-    const unsigned idx = va[i];
-    const float4 p = pts[idx];
-    spts[i] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
-    cs.inv0[base + idx] = i;
-  }
   const int nleaf = (n + kLeaf - 1) / kLeaf;
   float4* box = cs.lbox + 2 * (size_t)cs.leaf_off[c];
-  bstamp(stamps, 7);  // sorted points written
-  for (int l = warp; l < nleaf; l += (T >> 5)) leaf_box_of(pts, nullptr, va, n, l, lane, box);
-  bstamp(stamps, 8);  // boxes (this warp's)
+  for (int l = warp; l < nleaf; l += (T >> 5)) {
+    const int i = l * kLeaf + lane;
+    unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    if (i < n) {
+      const unsigned idx = va[i];
+      const float4 p = pts[idx];
+      spts[i] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
+      cs.inv0[base + idx] = i;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        lo[0] = hi[0] = enc_f(p.x); lo[1] = hi[1] = enc_f(p.y); lo[2] = hi[2] = enc_f(p.z);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
+      hi[a] = __reduce_max_sync(0xFFFFFFFFu, hi[a]);
+    }
+    if (lane == 0) {
+      const float inf = __int_as_float(0x7f800000);
+      const bool empty = lo[0] > hi[0];
+      box[2 * l] = empty ? make_float4(inf, inf, inf, 0.f) : make_float4(dec_f(lo[0]), dec_f(lo[1]), dec_f(lo[2]), 0.f);
+      box[2 * l + 1] = empty ? make_float4(-inf, -inf, -inf, 0.f) : make_float4(dec_f(hi[0]), dec_f(hi[1]), dec_f(hi[2]), 0.f);
+    }
+  }
+  bstamp(stamps, 8);  // sorted points, inverse order and boxes written
 }
 
 }  // namespace
@@ -959,7 +995,7 @@ cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap
   FusedLevels L;
   for (int l = 0; l <= kCoarseLevels; l++) { L.cap[l] = cap[l]; L.cellid[l] = cellid[l]; L.cursor[l] = cursor[l]; }
   if (smem_bytes > 0) {  // every cloud's sorted points + cell table fit shared memory
-    cudaError_t e = cudaFuncSetAttribute(build_fused_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = ensure_dynamic_smem(build_fused_smem_kernel, smem_bytes);
     if (e != cudaSuccess) return e;
     build_fused_smem_kernel<<<dim3(cs.n_clouds, 1 + kCoarseLevels), 1024, smem_bytes, stream>>>(cs, L);
     APD_LAUNCH_CHECK();
@@ -979,9 +1015,9 @@ cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t st
   // Measured on one 5000-point scan: the bitonic path takes 97 us against 44 us for the four radix passes (91 barrier-separated
   // steps of conflicting 64-bit shared-memory exchanges): kept for the record, not used.
   const bool bitonic = false;
-  size_t smem = (size_t)max_n * (2 * sizeof(unsigned) + 2 * sizeof(uint16_t)) + 16;
-  if (bitonic) smem = std::max(smem, (size_t)n2 * sizeof(unsigned long long) + 16);
-  cudaError_t e = cudaFuncSetAttribute(leaf_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = (size_t)max_n * (sizeof(float4) + 2 * sizeof(unsigned) + 2 * sizeof(uint16_t)) + 16;
+  if (bitonic) smem = std::max(smem, (size_t)max_n * sizeof(float4) + (size_t)n2 * sizeof(unsigned long long) + 16);
+  cudaError_t e = ensure_dynamic_smem(leaf_build_kernel, smem);
   if (e != cudaSuccess) return e;
   leaf_build_kernel<<<cs.n_clouds, 1024, smem, stream>>>(cs, bitonic, stamps);
   APD_LAUNCH_CHECK();

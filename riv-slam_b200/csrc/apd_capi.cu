@@ -11,6 +11,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "apd_internal.h"
@@ -189,7 +190,7 @@ struct apd_context {
   std::vector<cudaEvent_t> event_pool;
   // scratch (grow-only)
   DevBuf raw_upload, ws_bbox, ws_cellid, ws_cursor, sc_corr, sc_sqd, sc_m0, sc_m1, sc_m2, sc_anchor, sc_fit, results, guesses, idx_src, idx_tgt, fh, lin_b, trace, trace_count,
-      counters, search_counters, grid_partials, misc, timeline, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
+      counters, search_counters, grid_partials, misc, timeline, oneblock, knn_tmp, cov_tmp, pp_a, pp_b, pp_flag, pp_n, pp_ws, pp_seg, pp_tab;
   int scratch_slots = 0, scratch_max_src = 0;
   // last single-pair alignment
   bool has_last = false;
@@ -203,6 +204,8 @@ struct apd_context {
   unsigned char* stage_host[2] = {nullptr, nullptr};  // slot 0: cloud-set tables, slot 1: small point uploads
   size_t stage_cap[2] = {0, 0};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  std::map<std::tuple<int, int, bool, size_t>, int> team_fit;  // cached occupancy answers (max_teams_cached)
+  unsigned char* down_host = nullptr;  // pinned landing area of apd_align's result block
   apd_handle helper = nullptr;   // second stream/pool for pipelined batches (pipelined_align)
   long long helper_launches_seen = 0;
 };
@@ -546,7 +549,7 @@ int cloudset_prepare(apd_handle h, apd_cloudset_s* cs, int* knn_out = nullptr) {
     CK(h->search_counters.reserve(sizeof(unsigned long long) * 4));
     CK(cudaMemsetAsync(h->search_counters.p, 0, sizeof(unsigned long long) * 4, h->stream));
   }
-  if (cs->staged) CK(launch_knn_cov_leaf(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->max_n, dp, knn_out, h->search_counters.as<unsigned long long>(), h->stream, &h->stats));
+  if (cs->staged) CK(launch_knn_cov_leaf(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, cs->max_n, dp, knn_out, h->search_counters.as<unsigned long long>(), h->stream, &h->stats, h->timeline_opt != 0));
   else CK(launch_knn_cov(cs->view(), cs->d_tiles_knn, cs->n_tiles_knn, false, 0, dp, knn_out, h->stream, &h->stats));
   cs->cov_valid = true;
   cs->cov_k = k;
@@ -603,6 +606,16 @@ struct TeamPlan {
 // (or the whole cooperative grid for very large sources) when few pairs must be made fast.
 // plan_for_pairs: the batch size the team shape is chosen for (a pipelined call plans once for the whole
 // batch so that every chunk sums in the same order and the records do not depend on the chunking)
+// occupancy queries are driver calls (several microseconds each) and their answers never change for a handle: remember them
+int max_teams_cached(apd_handle h, int kind, int size, bool staged, size_t smem) {
+  const auto key = std::make_tuple(kind, size, staged, smem);
+  auto it = h->team_fit.find(key);
+  if (it != h->team_fit.end()) return it->second;
+  const int fit = align_max_teams(kind, size, staged, smem);
+  h->team_fit.emplace(key, fit);
+  return fit;
+}
+
 int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tgt, int n_pairs, int plan_for_pairs, TeamPlan* plan) {
   TeamPlan p;
   p.staged = tgt->staged;
@@ -621,7 +634,7 @@ int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tg
   const bool single_staged = p.staged && h->team_size <= 0 && n_pairs == 1 && plan_for_pairs <= 1 && src->max_n >= 256;
   if ((force_grid_team && n_pairs == 1) || single_staged || (!p.staged && h->team_size <= 0 && n_pairs == 1 && src->max_n > 16 * kAlignThreads * 2)) {
     // large source against a large target: the whole GPU on one pair
-    const int max_blocks = align_max_teams(TEAM_GRID, 0, p.staged, p.smem);
+    const int max_blocks = max_teams_cached(h, TEAM_GRID, 0, p.staged, p.smem);
     if (max_blocks >= 2) {
       p.kind = TEAM_GRID;
       p.size = std::min(max_blocks, (src->max_n + kAlignThreads - 1) / kAlignThreads);
@@ -634,10 +647,10 @@ int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tg
   }
   if (size > 1) {
     if (size > 16) size = 16;
-    int fit = align_max_teams(TEAM_CLUSTER, size, p.staged, p.smem);
+    int fit = max_teams_cached(h, TEAM_CLUSTER, size, p.staged, p.smem);
     while (fit < 1 && size > 1) {
       size /= 2;
-      fit = size > 1 ? align_max_teams(TEAM_CLUSTER, size, p.staged, p.smem) : 0;
+      fit = size > 1 ? max_teams_cached(h, TEAM_CLUSTER, size, p.staged, p.smem) : 0;
     }
     if (size > 1) {
       p.kind = TEAM_CLUSTER;
@@ -648,7 +661,7 @@ int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tg
       return APD_OK;
     }
   }
-  const int fit = align_max_teams(TEAM_CTA, 1, p.staged, p.smem);
+  const int fit = max_teams_cached(h, TEAM_CTA, 1, p.staged, p.smem);
   if (fit < 1) return fail(h, APD_ERR_CUDA, "align kernel does not fit on this device");
   p.kind = TEAM_CTA;
   p.size = 1;
@@ -670,7 +683,15 @@ struct AlignCall {
   double max_range = DBL_MAX;
   bool want_trace = false;
   bool want_hessian = false;
+  // single-pair calls: result record, work counters, trace count, final Hessian, b and the trace rows live in ONE device block
+  // (layout kOB_*), cleared by one memset and fetched by one copy into pinned memory
+  unsigned char* block = nullptr;
+  int block_trace_rows = 0;
 };
+
+constexpr size_t kOB_result = 0, kOB_counters = 128, kOB_tcount = 160, kOB_fh = 176, kOB_linb = 464, kOB_trace = 512;
+constexpr int kOB_fast_rows = 40;  // trace rows fetched together with the header (a registration rarely has more LM trials)
+static_assert(sizeof(apd_result) <= kOB_counters, "result record must fit its slot");
 
 // Enqueue the align kernel for a batch; results land in h->results (device).
 int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, TeamPlan* used_plan = nullptr) {
@@ -687,9 +708,16 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   if (rc) return rc;
   rc = ensure_align_scratch(h, plan.kind == TEAM_GRID ? 1 : plan.teams, std::max(c.src->max_n, 1));
   if (rc) return rc;
-  CK(h->results.reserve(sizeof(apd_result) * np));
-  CK(h->counters.reserve(sizeof(unsigned long long) * 4));
-  CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * 4, h->stream));
+  unsigned long long* d_counters = nullptr;
+  if (c.block) {
+    CK(cudaMemsetAsync(c.block, 0, kOB_trace, h->stream));
+    d_counters = reinterpret_cast<unsigned long long*>(c.block + kOB_counters);
+  } else {
+    CK(h->results.reserve(sizeof(apd_result) * np));
+    CK(h->counters.reserve(sizeof(unsigned long long) * 4));
+    CK(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * 4, h->stream));
+    d_counters = h->counters.as<unsigned long long>();
+  }
   AlignBatch b;
   memset(&b, 0, sizeof(b));
   b.src = c.src->view();
@@ -713,25 +741,34 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
     CK(cudaMemcpyAsync(h->guesses.p, c.guesses, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, h->stream));
     b.guesses = h->guesses.as<float>();
   }
-  b.out = h->results.as<apd_result>();
-  if (c.want_hessian || c.mode == 1) {
-    CK(h->fh.reserve(sizeof(double) * 36 * np));
-    CK(h->lin_b.reserve(sizeof(double) * 6 * np));
-    CK(cudaMemsetAsync(h->fh.p, 0, sizeof(double) * 36 * np, h->stream));
-    b.final_hessian = h->fh.as<double>();
-    b.lin_b = h->lin_b.as<double>();
-  }
-  if (c.want_trace) {
-    b.trace_rows = std::max(1, std::min(4096, h->prm.max_iterations * std::max(1, h->prm.lm_max_iterations)));
-    CK(h->trace.reserve(sizeof(double) * 8 * b.trace_rows * np));
-    CK(h->trace_count.reserve(sizeof(int) * np));
-    CK(cudaMemsetAsync(h->trace_count.p, 0, sizeof(int) * np, h->stream));
-    b.trace = h->trace.as<double>();
-    b.trace_count = h->trace_count.as<int>();
+  if (c.block) {
+    b.out = reinterpret_cast<apd_result*>(c.block + kOB_result);
+    b.final_hessian = reinterpret_cast<double*>(c.block + kOB_fh);
+    b.lin_b = reinterpret_cast<double*>(c.block + kOB_linb);
+    b.trace_rows = c.block_trace_rows;
+    b.trace = reinterpret_cast<double*>(c.block + kOB_trace);
+    b.trace_count = reinterpret_cast<int*>(c.block + kOB_tcount);
+  } else {
+    b.out = h->results.as<apd_result>();
+    if (c.want_hessian || c.mode == 1) {
+      CK(h->fh.reserve(sizeof(double) * 36 * np));
+      CK(h->lin_b.reserve(sizeof(double) * 6 * np));
+      CK(cudaMemsetAsync(h->fh.p, 0, sizeof(double) * 36 * np, h->stream));
+      b.final_hessian = h->fh.as<double>();
+      b.lin_b = h->lin_b.as<double>();
+    }
+    if (c.want_trace) {
+      b.trace_rows = std::max(1, std::min(4096, h->prm.max_iterations * std::max(1, h->prm.lm_max_iterations)));
+      CK(h->trace.reserve(sizeof(double) * 8 * b.trace_rows * np));
+      CK(h->trace_count.reserve(sizeof(int) * np));
+      CK(cudaMemsetAsync(h->trace_count.p, 0, sizeof(int) * np, h->stream));
+      b.trace = h->trace.as<double>();
+      b.trace_count = h->trace_count.as<int>();
+    }
   }
   b.n_pairs = np;
-  b.work_counter = reinterpret_cast<int*>(h->counters.as<unsigned long long>() + 2);
-  b.counters = h->counters.as<unsigned long long>();
+  b.work_counter = reinterpret_cast<int*>(d_counters + 2);
+  b.counters = d_counters;
   if (plan.kind == TEAM_GRID) {
     CK(h->grid_partials.reserve(sizeof(double) * 2 * plan.size * kNRed));
     b.grid_partials = h->grid_partials.as<double>();
@@ -874,6 +911,7 @@ int apd_destroy(apd_handle h) {
     if (h->stage_host[i]) cudaFreeHost(h->stage_host[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
   }
+  if (h->down_host) cudaFreeHost(h->down_host);
   for (auto& t : h->timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
   for (auto& e : h->event_pool) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1007,19 +1045,37 @@ int apd_align(apd_handle h, const float guess[16], apd_result* out) {
   c.n_pairs = 1;
   c.want_trace = true;
   c.want_hessian = true;
+  // One device block, one memset, one copy into pinned memory, one synchronisation. (Five separate copies into pageable host
+  // variables - record, trace count, Hessian, counters, trace - each blocked the host for a driver round trip: ~40 us of a
+  // 165 us call around a 90 us kernel.)
+  c.block_trace_rows = std::max(1, std::min(4096, h->prm.max_iterations * std::max(1, h->prm.lm_max_iterations)));
+  CK(h->oneblock.reserve(kOB_trace + sizeof(double) * 8 * (size_t)c.block_trace_rows));
+  c.block = h->oneblock.as<unsigned char>();
+  const size_t fast_bytes = kOB_trace + sizeof(double) * 8 * (size_t)std::min(c.block_trace_rows, kOB_fast_rows);
+  if (!h->down_host) CK(cudaHostAlloc(reinterpret_cast<void**>(&h->down_host), kOB_trace + sizeof(double) * 8 * kOB_fast_rows, cudaHostAllocDefault));
   AlignBatch b;
   rc = run_align(h, c, &b);
   if (rc) return rc;
+  CK(cudaMemcpyAsync(h->down_host, c.block, fast_bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  memcpy(&h->last, h->down_host + kOB_result, sizeof(apd_result));
+  {
+    unsigned long long cnt[4];
+    memcpy(cnt, h->down_host + kOB_counters, sizeof(cnt));
+    h->work_lin = (long long)cnt[0];
+    h->work_err = (long long)cnt[1];
+    h->work_pairs = 1;
+  }
   int n_rows = 0;
+  memcpy(&n_rows, h->down_host + kOB_tcount, sizeof(int));
   double fh[36];
-  CK(cudaMemcpyAsync(&h->last, h->results.p, sizeof(apd_result), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(&n_rows, h->trace_count.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(fh, h->fh.p, sizeof(fh), cudaMemcpyDeviceToHost, h->stream));
-  rc = fetch_counters(h, 1);
-  if (rc) return rc;
+  memcpy(fh, h->down_host + kOB_fh, sizeof(fh));
   if (n_rows > 0) {
     h->lm_trace.resize((size_t)n_rows * 8);
-    CK(cudaMemcpy(h->lm_trace.data(), h->trace.p, sizeof(double) * 8 * n_rows, cudaMemcpyDeviceToHost));
+    const int fast = std::min(n_rows, kOB_fast_rows);
+    memcpy(h->lm_trace.data(), h->down_host + kOB_trace, sizeof(double) * 8 * fast);
+    if (n_rows > fast)
+      CK(cudaMemcpy(h->lm_trace.data() + (size_t)fast * 8, c.block + kOB_trace + sizeof(double) * 8 * fast, sizeof(double) * 8 * (n_rows - fast), cudaMemcpyDeviceToHost));
   }
   bool any = false;
   for (int i = 0; i < 36; i++) any |= fh[i] != 0.0;
@@ -1801,8 +1857,13 @@ int apd_get_timeline(apd_handle h, uint64_t* phase_ns /* 2 per stamp */, int max
   // the last leaf build's phases (cloud 0), as phases 100 + k
   unsigned long long bs[16];
   CK(leaf_build_stamps(bs));
-  for (int k = 0; k < 9; k++)
+  for (int k = 0; k < 11; k++)
     if (bs[k]) { buf[1 + 2 * n] = 100 + k; buf[2 + 2 * n] = bs[k]; n++; }
+  CK(knn_leaf_stamps(bs));  // the last leaf kNN launch's first group
+  for (int k = 0; k < 8; k++)
+    if (bs[k]) { buf[1 + 2 * n] = 120 + k; buf[2 + 2 * n] = bs[k]; n++; }
+  if (bs[8]) { buf[1 + 2 * n] = 128; buf[2 + 2 * n] = bs[8]; n++; }              // latest group finish of the launch
+  if (bs[9]) { buf[1 + 2 * n] = 129; buf[2 + 2 * n] = bs[0] + bs[9]; n++; }      // enter + duration of the longest group
   *n_stamps = std::min(n, max_stamps);
   if (phase_ns) memcpy(phase_ns, buf + 1, sizeof(unsigned long long) * 2 * std::min(n, max_stamps));
   return APD_OK;

@@ -3,11 +3,37 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "../../include/apdgicp_b200.h"
 #include "apd_grid.cuh"
 
 namespace apd {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a driver call of a microsecond or two in front of every launch of the
+// single-pair path; the attribute only ever has to grow, so remember per (kernel, device) what was granted.
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kern, size_t bytes) {
+  static std::mutex m;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const auto key = std::make_pair(reinterpret_cast<const void*>(kern), dev);
+  {
+    std::lock_guard<std::mutex> lk(m);
+    auto it = granted.find(key);
+    if (it != granted.end() && it->second >= bytes) return cudaSuccess;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(m);
+  size_t& g = granted[key];
+  if (g < bytes) g = bytes;
+  return cudaSuccess;
+}
+
 
 // Coarser levels of the grid pyramid (cell edge x4 and x16): the same points sorted by a coarser cell
 // id. A search that is not finished after a few rings of the fine grid restarts here instead of
@@ -193,7 +219,8 @@ cudaError_t launch_grid_build_fused(const CloudSetView& cs, const int* const cap
 cudaError_t launch_leaf_build(const CloudSetView& cs, int max_n, cudaStream_t stream, LaunchStats* st, bool stamps = false);
 cudaError_t leaf_build_stamps(unsigned long long out[16]);  // profiling aid
 cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out /*nullable*/,
-                                unsigned long long* evals /*nullable: += distance evaluations*/, cudaStream_t stream, LaunchStats* st);
+                                unsigned long long* evals /*nullable: += distance evaluations*/, cudaStream_t stream, LaunchStats* st, bool stamps = false);
+cudaError_t knn_leaf_stamps(unsigned long long out[16]);  // profiling aid
 cudaError_t launch_knn_cov(const CloudSetView& cs, const int4* tiles, int n_tiles, bool staged, size_t smem_bytes, const DeviceParams& prm,
                            int* knn_out /*nullable: total*k, original order rows*/, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_align(const AlignBatch& b, int team_kind, int team_size, int n_teams, bool stage_target, size_t smem_bytes, cudaStream_t stream,

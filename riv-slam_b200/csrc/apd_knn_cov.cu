@@ -317,9 +317,19 @@ __device__ __noinline__ void knn_leaf_exact(LeafView L, float qx, float qy, floa
   for (int j = 0; j < K; j++) out[j] = tk.key[j];
 }
 
+// profiling aid (option "timeline"): %globaltimer stamps of the phases of the first group of CTA 0, appended to apd_get_timeline as phases 120+
+__device__ unsigned long long g_knn_stamps[16];
+__device__ __forceinline__ void kstamp(bool on, int k) {
+  if (on) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_knn_stamps[k] = t;
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kKnnLeafThreads, 1)
-knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out, unsigned long long* __restrict__ evals) {
+knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int method, int* __restrict__ knn_out, unsigned long long* __restrict__ evals, bool stamps) {
   constexpr int M = K + 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
@@ -328,6 +338,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
   const int c = tile.x;
   const int base = cs.pt_off[c];
   const int n = cs.pt_off[c + 1] - base;
+  kstamp(stamps && blockIdx.x == 0 && threadIdx.x == 0, 0);
   LeafView L;
   L.n = n;
   L.nleaf = (n + kLeaf - 1) / kLeaf;
@@ -338,6 +349,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
   L.P = sP;
   L.box = sbox;
   __syncthreads();
+  kstamp(stamps && blockIdx.x == 0 && threadIdx.x == 0, 1);  // staged
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NT = 32;  // every warp owns its own region: entry j of lane l at [j * 32 + l] (conflict-free)
@@ -352,6 +364,9 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
     k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
     if (k0 >= tile.z) break;
     const int g = tile.y + (tile.z - 1 - k0);  // from the end of the curve first (no particular reason beyond determinism)
+    const bool st = stamps && blockIdx.x == 0 && k0 == 0 && lane == 0;
+    unsigned long long t_group = 0;
+    if (stamps && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_group));
     const int q = g * kLeaf + lane;
     const float4 p = leaf_point(L, q);      // padding slots: NaN
     const bool valid = q < n && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
@@ -409,6 +424,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
         // merge when the next scan (up to 32 appends) could overflow a list, after the own leaf, and at the very end
         if (first || __any_sync(0xFFFFFFFFu, l < 0 ? cnt > 0 : cnt > kPendCap - kLeaf)) merge();
         if (l < 0) break;
+        if (first) kstamp(st, 2);  // own leaf scanned and merged
         if (first) {
           float glo[3], ghi[3];
           leaf_group_box(p.x, p.y, p.z, valid, glo, ghi);
@@ -427,6 +443,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       if (evals && lane == 0) atomicAdd(evals, (unsigned long long)n_scanned * (kLeaf * 32));
     }
 
+    kstamp(st, 3);  // search done
     // exact (d2, original index) keys of the K + 4 survivors, sorted; or the bounded exact scan when the packed list cannot
     // prove that it holds the whole K-th bucket
     unsigned long long k64[M];
@@ -458,6 +475,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       for (int j = 0; j < K; j++) k64[j] = fb[j];
     }
     __syncwarp();  // the pending lists are dead from here on: their memory now holds the neighbour slots
+    kstamp(st, 4);  // exact keys sorted
 #pragma unroll
     for (int j = 0; j < K; j++) nbr[j * NT] = (k64[j] >> 32) >= 0x7F800000ull ? (uint16_t)0xFFFFu : (uint16_t)(k64[j] & ((1u << kLeafPosBits) - 1u));
     // (0xFFFF marks "no neighbour": a non-finite query, or fewer than k finite points in the cloud)
@@ -490,7 +508,9 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
         cov.zz = dadd(cov.zz, dmul(dz, dz));
       }
       cov.xx /= inv_div; cov.xy /= inv_div; cov.xz /= inv_div; cov.yy /= inv_div; cov.yz /= inv_div; cov.zz /= inv_div;
+      kstamp(st, 5);  // covariance
       const Sym3 r = regularize(cov, method);
+      kstamp(st, 6);  // regularised
       cs.cov0[base + q] = make_double2(r.xx, r.xy);
       cs.cov1[base + q] = make_double2(r.xz, r.yy);
       cs.cov2[base + q] = make_double2(r.yz, r.zz);
@@ -504,17 +524,24 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       }
     }
     __syncwarp();  // the next group's pending lists reuse the neighbour slots
+    kstamp(st, 7);  // group done
+    if (stamps && lane == 0) {  // latest finish and longest group of the whole launch
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMax(&g_knn_stamps[8], t);
+      atomicMax(&g_knn_stamps[9], t - t_group);
+    }
   }
 }
 
 template <int K>
 cudaError_t launch_k_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out, unsigned long long* evals,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool stamps) {
   const int nleaf = (max_n + kLeaf - 1) / kLeaf;
   const size_t total = (size_t)nleaf * (kLeaf * 16 + 32) + sizeof(unsigned) * kPendCap * kKnnLeafThreads;
-  cudaError_t e = cudaFuncSetAttribute(knn_cov_leaf_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+  cudaError_t e = ensure_dynamic_smem(knn_cov_leaf_kernel<K>, total);
   if (e != cudaSuccess) return e;
-  knn_cov_leaf_kernel<K><<<n_tiles, kKnnLeafThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out, evals);
+  knn_cov_leaf_kernel<K><<<n_tiles, kKnnLeafThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, knn_out, evals, stamps);
   return cudaGetLastError();
 }
 
@@ -525,12 +552,12 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
   if (staged) {
     const size_t idx_off = (smem_bytes + 15) & ~(size_t)15;
     const size_t total = idx_off + sizeof(uint16_t) * K * kKnnThreads;
-    cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+    cudaError_t e = ensure_dynamic_smem(knn_cov_kernel<K, true>, total);
     if (e != cudaSuccess) return e;
     knn_cov_kernel<K, true><<<n_tiles, kKnnThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, (int)idx_off, knn_out);
   } else {
     const size_t total = sizeof(unsigned) * K * kKnnThreads;
-    cudaError_t e = cudaFuncSetAttribute(knn_cov_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+    cudaError_t e = ensure_dynamic_smem(knn_cov_kernel<K, false>, total);
     if (e != cudaSuccess) return e;
     knn_cov_kernel<K, false><<<n_tiles, kKnnThreads, total, stream>>>(cs, tiles, prm.k, prm.regularization, prm.knn_packed, prm.knn_fine_rings, 0, knn_out);
   }
@@ -541,16 +568,23 @@ cudaError_t launch_k(const CloudSetView& cs, const int4* tiles, int n_tiles, boo
 
 size_t knn_leaf_smem_bytes(int max_n) { return (size_t)((max_n + kLeaf - 1) / kLeaf) * (kLeaf * 16 + 32) + sizeof(unsigned) * kPendCap * kKnnLeafThreads; }
 
+cudaError_t knn_leaf_stamps(unsigned long long out[16]) {  // read and reset
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_knn_stamps, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return e;
+  const unsigned long long zero[16] = {0};
+  return cudaMemcpyToSymbol(g_knn_stamps, zero, sizeof(zero));
+}
+
 cudaError_t launch_knn_cov_leaf(const CloudSetView& cs, const int4* tiles, int n_tiles, int max_n, const DeviceParams& prm, int* knn_out,
-                                unsigned long long* evals, cudaStream_t stream, LaunchStats* st) {
+                                unsigned long long* evals, cudaStream_t stream, LaunchStats* st, bool stamps) {
   if (n_tiles == 0) return cudaSuccess;
   if (st) st->launches++;
   const int k = prm.k;
-  if (k <= 8) return launch_k_leaf<8>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
-  if (k <= 10) return launch_k_leaf<10>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
-  if (k <= 15) return launch_k_leaf<15>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
-  if (k <= 20) return launch_k_leaf<20>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
-  if (k <= 32) return launch_k_leaf<32>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream);
+  if (k <= 8) return launch_k_leaf<8>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream, stamps);
+  if (k <= 10) return launch_k_leaf<10>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream, stamps);
+  if (k <= 15) return launch_k_leaf<15>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream, stamps);
+  if (k <= 20) return launch_k_leaf<20>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream, stamps);
+  if (k <= 32) return launch_k_leaf<32>(cs, tiles, n_tiles, max_n, prm, knn_out, evals, stream, stamps);
   return cudaErrorInvalidValue;
 }
 

@@ -32,20 +32,38 @@ names = ["setInputTarget(cached)", "setInputSource(upload)", "grid+knn+cov", "al
 for nm, m, p in zip(names, np.median(r, 0), np.percentile(r, 95, 0)):
     print(f"{nm:26s} p50 {m:7.3f} ms   p95 {p:7.3f} ms")
 print(f"{'total':26s} p50 {np.median(r.sum(1)):7.3f} ms   iterations {reg.nr_iterations()} launches/pair {H.launch_count() / n:.1f}")
+# the caller's flow (no synchronisation between the calls) with the library's CUDA-event timers on: GPU time per kernel and pair
+reg.setOption("kernel_timing", 1)
+H.kernel_times()
+wall = []
+for i in range(n):
+    t0 = time.perf_counter()
+    reg.setInputTarget(clouds[i], cache_key=i + 1)
+    reg.setInputSource(clouds[i + 1], cache_key=i + 2)
+    reg.align(None, want_output=False)
+    reg.getFitnessScore()
+    wall.append(time.perf_counter() - t0)
+k_ms, k_n = H.kernel_times()
+reg.setOption("kernel_timing", 0)
+print("caller's flow: wall p50 %.3f ms; GPU time per pair (CUDA events): %s" % (np.median(wall) * 1e3, "  ".join(f"{k} {1e3 * v / max(k_n[k], 1):.1f} us x{k_n[k] / n:.1f}" for k, v in k_ms.items())))
 # in-kernel timeline of one more align (phase stamps from %globaltimer)
 reg.setOption("timeline", 1)
 reg.setInputTarget(clouds[0], cache_key=1001); reg.setInputSource(clouds[1], cache_key=1002)
 reg.computeCovariances()
 reg.align(None, want_output=False)
 tl = H.timeline()
-names = {0: "enter", 1: "staged", 2: "iter", 3: "corr", 4: "H/b", 5: "LM trial", 6: "fitness", 10: "nn1>", 11: "<nn1", 12: "mahal", 13: "passend", 14: "synced", 20: "acc", 21: "solved", 22: "erracc", 23: "unpacked", 24: "ldlt", 25: "so3exp"}
+names = {0: "enter", 1: "staged", 2: "iter", 3: "corr", 4: "H/b", 5: "LM trial", 6: "fitness", 10: "nn1>", 11: "<nn1", 12: "mahal", 13: "passend", 14: "synced", 20: "acc", 21: "solved", 22: "erracc", 23: "unpacked", 24: "ldlt", 25: "so3exp", 30: "wsum", 31: "part", 32: "barrier"}
 if tl:
     t0 = tl[0][1]
     print("timeline (us):", " ".join(f"{names.get(p, p)}@{(t - t0) / 1e3:.1f}" for p, t in tl if p < 100))
-    bl = [(p, t) for p, t in tl if p >= 100]
+    kl = [(p, t) for p, t in tl if p >= 120]
+    if kl:
+        kn = {120: "enter", 121: "staged", 122: "own leaf", 123: "searched", 124: "exact", 125: "cov", 126: "regularised", 127: "done", 128: "last group done", 129: "longest group (as if started at enter)"}
+        print("leaf kNN, first group (us):", " ".join(f"{kn.get(p, p)}@{(t - kl[0][1]) / 1e3:.1f}" for p, t in kl))
+    bl = [(p, t) for p, t in tl if 100 <= p < 120]
     if bl:
-        bn = {100: "enter", 101: "bbox", 102: "keys", 103: "pass0", 104: "pass1", 105: "pass2", 106: "pass3", 107: "gather", 108: "boxes"}
-        print("leaf build (us):", " ".join(f"{bn.get(p, p)}@{(t - bl[0][1]) / 1e3:.1f}" for p, t in bl))
+        bn = {100: "enter", 101: "bbox", 102: "keys", 103: "pass0", 104: "pass1", 105: "pass2", 106: "pass3", 107: "gather", 108: "boxes", 109: "p0 hist", 110: "p0 ranked"}
+        print("leaf build (us):", " ".join(f"{bn.get(p, p)}@{(t - bl[0][1]) / 1e3:.1f}" for p, t in sorted(bl, key=lambda x: x[1])))
 dc = H.debug_counters()
 for nm, c in (("first pass", dc[:8]), ("seeded passes", dc[8:])):
     if c[0]:
