@@ -186,6 +186,7 @@ int apd_synchronize(apd_handle h);
  *   "fitness_max_range" max_range of the getFitnessScore the batched calls fill into apd_result.fitness (default DBL_MAX)
  *   "fused_build"      1 = small clouds are gridded by one launch for all levels (default), 0 = the multi-kernel pipeline
  *   "knn_fine_rings"   kNN: rings searched on one level of the grid pyramid before restarting on the next coarser one
+ *   "knn_leaf_parts"   leaf-mode kNN: warps that share the 32 queries of one leaf (0 = automatic: 1 for batches, up to 4 for one scan)
  *   "timeline"         1 = the align kernel stamps its phases for apd_get_timeline (profiling aid)
  *   "kernel_timing"    1 = CUDA events around the hot launches (apd_get_kernel_times) */
 int apd_set_option(apd_handle h, const char* name, double value);

@@ -381,7 +381,7 @@ __device__ __forceinline__ void correspondence_pass_leaf(const AlignBatch& B, Al
     float unexplored = 0.f;
     if (prev >= 0) {
       // the previous correspondence bounds the nearest neighbour (capped by the gate: beyond it nothing can match)
-      const float4 t = leaf_point(T.L, prev);
+      const float4 t = leaf_point_gather(T.L, prev);
       bound = fminf(sqdist_rn(qx, qy, qz, t.x, t.y, t.z), B.prm.corr_limit2);
     } else if (prev == -1 && gated) {
       // ANCHOR of a point that had no correspondence: where it was searched and how far every target point is from there at
@@ -447,7 +447,7 @@ __device__ __forceinline__ void fitness_search_leaf(const AlignBatch& B, AlignSh
     const int prev = (seeded && act) ? B.scratch.corr[sbase + i] : -1;
     float bound = inf;
     if (prev >= 0) {  // seeded by the correspondence of the last linearization
-      const float4 t = leaf_point(T.L, prev);
+      const float4 t = leaf_point_gather(T.L, prev);
       bound = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
     }
     LeafTop1 v;
@@ -539,7 +539,7 @@ __device__ __forceinline__ void accumulate_pass(const AlignBatch& B, const doubl
     const int c = B.scratch.corr[sbase + i];
     if (c < 0) continue;
     const float4 a = sspts[i];
-    const float4 bt = LEAF ? leaf_point(T.L, c) : T.G.spts[c];
+    const float4 bt = LEAF ? leaf_point_gather(T.L, c) : T.G.spts[c];
     const double2 m0 = B.scratch.m0[sbase + i], m1 = B.scratch.m1[sbase + i], m2 = B.scratch.m2[sbase + i];
     const double Mxx = m0.x, Mxy = m0.y, Mxz = m1.x, Myy = m1.y, Myz = m2.x, Mzz = m2.y;
     const double ax = (double)a.x, ay = (double)a.y, az = (double)a.z;

@@ -182,6 +182,7 @@ struct apd_context {
   int no_smem_build = 0;
   double fitness_max_range = DBL_MAX;  // getFitnessScore(max_range) used by the batched calls
   int knn_fine_rings = kFineRingsKnn;
+  int knn_leaf_parts = 0;  // 0 = automatic; 1, 2, 4, 8: warps per leaf in the leaf kNN kernel (experiments)
   int timeline_opt = 0;  // profiling aid: the align kernel stamps its phases (apd_get_timeline)
   // kernel timing (option "kernel_timing"): CUDA events around the hot launches, on the stream they are launched on
   int kernel_timing = 0;
@@ -328,7 +329,7 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs, bool force_grid = false) {
   // (staged target + its static state) and the kNN kernel (staged cloud + per-lane pending lists)
   const size_t stage_bytes = (size_t)((cs->max_n + kLeaf - 1) / kLeaf) * (kLeaf * 16 + 32);
   const bool leaf = nc > 0 && !force_grid && !h->force_unstaged && cs->max_n <= kLeafMaxPoints && stage_bytes + align_static_smem() + 1024 <= h->smem_optin &&
-                    knn_leaf_smem_bytes(cs->max_n) + 1024 <= h->smem_optin;
+                    knn_leaf_smem_bytes(cs->max_n) + 14336 <= h->smem_optin;  // + the kNN kernel's static query slots (12.8 KB)
   cs->staged = leaf;
   cs->staged_smem = leaf ? ((stage_bytes + 15) & ~(size_t)15) : 0;
   for (int c = 0; c < nc; c++) {
@@ -380,9 +381,13 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs, bool force_grid = false) {
   const long long target_ctas = h->sm_count;  // one CTA per SM fits (shared memory): a single wave
   if (leaf) {
     const long long per = nc >= target_ctas ? (1ll << 30) : std::max<long long>((cs->total_leaves + target_ctas - 1) / std::max<long long>(target_ctas, 1), 1);
+    // fewer leaves than warps (a single scan): every leaf's queries are cut into `sub` parts, one warp each (knn_cov_leaf_kernel)
+    int sub = 1;
+    while (sub < 4 && cs->total_leaves * sub * 2 <= (long long)h->sm_count * 20) sub *= 2;  // measured on one 5000-point scan: 79 / 73 / 68 / 67 us for 1 / 2 / 4 / 8 parts
+    if (h->knn_leaf_parts > 0) sub = h->knn_leaf_parts;
     for (int c = 0; c < nc; c++) {
       const int nl = leaf_off[c + 1] - leaf_off[c];
-      for (long long s = 0; s < nl; s += per) tk.push_back(int4{c, (int)s, (int)std::min<long long>(per, nl - s), 0});
+      for (long long s = 0; s < nl; s += per) tk.push_back(int4{c, (int)s, (int)std::min<long long>(per, nl - s), sub});
     }
   } else {
     long long tile_q = nc >= target_ctas ? (long long)cs->max_n : std::max<long long>((cs->total + target_ctas - 1) / std::max<long long>(target_ctas, 1), 16);
@@ -693,6 +698,15 @@ constexpr size_t kOB_result = 0, kOB_counters = 128, kOB_tcount = 160, kOB_fh = 
 constexpr int kOB_fast_rows = 40;  // trace rows fetched together with the header (a registration rarely has more LM trials)
 static_assert(sizeof(apd_result) <= kOB_counters, "result record must fit its slot");
 
+// the device block and its pinned landing area for a single-pair call (AlignCall::block)
+int single_block(apd_handle h, AlignCall* c) {
+  c->block_trace_rows = std::max(1, std::min(4096, h->prm.max_iterations * std::max(1, h->prm.lm_max_iterations)));
+  CK(h->oneblock.reserve(kOB_trace + sizeof(double) * 8 * (size_t)c->block_trace_rows));
+  c->block = h->oneblock.as<unsigned char>();
+  if (!h->down_host) CK(cudaHostAlloc(reinterpret_cast<void**>(&h->down_host), kOB_trace + sizeof(double) * 8 * kOB_fast_rows, cudaHostAllocDefault));
+  return APD_OK;
+}
+
 // Enqueue the align kernel for a batch; results land in h->results (device).
 int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, TeamPlan* used_plan = nullptr) {
   // mode 2 (fitness score only) needs the grids but no covariances
@@ -959,6 +973,11 @@ int apd_set_option(apd_handle h, const char* name, double value) {
   else if (n == "fitness_max_range") h->fitness_max_range = value;
   else if (n == "knn_fine_rings") h->knn_fine_rings = std::max(0, (int)value);
   else if (n == "timeline") h->timeline_opt = value != 0;
+  else if (n == "knn_leaf_parts") {
+    const int v = (int)value;
+    if (v != 0 && v != 1 && v != 2 && v != 4 && v != 8) return fail(h, APD_ERR_INVALID, "knn_leaf_parts must be 0, 1, 2, 4 or 8");
+    h->knn_leaf_parts = v;
+  }
   else if (n == "kernel_timing") h->kernel_timing = value != 0;
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
@@ -1048,11 +1067,9 @@ int apd_align(apd_handle h, const float guess[16], apd_result* out) {
   // One device block, one memset, one copy into pinned memory, one synchronisation. (Five separate copies into pageable host
   // variables - record, trace count, Hessian, counters, trace - each blocked the host for a driver round trip: ~40 us of a
   // 165 us call around a 90 us kernel.)
-  c.block_trace_rows = std::max(1, std::min(4096, h->prm.max_iterations * std::max(1, h->prm.lm_max_iterations)));
-  CK(h->oneblock.reserve(kOB_trace + sizeof(double) * 8 * (size_t)c.block_trace_rows));
-  c.block = h->oneblock.as<unsigned char>();
+  rc = single_block(h, &c);
+  if (rc) return rc;
   const size_t fast_bytes = kOB_trace + sizeof(double) * 8 * (size_t)std::min(c.block_trace_rows, kOB_fast_rows);
-  if (!h->down_host) CK(cudaHostAlloc(reinterpret_cast<void**>(&h->down_host), kOB_trace + sizeof(double) * 8 * kOB_fast_rows, cudaHostAllocDefault));
   AlignBatch b;
   rc = run_align(h, c, &b);
   if (rc) return rc;
@@ -1258,16 +1275,17 @@ static int linearize_common(apd_handle h, const float* pose_f, const double* pos
   c.guesses64 = pose_d;
   c.n_pairs = 1;
   c.mode = 1;
+  // record, H and b in one device block, fetched by one copy into pinned memory (as apd_align)
+  rc = single_block(h, &c);
+  if (rc) return rc;
   rc = run_align(h, c);
   if (rc) return rc;
-  apd_result r;
-  double Hh[36], bh[6];
-  CK(cudaMemcpyAsync(&r, h->results.p, sizeof(r), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(Hh, h->fh.p, sizeof(Hh), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(bh, h->lin_b.p, sizeof(bh), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->down_host, c.block, kOB_trace, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (H) memcpy(H, Hh, sizeof(Hh));
-  if (b) memcpy(b, bh, sizeof(bh));
+  apd_result r;
+  memcpy(&r, h->down_host + kOB_result, sizeof(r));
+  if (H) memcpy(H, h->down_host + kOB_fh, sizeof(double) * 36);
+  if (b) memcpy(b, h->down_host + kOB_linb, sizeof(double) * 6);
   if (error) *error = r.error;
   h->last_lin_valid = true;
   h->fit_valid = false;

@@ -259,7 +259,11 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
 // (d2 bits, original index) of its entries are recomputed from the staged points and sorted; a crowded bucket (lattice
 // data, duplicates) falls back to a bounded exact scan. Either way the result is the exact (d2, index)-ordered top-k.
 constexpr int kKnnLeafThreads = 640;
-constexpr int kPendCap = 40;  // pending keys per lane; a leaf scan appends at most 32
+constexpr int kKnnTransposeMax = 10;  // a leaf that at most this many of the warp's queries can reach is scanned transposed (one turn per query)
+#ifndef APD_PEND_CAP
+#define APD_PEND_CAP 40
+#endif
+constexpr int kPendCap = APD_PEND_CAP;  // pending keys per lane; a leaf scan appends at most 32
 
 template <int K, int M>
 struct LeafTopK {
@@ -285,7 +289,7 @@ __device__ __forceinline__ unsigned leaf_pack_key(float d2, int pos) { return ((
 
 // exact 64-bit key of a staged slot: (d2 bits) << 32 | tag, tag = original index << 13 | slot (apd_leaf.cuh)
 __device__ __forceinline__ unsigned long long leaf_exact_key(const LeafView& L, int pos, float qx, float qy, float qz) {
-  const float4 t = leaf_point(L, pos);
+  const float4 t = leaf_point_gather(L, pos);
   const float d2 = sqdist_rn(qx, qy, qz, t.x, t.y, t.z);
   return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)__float_as_uint(t.w);
 }
@@ -333,7 +337,9 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
   constexpr int M = K + 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
-  const int4 tile = tiles[blockIdx.x];  // (cloud, first leaf, leaves, -)
+  __shared__ float4 s_q[kKnnLeafThreads];    // transposed scans: every lane's query (x, y, z, gate) ...
+  __shared__ unsigned s_qc[kKnnLeafThreads];  // ... and the fill of its pending list
+  const int4 tile = tiles[blockIdx.x];  // (cloud, first leaf, leaves, parts per leaf)
   if (threadIdx.x == 0) s_next = 0;
   const int c = tile.x;
   const int base = cs.pt_off[c];
@@ -362,14 +368,20 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
     int k0 = 0;
     if (lane == 0) k0 = atomicAdd(&s_next, 1);
     k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
-    if (k0 >= tile.z) break;
-    const int g = tile.y + (tile.z - 1 - k0);  // from the end of the curve first (no particular reason beyond determinism)
+    // A launch with fewer leaves than the GPU has warps (one scan: 157 leaves for 2960 warps) cuts every leaf's 32 queries into
+    // `sub` parts of 32 / sub lanes, one warp each. The instruction count of a search does not depend on how many lanes take part,
+    // but the union of leaves a warp must scan does: the longest group of a radar scan (32 clutter points spread over tens of
+    // metres) took 76 us against 24 us for a typical one, and the kernel lasts as long as its longest warp.
+    const int sub = tile.w > 1 ? tile.w : 1, qpw = kLeaf / sub;
+    if (k0 >= tile.z * sub) break;
+    const int g = tile.y + (tile.z - 1 - k0 / sub);  // from the end of the curve first (no particular reason beyond determinism)
     const bool st = stamps && blockIdx.x == 0 && k0 == 0 && lane == 0;
     unsigned long long t_group = 0;
     if (stamps && lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_group));
-    const int q = g * kLeaf + lane;
+    const bool mine = lane < qpw;           // lanes beyond the part's queries idle along (they repeat its first query, invalid)
+    const int q = g * kLeaf + (k0 % sub) * qpw + (mine ? lane : 0);
     const float4 p = leaf_point(L, q);      // padding slots: NaN
-    const bool valid = q < n && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    const bool valid = mine && q < n && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
     const f32x2_t qx2 = f2_pack(p.x, p.x), qy2 = f2_pack(p.y, p.y), qz2 = f2_pack(p.z, p.z);
 
     LeafTopK<K, M> tk;
@@ -412,15 +424,58 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       }
     };
 
+    // The same leaf TRANSPOSED, for a leaf only a few of the warp's queries can reach (bit mask `need`): every lane holds one
+    // CANDIDATE, the queries take turns (two per trip: independent chains). A turn costs ~20 instructions against ~250 for the
+    // broadcast scan, and only the queries that need the leaf pay. The lanes that pass a query's gate append to THAT query's
+    // pending list (any lane may write any list: shared memory), at consecutive slots by their rank in the vote.
+    float4* qs = s_q + warp * 32;
+    unsigned* qc = s_qc + warp * 32;
+    unsigned* lst_w = s_list + warp * 32 * kPendCap;
+    auto scan_transposed = [&](int leaf, unsigned need) {
+      const int cpos = leaf * kLeaf + lane;
+      const float4 c = leaf_point(L, cpos);   // NaN coordinates in padding slots and for non-finite points: never pass
+      qs[lane] = make_float4(p.x, p.y, p.z, gate);
+      qc[lane] = (unsigned)cnt;
+      __syncwarp();
+      const unsigned lt = (1u << lane) - 1u;
+      while (need) {
+        const int q0 = __ffs(need) - 1;
+        need &= need - 1;
+        const bool two = need != 0u;
+        const int q1 = two ? __ffs(need) - 1 : q0;
+        need &= need - 1;
+        const float4 Q0 = qs[q0], Q1 = qs[q1];
+        const float d0 = sqdist_rn(Q0.x, Q0.y, Q0.z, c.x, c.y, c.z);
+        const float d1 = sqdist_rn(Q1.x, Q1.y, Q1.z, c.x, c.y, c.z);
+        const bool p0 = d0 <= Q0.w, p1 = two && d1 <= Q1.w;
+        const unsigned m0 = __ballot_sync(0xFFFFFFFFu, p0), m1 = __ballot_sync(0xFFFFFFFFu, p1);
+        if (m0) {
+          const unsigned c0 = qc[q0];
+          if (p0) lst_w[(c0 + __popc(m0 & lt)) * NT + q0] = leaf_pack_key(d0, cpos);
+          if (lane == q0) qc[q0] = c0 + __popc(m0);
+        }
+        if (m1) {
+          const unsigned c1 = qc[q1];
+          if (p1) lst_w[(c1 + __popc(m1 & lt)) * NT + q1] = leaf_pack_key(d1, cpos);
+          if (lane == q1) qc[q1] = c1 + __popc(m1);
+        }
+      }
+      __syncwarp();
+      cnt = (int)qc[lane];
+    };
+
     if (__any_sync(0xFFFFFFFFu, valid)) {
       // The query's own leaf first (it fills the list: 32 points >= K, and gives every lane a first bound), then the other
-      // leaves nearest first. ONE scan site and ONE merge site: the two are the bulk of the loop's instruction footprint.
+      // leaves nearest first. ONE broadcast scan site and ONE merge site: the two are the bulk of the loop's instruction footprint.
       LeafSchedule S;
       int l = g;
       bool first = true;
-      unsigned n_scanned = 0;
+      unsigned n_evals = 0, need = 0xFFFFFFFFu;
       for (;;) {
-        if (l >= 0) { scan(l); n_scanned++; }
+        if (l >= 0) {
+          if (__popc(need) > kKnnTransposeMax) { scan(l); n_evals += kLeaf * 32; }
+          else { n_evals += __popc(need) * 32; scan_transposed(l, need); }
+        }
         // merge when the next scan (up to 32 appends) could overflow a list, after the own leaf, and at the very end
         if (first || __any_sync(0xFFFFFFFFu, l < 0 ? cnt > 0 : cnt > kPendCap - kLeaf)) merge();
         if (l < 0) break;
@@ -436,11 +491,12 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
           l = S.next(G);
           if (l < 0) break;
           const float dl = leaf_point_box2(p.x, p.y, p.z, L.box[2 * l], L.box[2 * l + 1]);
-          if (__any_sync(0xFFFFFFFFu, valid && dl <= gate)) break;
+          need = __ballot_sync(0xFFFFFFFFu, valid && dl <= gate);
+          if (need) break;
         }
       }
-      // distance evaluations executed by this group: every lane computes every candidate of every scanned leaf (bench.py's figure)
-      if (evals && lane == 0) atomicAdd(evals, (unsigned long long)n_scanned * (kLeaf * 32));
+      // distance evaluations executed by this group (bench.py's figure): 32 lanes x 32 candidates per broadcast scan, 32 per turn
+      if (evals && lane == 0) atomicAdd(evals, (unsigned long long)n_evals);
     }
 
     kstamp(st, 3);  // search done
@@ -480,14 +536,14 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
     for (int j = 0; j < K; j++) nbr[j * NT] = (k64[j] >> 32) >= 0x7F800000ull ? (uint16_t)0xFFFFu : (uint16_t)(k64[j] & ((1u << kLeafPosBits) - 1u));
     // (0xFFFF marks "no neighbour": a non-finite query, or fewer than k finite points in the cloud)
 
-    if (q < n) {
+    if (mine && q < n) {
       // neighbours -> mean -> covariance / k   (fast_apdgicp_impl.hpp:318-324), in (d2, index) order from shared memory
       double mx = 0.0, my = 0.0, mz = 0.0;
 #pragma unroll 4
       for (int j = 0; j < k; j++) {
         int s = nbr[j * NT];
         if (s == 0xFFFF) s = q;
-        const float4 nb = leaf_point(L, s);
+        const float4 nb = leaf_point_gather(L, s);
         mx = dadd(mx, (double)nb.x);
         my = dadd(my, (double)nb.y);
         mz = dadd(mz, (double)nb.z);
@@ -498,7 +554,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
       for (int j = 0; j < k; j++) {
         int s = nbr[j * NT];
         if (s == 0xFFFF) s = q;
-        const float4 nb = leaf_point(L, s);
+        const float4 nb = leaf_point_gather(L, s);
         const double dx = dsub((double)nb.x, mx), dy = dsub((double)nb.y, my), dz = dsub((double)nb.z, mz);
         cov.xx = dadd(cov.xx, dmul(dx, dx));
         cov.xy = dadd(cov.xy, dmul(dx, dy));
@@ -519,7 +575,7 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
 #pragma unroll 1
         for (int j = 0; j < k; j++) {
           const int s = nbr[j * NT];
-          row[j] = s == 0xFFFF ? -1 : (int)leaf_tag_index(leaf_point(L, s).w);
+          row[j] = s == 0xFFFF ? -1 : (int)leaf_tag_index(leaf_point_gather(L, s).w);
         }
       }
     }

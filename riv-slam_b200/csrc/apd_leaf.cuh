@@ -115,6 +115,14 @@ __device__ __forceinline__ float4 leaf_point(const LeafView& L, int pos) {
   return (pos & 1) ? make_float4(-A.y, -A.w, -B.y, B.w) : make_float4(-A.x, -A.z, -B.x, B.z);
 }
 __device__ __forceinline__ unsigned leaf_tag_index(float w) { return __float_as_uint(w) >> kLeafPosBits; }
+// The same point for a GATHER (every lane a different, unrelated slot: neighbour lists, seeds, correspondences): four scalar
+// loads of exactly the words wanted instead of two 16-byte loads of which half is dropped by selects - fewer instructions, and
+// about half the shared-memory wavefronts (a random 16-byte access pattern serialises into 8-10 wavefronts per load; the
+// compiler drops the tag load where only the coordinates are used). Slots in order (pos = base + lane) keep leaf_point.
+__device__ __forceinline__ float4 leaf_point_gather(const LeafView& L, int pos) {
+  const float* w = reinterpret_cast<const float*>(L.P) + ((pos >> 1) << 3) + (pos & 1);
+  return make_float4(-w[0], -w[2], -w[4], w[6]);
+}
 
 // squared distance from a point to a box (0 inside), as a lower bound of the distance to every point of the box;
 // scaled down so that float rounding of this bound itself can never exclude a candidate (same 0.99999 as the grid search)
