@@ -1578,6 +1578,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->kernel_timing = h->kernel_timing;
   x->fitness_max_range = h->fitness_max_range;
   x->knn_fine_rings = h->knn_fine_rings;
+  x->knn_leaf_parts = h->knn_leaf_parts;
   *out = x;
   return APD_OK;
 }
@@ -1622,8 +1623,12 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
   } drain{slots};
   // the first chunk's upload is the one nothing can hide: keep it to a single wave of teams when the batch is large
   const int first_pairs = (slots[1].h && n_pairs > 3 * h->sm_count) ? h->sm_count : kChunkPairs;  // measured: 74 / 148 / 256 pairs -> 12.85 / 12.31 / 12.54 ms per 1000 pairs
+  // A chunk of np odometry pairs holds np + 1 scans, and the kNN kernel takes whole scans per CTA, one CTA per SM: 297 scans are
+  // three waves where 296 are two (a 1000-pair call ran 2 + 3 + 3 + 2 = 10 waves of kNN instead of 7, +1.4 ms). Odometry chunks
+  // therefore hold one pair less than a multiple of the SM count.
+  const int odo = odometry && n_pairs > kChunkPairs ? 1 : 0;
   for (int p0 = 0, np = 0; p0 < n_pairs; p0 += np, chunk++) {
-    np = std::min(chunk == 0 ? first_pairs : kChunkPairs, n_pairs - p0);
+    np = std::min((chunk == 0 ? first_pairs : kChunkPairs) - odo, n_pairs - p0);
     ChunkSlot& s = slots[slots[1].h ? (chunk & 1) : 0];
     int rc = retire(h, s, &lin, &err);
     if (rc) return rc;

@@ -193,3 +193,33 @@ def test_dropin_matches_python_path_and_oracle(tmp_path):
     assert any(l[:2] == ["cleared", "converged"] for l in lines)
     assert ["notarget", "converged", "0"] in lines
     assert "No input target dataset" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_class_single_pair_latency(tmp_path):
+    """Per-call latency THROUGH THE C++ CLASS (setInputTarget cached + setInputSource + align + lastFitnessScore on 5000-point scans),
+    the figure INTEGRATION.md quotes beside the ctypes one. The shim's kd-tree has no build step, so what a ROS machine adds on
+    top (pcl::KdTreeFLANN build in initCompute, the CPU walk of getFitnessScore) is quoted there from the reference's own nanoflann."""
+    from riv_slam_b200 import datagen
+    exe = _build()
+    scans, _ = datagen.make_drive(2, 0, 6, 5000, workers=2)
+    path = tmp_path / "scans5k.bin"
+    with open(path, "wb") as f:
+        f.write(np.int32(len(scans)).tobytes())
+        for s in scans:
+            blk = np.zeros((s.shape[0], 8), dtype=np.float32)
+            blk[:, :3] = s[:, :3]
+            blk[:, 3] = 1.0
+            blk[:, 4] = s[:, 3]
+            f.write(np.int32(s.shape[0]).tobytes())
+            f.write(blk.tobytes())
+    r = subprocess.run([exe, str(path), "--latency"], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stderr
+    line = next(l for l in r.stdout.splitlines() if l.startswith("latency_cpp_p50_ms"))
+    p50 = float(line.split()[1])
+    print(line)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "cpp_class_latency.txt"), "w") as f:
+            f.write(line + "\n")
+    assert 0.0 < p50 < 1.0, line   # round 2: 0.25-0.3 ms; a regression to the pageable-copy path would show as > 0.35
