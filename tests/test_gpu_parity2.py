@@ -394,3 +394,34 @@ def test_protected_hooks_and_inlier_count(small_pair):
     g2.setInputSource(src); g2.setInputTarget(tgt)
     with pytest.raises(Exception):
         g2.compute_error(x)                 # no linearize yet: refused, not garbage
+
+
+@pytest.mark.gpu
+def test_leaf_knn_warp_parts_give_identical_results():
+    """knn_cov_leaf_kernel cuts the 32 queries of a leaf into 1 / 2 / 4 / 8 warp parts for a single scan (fewer leaves than warps).
+    The split only changes which warp serves a query, and with it whether a leaf is scanned broadcast or transposed: neighbour
+    lists and covariances must come out bit-identical, and equal to the oracle's."""
+    from oracle.oracle import Oracle
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import FastAPDGICP
+    scans, _ = datagen.make_sequence(2, 3, n_scans=1, n_points=3000)
+    cloud = np.ascontiguousarray(scans[0][:, :3])
+    o = Oracle(**LAUNCH_PARAMS)
+    o.set_source(cloud); o.set_target(cloud)
+    o.compute_covariances()
+    ref_knn = o.knn(0)
+    ref_cov = o.covariances(0)
+    got = {}
+    for parts in (1, 2, 4, 8):
+        reg = FastAPDGICP(0)
+        reg.handle().set_params(**LAUNCH_PARAMS)
+        reg.setOption("knn_leaf_parts", parts)
+        reg.setInputSource(cloud, cache_key=10 + parts)
+        reg.setInputTarget(cloud, cache_key=10 + parts)
+        reg.computeCovariances()
+        got[parts] = (reg.getKnn(0), reg.getSourceCovariances())
+        assert np.array_equal(got[parts][0], ref_knn), parts
+        assert np.abs(got[parts][1][:, :3, :3] - ref_cov[:, :3, :3]).max() <= 1e-9
+    for parts in (2, 4, 8):
+        assert np.array_equal(got[parts][0], got[1][0])
+        assert np.array_equal(got[parts][1], got[1][1])   # bit-identical covariances
