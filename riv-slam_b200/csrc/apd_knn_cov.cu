@@ -258,7 +258,10 @@ knn_cov_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int metho
 // completeness (bucket of entry K+3 strictly beyond the bucket of entry K-1), then the exact 64-bit keys
 // (d2 bits, original index) of its entries are recomputed from the staged points and sorted; a crowded bucket (lattice
 // data, duplicates) falls back to a bounded exact scan. Either way the result is the exact (d2, index)-ordered top-k.
-constexpr int kKnnLeafThreads = 640;
+#ifndef APD_KNN_LEAF_THREADS
+#define APD_KNN_LEAF_THREADS 640
+#endif
+constexpr int kKnnLeafThreads = APD_KNN_LEAF_THREADS;
 constexpr int kKnnTransposeMax = 10;  // a leaf that at most this many of the warp's queries can reach is scanned transposed (one turn per query)
 #ifndef APD_PEND_CAP
 #define APD_PEND_CAP 40
