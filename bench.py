@@ -101,6 +101,11 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)   # its teardown (NVML handle, driver bookkeeping) must not overlap the latency loops that follow:
+        except Exception:               # a lingering nvidia-smi stalled single CUDA calls by tens of ms in one run out of three
+            pass
+        time.sleep(0.25)
         rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -474,6 +479,7 @@ def main():
     # ---- single-pair latency through the reference-shaped object (setInputTarget/Source + align + fitness) ----
     p50 = None
     seq_rate = None
+    seq_rate_mean = None
     if rank == 0 and args.latency_pairs > 0:
         lat = []
         reg = F.FastAPDGICP(local_rank)
@@ -502,14 +508,18 @@ def main():
             # truly sequential odometry (scan_matching_odometry_nodelet.cpp:461-468): the guess of pair t is the result of pair t-1,
             # so pairs cannot be batched; one stream of dependent registrations
             g = np.eye(4, dtype=np.float32)
-            ta = time.perf_counter()
+            seq = []
             for i in range(n_lat):
+                ta = time.perf_counter()
                 reg.setInputTarget(clouds[i], cache_key=i + 1)
                 reg.setInputSource(clouds[i + 1], cache_key=i + 2)
                 reg.align(g, want_output=False)
                 reg.getFitnessScore()
                 g = reg.getFinalTransformation()
-            seq_rate = n_lat / (time.perf_counter() - ta)
+                seq.append(time.perf_counter() - ta)
+            # rate of the dependent stream from the median registration (one host hiccup of 30 ms in a 10 ms loop would otherwise set the figure)
+            seq_rate = 1.0 / float(np.median(seq))
+            seq_rate_mean = n_lat / float(np.sum(seq))
 
     if rank != 0:
         if world > 1:
@@ -560,7 +570,7 @@ def main():
                    "l2": f"inputs larger than L2 (per-step working set ~{n_pts_step * 100 / 1e9:.1f} GB per GPU)", "parallelism": f"pair-sharded x{world}",
                    "segments": "same on every rank" if args.same_workload else "one drive segment per rank"},
         "p50_align_latency_ms": p50,
-        "sequential_chained_reg_per_s": seq_rate,
+        "sequential_chained_reg_per_s": seq_rate, "sequential_chained_mean_reg_per_s": seq_rate_mean,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_np.nbytes), "d2h_bytes_per_step": int(P * 96),
                 "ms_per_step": 1e3 * e_m / args.steps, "wall_ms_per_step": 1e3 * allmax(e_wall) / args.steps if world == 1 else 1e3 * e_m / args.steps},
         "gpu_launches": int(launches),
