@@ -454,11 +454,13 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
         const unsigned m0 = __ballot_sync(0xFFFFFFFFu, p0), m1 = __ballot_sync(0xFFFFFFFFu, p1);
         if (m0) {
           const unsigned c0 = qc[q0];
+          __syncwarp();  // every lane holds the fill before the owner advances it (write after read)
           if (p0) lst_w[(c0 + __popc(m0 & lt)) * NT + q0] = leaf_pack_key(d0, cpos);
           if (lane == q0) qc[q0] = c0 + __popc(m0);
         }
         if (m1) {
           const unsigned c1 = qc[q1];
+          __syncwarp();
           if (p1) lst_w[(c1 + __popc(m1 & lt)) * NT + q1] = leaf_pack_key(d1, cpos);
           if (lane == q1) qc[q1] = c1 + __popc(m1);
         }

@@ -248,6 +248,7 @@ __device__ __forceinline__ void leaf_scan_top1_transposed(const LeafView& L, int
     const unsigned m1 = __reduce_min_sync(0xFFFFFFFFu, d1);
     const bool h0 = m0 <= __float_as_uint(Q0.w), h1 = q1 != q0 && m1 <= __float_as_uint(Q1.w);  // warp-uniform
     if (h0 || h1) {
+      __syncwarp();  // every lane has read the two slots before an owner updates its bound (write after read)
       // lowest tag (= lowest original index) among the candidates at that distance, then the 64-bit (d2, index) comparison
       if (h0) {
         const unsigned wtag = __reduce_min_sync(0xFFFFFFFFu, d0 == m0 ? ctag : 0xFFFFFFFFu);
@@ -262,6 +263,7 @@ __device__ __forceinline__ void leaf_scan_top1_transposed(const LeafView& L, int
       __syncwarp();
     }
   }
+  __syncwarp();  // the slots are rewritten by their owners after a broadcast scan: no lane may still be reading them here
 }
 
 // Exact nearest neighbour of every lane's query among the staged target, inside the bound v was initialised with

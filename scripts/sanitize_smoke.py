@@ -20,6 +20,17 @@ for team in (0, 1, 2, 4):
         r.align(want_output=True)
         r.getFitnessScore(1.0); r.getKnn(0); r.getCorrespondences(); r.evaluateCost(np.eye(4))
         print("team", team, "unstaged", unstaged, r.hasConverged(), r.nr_iterations())
+# leaf kNN with its queries cut into 1 / 4 / 8 warp parts (transposed scans write into other lanes' pending lists), and the
+# profiling stamps of the three kernels
+for parts in (1, 4, 8):
+    r = F.FastAPDGICP(0)
+    r.handle().set_params(**LAUNCH_PARAMS)
+    r.setOption("knn_leaf_parts", parts)
+    r.setOption("timeline", 1 if parts == 4 else 0)
+    r.setInputTarget(tgt, cache_key=100 + parts); r.setInputSource(src, cache_key=200 + parts)
+    r.computeCovariances()
+    r.align(want_output=False)
+    print("parts", parts, r.hasConverged(), len(r.handle().timeline()))
 H = F.Handle(0)
 H.set_params(**LAUNCH_PARAMS)
 clouds = [src[:300], src, tgt[:500], src[:0], tgt]
