@@ -1,14 +1,18 @@
 // TEST INFRASTRUCTURE — CPU oracle for the FastAPDGICP hot path. Not part of the product.
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
 //
-// PARITY: pinned for the nearest-neighbour search, UNPINNED beyond it. The reference holds no golden vector,
-// known-answer test or fixture for FastAPDGICP (its only test, fast_apdgicp/src/test/gicp_test.cpp:99-128, never
-// builds it and its data/ directory is absent), and FastAPDGICP cannot be compiled here (PCL, Eigen, FLANN, Boost
-// are not installed). The exact kd-tree the reference vendors (radar_graph_slam/include/scan_context/nanoflann.hpp,
-// nanoflann 1.3.2: FLANN's L2_Simple float metric) does compile from the reference tree (oracle/_ref, `make ref`,
-// oracle/ref_nanoflann.cpp) and pins the kNN / 1-NN results of this file (tests/test_reference_knn.py,
-// tests/golden/knn_nanoflann_v1.npz). Covariances, APD model, Mahalanobis, H/b and the LM loop are a restatement
-// written from the cited lines, cross-checked by an independent numpy/LAPACK twin (oracle/pyref.py) only.
+// PARITY: pinned to the reference's own sources. The reference holds no golden vector, known-answer test or fixture for
+// FastAPDGICP (its only test, fast_apdgicp/src/test/gicp_test.cpp:99-128, never builds it and its data/ directory is
+// absent), and PCL, Eigen, FLANN and Boost are not installed. What compiles from the reference tree (`make ref`, outputs in
+// oracle/_ref): (1) the exact kd-tree it vendors (radar_graph_slam/include/scan_context/nanoflann.hpp, nanoflann 1.3.2:
+// FLANN's L2_Simple float metric; oracle/ref_nanoflann.cpp), which pins the kNN / 1-NN results of this file
+// (tests/test_reference_knn.py, tests/golden/knn_nanoflann_v1.npz); (2) FastAPDGICP itself - fast_apdgicp.hpp,
+// lsq_registration.hpp, their impl/ files, so3.hpp - UNMODIFIED, over stand-in Eigen / PCL / Boost headers
+// (oracle/ref_apdgicp.cpp, oracle/ref_standins/), which pins covariances, APD model, Mahalanobis, H / b, compute_error and
+// the whole LM loop of this file to the reference's text at 1e-9 (tests/test_reference_apdgicp.py) and generates
+// tests/golden/apd_ref_golden_v1.npz for the GPU box. The third-party arithmetic under that text (Eigen's product, inverse,
+// JacobiSVD and LDLT kernels) remains a restatement of the published algorithms on both sides; oracle/pyref.py
+// (numpy / LAPACK) is an independent third opinion.
 //
 // Restates, line by line (paths relative to /root/reference/fast_apdgicp/include/fast_gicp):
 //   FastAPDGICP            gicp/impl/fast_apdgicp_impl.hpp:14-363   (APD_I)

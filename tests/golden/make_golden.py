@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Generates tests/golden/apd_golden_v1.npz from the CPU oracle (oracle/liboracle.so).
 
-PARITY UNPINNED at the reference level: the reference holds no golden vector for FastAPDGICP and
-cannot be built or imported here, so these vectors pin the ORACLE — they guard it
-against drift and give the GPU tests a committed target that does not depend on rebuilding it.
+These vectors pin the ORACLE - they guard it against drift and give the GPU tests a committed target that does
+not depend on rebuilding it. The reference holds no golden vector for FastAPDGICP; the vectors made
+by the reference's own compiled sources are tests/golden/apd_ref_golden_v1.npz (make_ref_golden.py), and
+tests/test_reference_apdgicp.py holds the oracle to those sources directly.
 Inputs come from the deterministic generator (riv_slam_b200.datagen, seed 20260000+1000*config+index).
 
     python tests/golden/make_golden.py        # rewrites the .npz next to this script

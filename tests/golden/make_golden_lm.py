@@ -2,8 +2,9 @@
 """Generates tests/golden/apd_golden_lm_v1.npz from the CPU oracle: LM traces of the cases in
 tests/lm_cases.py (rejected trials, rejected-but-converged, "lm not converged!!", non-default initial lambda).
 
-PARITY UNPINNED at the reference level (the reference holds no vectors for FastAPDGICP and cannot be built
-here): these vectors pin the ORACLE's walk through lsq_registration_impl.hpp:127-173.
+These vectors pin the ORACLE's walk through lsq_registration_impl.hpp:127-173; tests/test_reference_apdgicp.py::test_lm_branches
+runs the same cases through the reference's own compiled sources (oracle/ref_apdgicp.cpp) and checks these vectors against them,
+and tests/golden/apd_ref_golden_v1.npz holds the reference-made twins (lm_* keys).
 
     python tests/golden/make_golden_lm.py
 """
