@@ -191,6 +191,9 @@ int ref_apd_align(void* h, const float* guess16, int debug, float* T16, int* con
   return 0;
 }
 
+// pcl::Registration::getFitnessScore (the base class's own 1-NN pass over tree_, which align()'s initCompute built)
+double ref_apd_fitness(void* h, double max_range) { return static_cast<RefAPD*>(h)->getFitnessScore(max_range); }
+
 int ref_apd_get_debug_text(void* h, char* buf, int cap) {
   const std::string& s = static_cast<RefAPD*>(h)->debug_text;
   if (buf && cap > 0) { const int n = (int)s.size() < cap - 1 ? (int)s.size() : cap - 1; std::memcpy(buf, s.data(), n); buf[n] = 0; }

@@ -49,6 +49,8 @@ def lib():
         for name in ("ref_apd_swap", "ref_apd_clear_source", "ref_apd_clear_target", "ref_apd_lm_failed", "ref_apd_compute_covariances"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.ref_apd_align.argtypes = [C.c_void_p, fp, C.c_int, fp, ip, ip, fp]
+        L.ref_apd_fitness.argtypes = [C.c_void_p, C.c_double]
+        L.ref_apd_fitness.restype = C.c_double
         L.ref_apd_get_debug_text.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.ref_apd_get_covariances.argtypes = [C.c_void_p, C.c_int, dp]
         L.ref_apd_get_covariances4.argtypes = [C.c_void_p, C.c_int, dp]
@@ -181,6 +183,9 @@ class RefAPD:
 
     def lm_failed(self) -> bool:
         return bool(self.L.ref_apd_lm_failed(self.h))
+
+    def fitness(self, max_range=float(np.finfo(np.float64).max)):
+        return self.L.ref_apd_fitness(self.h, max_range)
 
     def trace(self):
         return self._trace

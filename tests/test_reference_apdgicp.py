@@ -193,6 +193,7 @@ def test_align(small_pair, params):
     _compare_align(o, r)
     G = np.eye(4); G[:3, :3] = so3_exp_matrix(np.array([0.0, 0.0, 0.03])); G[:3, 3] = [0.3, -0.2, 0.0]
     _compare_align(o, r, G.astype(np.float32))
+    assert abs(o.fitness() - r.fitness()) <= 1e-6 * r.fitness() and abs(o.fitness(1.5) - r.fitness(1.5)) <= 1e-6 * r.fitness(1.5)   # float T may differ in its last bit
     # the aligned cloud (pcl::transformPointCloud, LSQ_I:80) is the float transform of the input
     T1 = r.align(G.astype(np.float32))[1]
     assert np.array_equal(r.aligned, o.transform_source(T1))
