@@ -219,7 +219,8 @@ typedef struct apd_preprocess_params {
   double distance_far_thresh;       /* :203 (100.0) */
   double z_low_thresh;              /* :204 (-5.0)  */
   double z_high_thresh;             /* :205 (20.0)  */
-  double downsample_resolution;     /* :138 (0.1); <= 0 = downsample_method NONE; otherwise pcl::VoxelGrid with this leaf */
+  double downsample_resolution;     /* :138 (0.1); <= 0 = downsample_method NONE; otherwise the leaf of pcl::VoxelGrid, or of pcl::ApproximateVoxelGrid
+                                       after apd_set_option(h, "downsample_method", 1) (:137-149; 0 = VOXELGRID, the default) */
   double radius_radius;             /* :177 (0.8)   */
   double statistical_stddev;        /* :169 (1.0)   */
 } apd_preprocess_params;

@@ -91,6 +91,8 @@ def lib():
         L.oracle_max_threads.restype = C.c_int
         L.oracle_distance_filter.argtypes = [fp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, fp]
         L.oracle_voxel_grid.argtypes = [fp, C.c_int, C.c_float, fp]
+        L.oracle_approx_voxel_grid.argtypes = [fp, C.c_int, C.c_float, fp]
+        L.oracle_accumulate_submap_m.argtypes = [fp, ip, C.c_int, dp, C.c_float, C.c_int, fp]
         L.oracle_radius_outlier_removal.argtypes = [fp, C.c_int, C.c_double, C.c_int, fp]
         L.oracle_statistical_outlier_removal.argtypes = [fp, C.c_int, C.c_int, C.c_double, fp]
         L.oracle_accumulate_submap.argtypes = [fp, ip, C.c_int, dp, C.c_float, fp]
@@ -302,6 +304,14 @@ def voxel_grid(cloud, leaf):
     return out[:n]
 
 
+def approx_voxel_grid(cloud, leaf):
+    """pcl::ApproximateVoxelGrid (downsample_method APPROX_VOXELGRID)."""
+    a = _xyzi(cloud)
+    out = np.zeros_like(a)
+    n = lib().oracle_approx_voxel_grid(_ptr(a, C.c_float), a.shape[0], leaf, _ptr(out, C.c_float))
+    return out[:n]
+
+
 def radius_outlier_removal(cloud, radius, min_pts):
     a = _xyzi(cloud)
     out = np.zeros_like(a)
@@ -316,13 +326,13 @@ def statistical_outlier_removal(cloud, mean_k, stddev_mult):
     return out[:n]
 
 
-def accumulate_submap(clouds, rel_poses, leaf=0.0):
+def accumulate_submap(clouds, rel_poses, leaf=0.0, approx=False):
     off = np.zeros(len(clouds) + 1, dtype=np.int32)
     off[1:] = np.cumsum([c.shape[0] for c in clouds])
     a = _xyzi(np.concatenate(clouds))
     P = np.ascontiguousarray(rel_poses, dtype=np.float64).reshape(len(clouds), 16)
     out = np.zeros_like(a)
-    n = lib().oracle_accumulate_submap(_ptr(a, C.c_float), _ptr(off, C.c_int), len(clouds), _ptr(P, C.c_double), leaf, _ptr(out, C.c_float))
+    n = lib().oracle_accumulate_submap_m(_ptr(a, C.c_float), _ptr(off, C.c_int), len(clouds), _ptr(P, C.c_double), leaf, int(approx), _ptr(out, C.c_float))
     return out[:n]
 
 

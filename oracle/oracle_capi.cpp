@@ -246,6 +246,11 @@ int oracle_voxel_grid(const float* xyzi, int n, float leaf, float* out) {
   std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
   return (int)r.size();
 }
+int oracle_approx_voxel_grid(const float* xyzi, int n, float leaf, float* out) {
+  const auto r = apd_oracle::approx_voxel_grid(to_pts(xyzi, n), leaf);
+  std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
+  return (int)r.size();
+}
 int oracle_radius_outlier_removal(const float* xyzi, int n, double radius, int min_pts, float* out) {
   const auto r = apd_oracle::radius_outlier_removal(to_pts(xyzi, n), radius, min_pts);
   std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
@@ -256,7 +261,12 @@ int oracle_statistical_outlier_removal(const float* xyzi, int n, int mean_k, dou
   std::memcpy(out, r.data(), sizeof(apd_oracle::PointI) * r.size());
   return (int)r.size();
 }
+int oracle_accumulate_submap_m(const float* xyzi, const int* offsets, int n_clouds, const double* rel_poses16, float leaf, int approx, float* out);
 int oracle_accumulate_submap(const float* xyzi, const int* offsets, int n_clouds, const double* rel_poses16, float leaf, float* out) {
+  return oracle_accumulate_submap_m(xyzi, offsets, n_clouds, rel_poses16, leaf, 0, out);
+}
+// approx != 0: downsample_method APPROX_VOXELGRID (scan_matching_odometry_nodelet.cpp:156-160)
+int oracle_accumulate_submap_m(const float* xyzi, const int* offsets, int n_clouds, const double* rel_poses16, float leaf, int approx, float* out) {
   std::vector<std::vector<apd_oracle::PointI>> clouds(n_clouds);
   std::vector<const double*> poses(n_clouds);
   for (int k = 0; k < n_clouds; k++) {
@@ -266,7 +276,7 @@ int oracle_accumulate_submap(const float* xyzi, const int* offsets, int n_clouds
   auto acc = apd_oracle::accumulate_submap(clouds, poses);
   if (leaf > 0.f) {
     std::vector<apd_oracle::PointI> r;
-    apd_oracle::voxel_grid(acc, leaf, r);
+    if (approx) r = apd_oracle::approx_voxel_grid(acc, leaf); else apd_oracle::voxel_grid(acc, leaf, r);
     acc.swap(r);
   }
   std::memcpy(out, acc.data(), sizeof(apd_oracle::PointI) * acc.size());

@@ -98,6 +98,45 @@ inline bool voxel_grid(const std::vector<PointI>& in, float leaf, std::vector<Po
   return true;
 }
 
+// pcl::ApproximateVoxelGrid::applyFilter (pcl/filters/impl/approximate_voxel_grid.hpp, PCL 1.10; the APPROX_VOXELGRID branch of
+// preprocessing_nodelet.cpp:145-149 and scan_matching_odometry_nodelet.cpp:156-160), restated as PCL writes it: one pass over the
+// points with a history table of histsize_ = 512 entries indexed by (ix * 7171 + iy * 3079 + iz * 4231) & 511; a point whose voxel
+// differs from the one stored in its entry flushes that entry (centroid / count becomes the next output point) and restarts it; the
+// non-empty entries are flushed in table order at the end. All four fields are averaged (downsample_all_data_). PARITY UNPINNED:
+// PCL is absent; the table size and hash constants are quoted from PCL 1.10's header. ix = static_cast<int>(floor(x * inv)) of a
+// non-finite / out-of-range value is taken as INT_MIN (what cvttss2si yields on x86; undefined in C++).
+inline int approx_cell(float v, float inv) {
+  const float f = std::floor(v * inv);
+  return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : std::numeric_limits<int>::min();
+}
+inline std::vector<PointI> approx_voxel_grid(const std::vector<PointI>& in, float leaf) {
+  const unsigned histsize = 512;
+  struct He { int ix, iy, iz, count; float c[4]; };
+  std::vector<He> history(histsize, He{0, 0, 0, 0, {0.f, 0.f, 0.f, 0.f}});
+  const float inv = 1.0f / leaf;
+  std::vector<PointI> out;
+  auto flush = [&](He& h) {
+    const float n = (float)h.count;
+    out.push_back(PointI{h.c[0] / n, h.c[1] / n, h.c[2] / n, h.c[3] / n});
+  };
+  for (const PointI& p : in) {
+    const int ix = approx_cell(p.x, inv), iy = approx_cell(p.y, inv), iz = approx_cell(p.z, inv);
+    const unsigned hash = ((unsigned)ix * 7171u + (unsigned)iy * 3079u + (unsigned)iz * 4231u) & (histsize - 1);
+    He& h = history[hash];
+    if (h.count && (ix != h.ix || iy != h.iy || iz != h.iz)) {
+      flush(h);
+      h.count = 0;
+      h.c[0] = h.c[1] = h.c[2] = h.c[3] = 0.f;
+    }
+    h.ix = ix; h.iy = iy; h.iz = iz;
+    h.count++;
+    h.c[0] = h.c[0] + p.x; h.c[1] = h.c[1] + p.y; h.c[2] = h.c[2] + p.z; h.c[3] = h.c[3] + p.intensity;
+  }
+  for (He& h : history)
+    if (h.count) flush(h);
+  return out;
+}
+
 // pcl::RadiusOutlierRemoval on dense input: keep a point iff its (min_pts + 1)-th nearest point (itself included)
 // exists and lies within the radius: !(r*r < d2), d2 = L2_Simple<float>
 inline std::vector<PointI> radius_outlier_removal(const std::vector<PointI>& in, double radius, int min_pts) {

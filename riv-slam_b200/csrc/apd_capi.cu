@@ -186,6 +186,7 @@ struct apd_context {
   int timeline_opt = 0;  // profiling aid: the align kernel stamps its phases (apd_get_timeline)
   // kernel timing (option "kernel_timing"): CUDA events around the hot launches, on the stream they are launched on
   int kernel_timing = 0;
+  int downsample_method = 0;  // option "downsample_method": 0 = VOXELGRID (pcl::VoxelGrid), 1 = APPROX_VOXELGRID (pcl::ApproximateVoxelGrid)
   struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
   std::vector<TimedLaunch> timed;
   std::vector<cudaEvent_t> event_pool;
@@ -979,6 +980,10 @@ int apd_set_option(apd_handle h, const char* name, double value) {
     h->knn_leaf_parts = v;
   }
   else if (n == "kernel_timing") h->kernel_timing = value != 0;
+  else if (n == "downsample_method") {   // the rosparam of preprocessing_nodelet.cpp:137 / scan_matching_odometry_nodelet.cpp:149 (NONE = downsample_resolution <= 0)
+    if (value != 0 && value != 1) return fail(h, APD_ERR_UNSUPPORTED, "downsample_method must be 0 (VOXELGRID) or 1 (APPROX_VOXELGRID)");
+    h->downsample_method = (int)value;
+  }
   else return fail(h, APD_ERR_INVALID, "unknown option " + n);
   return APD_OK;
 }
@@ -1752,7 +1757,8 @@ int apd_preprocess(apd_handle h, const float* points, int stride_bytes, int inte
   float4 *cur = B, *other = A;
   int* cur_n = nd + 0;
   if (voxel) {
-    CK(launch_voxel_grid(cur, cur_n, n, (float)p->downsample_resolution, h->pp_ws.as<unsigned>(), h->pp_seg.as<int>(), other, nd + 1, h->stream, &h->stats));
+    CK((h->downsample_method == 1 ? launch_approx_voxel_grid : launch_voxel_grid)(cur, cur_n, n, (float)p->downsample_resolution, h->pp_ws.as<unsigned>(), h->pp_seg.as<int>(), other,
+                                                                                    nd + 1, h->stream, &h->stats));
     std::swap(cur, other);
     cur_n = nd + 1;
   }
@@ -1841,7 +1847,8 @@ int apd_build_submap(apd_handle h, apd_cloudset keyframes, const int32_t* which,
   int m = total;
   if (downsample_resolution > 0) {
     int* nd = h->pp_n.as<int>();
-    CK(launch_voxel_grid(A, nullptr, total, (float)downsample_resolution, h->pp_ws.as<unsigned>(), h->pp_seg.as<int>(), B, nd, h->stream, &h->stats));
+    CK((h->downsample_method == 1 ? launch_approx_voxel_grid : launch_voxel_grid)(A, nullptr, total, (float)downsample_resolution, h->pp_ws.as<unsigned>(), h->pp_seg.as<int>(), B, nd,
+                                                                                    h->stream, &h->stats));
     CK(cudaMemcpyAsync(&m, nd, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     cur = B;
   }

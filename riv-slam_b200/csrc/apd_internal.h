@@ -244,6 +244,8 @@ cudaError_t launch_distance_filter(const float4* in, int n, double near_t, doubl
                                    int* n_out, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_voxel_grid(const float4* in, const int* n_in_dev, int n_in_host, float leaf, unsigned* ws_u32 /*4*n*/, int* seg_start /*n+1*/, float4* out, int* n_out,
                               cudaStream_t stream, LaunchStats* st);
+cudaError_t launch_approx_voxel_grid(const float4* in, const int* n_in_dev, int n_in_host, float leaf, unsigned* ws_u32 /*4*n*/, int* seg_start /*n+1*/, float4* out, int* n_out,
+                              cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_radius_flags(const CloudSetView& cs, int n, double radius, int min_pts, unsigned char* flag, cudaStream_t stream, LaunchStats* st);
 cudaError_t launch_statistical_flags(const CloudSetView& cs, int n, const int* n_dev, int mean_k, double stddev_mult, float* dist /*n*/, double* thr /*1*/, unsigned char* flag,
                                      cudaStream_t stream, LaunchStats* st);

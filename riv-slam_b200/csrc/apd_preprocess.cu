@@ -90,6 +90,65 @@ __device__ __forceinline__ unsigned enc_f(float f) {
 }
 __device__ __forceinline__ float dec_f(unsigned u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
+// Stable LSD radix sort of (key, value) pairs by one CTA of kPT threads, 8 bits per pass, as many passes as maxkey needs. On return
+// ka / va point at the sorted arrays (the caller's pointers are swapped once per pass).
+__device__ __forceinline__ void block_radix_sort(unsigned*& ka, unsigned*& va, unsigned*& kb, unsigned*& vb, int n, unsigned maxkey, unsigned (*s_hist)[256], unsigned* s_warp) {
+  // Stable LSD radix sort, 8 bits per pass. Every warp owns a contiguous band of 32-element rows (coalesced
+  // loads and stores) and a private 256-bin histogram; bins are ranked digit-major / warp-minor, and inside a
+  // row the lanes that share a digit are ordered by lane (__match_any_sync), so equal keys keep their input order.
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rows = (n + 31) >> 5;
+  const int band = (rows + (kPT >> 5) - 1) / (kPT >> 5);
+  const int r0 = min(warp * band, rows), r1 = min(r0 + band, rows);
+  for (int shift = 0; shift < 32 && (maxkey >> shift) != 0u; shift += 8) {
+    for (int d = lane; d < 256; d += 32) s_hist[warp][d] = 0u;
+    __syncwarp();
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      if (j < n) atomicAdd(&s_hist[warp][(ka[j] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    {  // exclusive scan of the 256 x 32 bins in (digit, warp) order: 8 consecutive bins per thread
+      unsigned loc[8], sum = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int e = tid * 8 + k;
+        loc[k] = s_hist[e & 31][e >> 5];
+        sum += loc[k];
+      }
+      unsigned total;
+      unsigned run = block_excl_scan(sum, s_warp, &total);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int e = tid * 8 + k;
+        s_hist[e & 31][e >> 5] = run;
+        run += loc[k];
+      }
+    }
+    __syncthreads();
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      const bool valid = j < n;
+      const unsigned k = valid ? ka[j] : 0u;
+      const unsigned d = valid ? ((k >> shift) & 255u) : (0x10000u + (unsigned)lane);
+      const unsigned same = __match_any_sync(0xFFFFFFFFu, d);
+      const unsigned rank = __popc(same & ((1u << lane) - 1u));
+      unsigned dst = 0u;
+      if (valid) {
+        dst = s_hist[warp][d] + rank;
+        kb[dst] = k;
+        vb[dst] = va[j];
+      }
+      __syncwarp();
+      if (valid && rank == 0u) s_hist[warp][d] += __popc(same);
+      __syncwarp();
+    }
+    __syncthreads();
+    unsigned* t = ka; ka = kb; kb = t;
+    t = va; va = vb; vb = t;
+  }
+}
+
 __global__ void __launch_bounds__(kPT) voxel_grid_kernel(const float4* __restrict__ in, const int* __restrict__ n_in_dev, int n_in_host, float leaf, VoxelWs ws,
                                                          float4* __restrict__ out, int* __restrict__ n_out) {
   __shared__ unsigned s_hist[kPT / 32][256];  // per-warp digit histograms / scatter cursors
@@ -169,61 +228,13 @@ __global__ void __launch_bounds__(kPT) voxel_grid_kernel(const float4* __restric
   __syncthreads();
   const unsigned maxkey = s_maxkey;
 
-  // Stable LSD radix sort, 8 bits per pass. Every warp owns a contiguous band of 32-element rows (coalesced
-  // loads and stores) and a private 256-bin histogram; bins are ranked digit-major / warp-minor, and inside a
-  // row the lanes that share a digit are ordered by lane (__match_any_sync), so equal keys keep their input order.
+  // stable sort by voxel index (block_radix_sort above); ka / va hold the result
   unsigned *ka = ws.key_a, *va = ws.val_a, *kb = ws.key_b, *vb = ws.val_b;
+  block_radix_sort(ka, va, kb, vb, n, maxkey, s_hist, s_warp);
   const int lane = tid & 31, warp = tid >> 5;
   const int rows = (n + 31) >> 5;
   const int band = (rows + (kPT >> 5) - 1) / (kPT >> 5);
   const int r0 = min(warp * band, rows), r1 = min(r0 + band, rows);
-  for (int shift = 0; shift < 32 && (maxkey >> shift) != 0u; shift += 8) {
-    for (int d = lane; d < 256; d += 32) s_hist[warp][d] = 0u;
-    __syncwarp();
-    for (int r = r0; r < r1; r++) {
-      const int j = (r << 5) + lane;
-      if (j < n) atomicAdd(&s_hist[warp][(ka[j] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    {  // exclusive scan of the 256 x 32 bins in (digit, warp) order: 8 consecutive bins per thread
-      unsigned loc[8], sum = 0u;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int e = tid * 8 + k;
-        loc[k] = s_hist[e & 31][e >> 5];
-        sum += loc[k];
-      }
-      unsigned total;
-      unsigned run = block_excl_scan(sum, s_warp, &total);
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int e = tid * 8 + k;
-        s_hist[e & 31][e >> 5] = run;
-        run += loc[k];
-      }
-    }
-    __syncthreads();
-    for (int r = r0; r < r1; r++) {
-      const int j = (r << 5) + lane;
-      const bool valid = j < n;
-      const unsigned k = valid ? ka[j] : 0u;
-      const unsigned d = valid ? ((k >> shift) & 255u) : (0x10000u + (unsigned)lane);
-      const unsigned same = __match_any_sync(0xFFFFFFFFu, d);
-      const unsigned rank = __popc(same & ((1u << lane) - 1u));
-      unsigned dst = 0u;
-      if (valid) {
-        dst = s_hist[warp][d] + rank;
-        kb[dst] = k;
-        vb[dst] = va[j];
-      }
-      __syncwarp();
-      if (valid && rank == 0u) s_hist[warp][d] += __popc(same);
-      __syncwarp();
-    }
-    __syncthreads();
-    unsigned* t = ka; ka = kb; kb = t;
-    t = va; va = vb; vb = t;
-  }
 
   // voxel heads -> segment starts (valid keys only), then one thread per voxel accumulates its points in order
   unsigned carry = 0u;
@@ -259,6 +270,118 @@ __global__ void __launch_bounds__(kPT) voxel_grid_kernel(const float4* __restric
     out[s] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
   }
   if (tid == 0) *n_out = n_vox;
+}
+
+// pcl::ApproximateVoxelGrid::applyFilter (pcl/filters/impl/approximate_voxel_grid.hpp, PCL 1.10; downsample_all_data, histsize_ = 512),
+// the APPROX_VOXELGRID branch of preprocessing_nodelet.cpp:145-149 / scan_matching_odometry_nodelet.cpp:156-160. PCL walks the points
+// once with a 512-entry history table indexed by hash(ix, iy, iz) = (ix * 7171 + iy * 3079 + iz * 4231) & 511: a point whose voxel
+// differs from the one its entry holds FLUSHES that entry (its centroid becomes the next output point) and starts a new one; at the end
+// the non-empty entries are flushed in table order. Sequential as written, but every entry only ever sees the points that hash to it,
+// in input order, so the result is a function of per-entry runs:
+//   * stable sort of the points by hash -> per entry, its points in input order; a RUN = maximal stretch with the same (ix, iy, iz)
+//   * every run is one output point: sum of its points in input order (float, all four fields), divided by the count
+//   * a run that is not the last of its entry is flushed by the first point of the next run: output slot = number of flushing points
+//     before that point in INPUT order (exclusive scan of a flag array in input order)
+//   * the last run of an entry is flushed at the end: slot = (number of flushing points) + (number of non-empty entries before it)
+// static_cast<int>(floor(x * inv)) of a non-finite or out-of-range float is what cvttss2si returns on the reference's x86: INT_MIN.
+__device__ __forceinline__ int approx_cell(float v, float inv) {
+  const float f = floorf(fmul(v, inv));
+  return (f >= -2147483648.0f && f < 2147483648.0f) ? (int)f : (int)0x80000000;
+}
+__device__ __forceinline__ void approx_cells(const float4& p, float inv, int c[3]) {
+  c[0] = approx_cell(p.x, inv); c[1] = approx_cell(p.y, inv); c[2] = approx_cell(p.z, inv);
+}
+
+__global__ void __launch_bounds__(kPT) approx_voxel_grid_kernel(const float4* __restrict__ in, const int* __restrict__ n_in_dev, int n_in_host, float leaf, VoxelWs ws,
+                                                                float4* __restrict__ out, int* __restrict__ n_out) {
+  __shared__ unsigned s_hist[kPT / 32][256];
+  __shared__ unsigned s_warp[33];
+  __shared__ unsigned s_entry[512];   // entry non-empty flag, then rank among the non-empty entries
+  const int tid = threadIdx.x;
+  const int n = n_in_dev ? *n_in_dev : n_in_host;
+  const float inv = 1.0f / leaf;      // inverse_leaf_size_ = Array3f::Ones() / leaf_size_
+  for (int i = tid; i < n; i += kPT) {
+    int c[3];
+    approx_cells(in[i], inv, c);
+    ws.key_a[i] = ((unsigned)c[0] * 7171u + (unsigned)c[1] * 3079u + (unsigned)c[2] * 4231u) & 511u;
+    ws.val_a[i] = (unsigned)i;
+  }
+  if (tid < 512) s_entry[tid] = 0u;
+  __syncthreads();
+  unsigned *ka = ws.key_a, *va = ws.val_a, *kb = ws.key_b, *vb = ws.val_b;
+  block_radix_sort(ka, va, kb, vb, n, 511u, s_hist, s_warp);
+  const int lane = tid & 31, warp = tid >> 5;
+  const int rows = (n + 31) >> 5;
+  const int band = (rows + (kPT >> 5) - 1) / (kPT >> 5);
+  const int r0 = min(warp * band, rows), r1 = min(r0 + band, rows);
+
+  // run heads -> seg_start; flushing points flagged in INPUT order (kb); non-empty entries
+  unsigned carry = 0u;
+  for (int pass = 0; pass < 2; pass++) {
+    unsigned pos = 0u, total = 0u;
+    if (pass == 1) {
+      pos = block_excl_scan(lane == 0 ? carry : 0u, s_warp, &total);
+      pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    }
+    for (int r = r0; r < r1; r++) {
+      const int j = (r << 5) + lane;
+      bool head = false, first = false;
+      if (j < n) {
+        first = j == 0 || ka[j] != ka[j - 1];
+        head = first;
+        if (!first) {
+          int c[3], q[3];
+          approx_cells(in[va[j]], inv, c);
+          approx_cells(in[va[j - 1]], inv, q);
+          head = c[0] != q[0] || c[1] != q[1] || c[2] != q[2];
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+      if (pass == 0) {
+        carry += __popc(m);
+        if (j < n) kb[va[j]] = (head && !first) ? 1u : 0u;
+        if (first) s_entry[ka[j]] = 1u;
+      } else {
+        if (head) ws.seg_start[pos + __popc(m & ((1u << lane) - 1u))] = j;
+        pos += __popc(m);
+      }
+    }
+    if (pass == 1 && tid == 0) ws.seg_start[total] = n;
+    if (pass == 1) carry = total;
+    __syncthreads();
+  }
+  const int n_runs = (int)__shfl_sync(0xFFFFFFFFu, carry, 0);   // every thread holds `total` already; keeps the value warp-uniform
+  // rank of every entry among the non-empty ones
+  unsigned n_entries;
+  {
+    const unsigned v = tid < 512 ? s_entry[tid] : 0u;
+    const unsigned ex = block_excl_scan(v, s_warp, &n_entries);
+    __syncthreads();
+    if (tid < 512) s_entry[tid] = ex;
+  }
+  // exclusive scan of the flush flags in input order: every thread owns a contiguous segment; vb[i] = flushes before point i
+  unsigned n_flush;
+  {
+    const int seg = (n + kPT - 1) / kPT;
+    const int j0 = min(tid * seg, n), j1 = min(j0 + seg, n);
+    unsigned cnt = 0u;
+    for (int j = j0; j < j1; j++) cnt += kb[j];
+    unsigned run = block_excl_scan(cnt, s_warp, &n_flush);
+    for (int j = j0; j < j1; j++) { vb[j] = run; run += kb[j]; }
+  }
+  __syncthreads();
+  for (int s = tid; s < n_runs; s += kPT) {
+    const int a = ws.seg_start[s], b = ws.seg_start[s + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (int j = a; j < b; j++) {
+      const float4 p = in[va[j]];
+      sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z); si = fadd(si, p.w);   // hhe->centroid += scratch
+    }
+    const float cnt = (float)(b - a);
+    const unsigned slot = (b < n && ka[b] == ka[a]) ? vb[va[b]] : n_flush + s_entry[ka[a]];
+    out[slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);                      // hhe->centroid /= count
+  }
+  if (tid == 0) *n_out = n_runs;
 }
 
 // count of target points within the radius (d2 <= r2 as in PCL's dense branch), for RadiusOutlierRemoval
@@ -399,6 +522,14 @@ cudaError_t launch_voxel_grid(const float4* in, const int* n_in_dev, int n_in_ho
                               cudaStream_t stream, LaunchStats* st) {
   VoxelWs ws{ws_u32, ws_u32 + n_in_host, ws_u32 + 2 * (size_t)n_in_host, ws_u32 + 3 * (size_t)n_in_host, seg_start};
   voxel_grid_kernel<<<1, kPT, 0, stream>>>(in, n_in_dev, n_in_host, leaf, ws, out, n_out);
+  APD_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_approx_voxel_grid(const float4* in, const int* n_in_dev, int n_in_host, float leaf, unsigned* ws_u32 /*4*n*/, int* seg_start /*n+1*/, float4* out,
+                                     int* n_out, cudaStream_t stream, LaunchStats* st) {
+  VoxelWs ws{ws_u32, ws_u32 + n_in_host, ws_u32 + 2 * (size_t)n_in_host, ws_u32 + 3 * (size_t)n_in_host, seg_start};
+  approx_voxel_grid_kernel<<<1, kPT, 0, stream>>>(in, n_in_dev, n_in_host, leaf, ws, out, n_out);
   APD_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -657,10 +657,25 @@ def preprocess_params(**kw) -> ApdPreprocessParams:
     return p
 
 
-def preprocess(handle: Handle, cloud, params: ApdPreprocessParams | None = None, **kw) -> np.ndarray:
+DOWNSAMPLE_METHODS = {"VOXELGRID": 0, "APPROX_VOXELGRID": 1}
+
+
+def set_downsample_method(handle: Handle, method: str):
+    """The ``downsample_method`` rosparam (preprocessing_nodelet.cpp:137-156, scan_matching_odometry_nodelet.cpp:149-167): VOXELGRID
+    (pcl::VoxelGrid, the default and the launch file's choice) or APPROX_VOXELGRID (pcl::ApproximateVoxelGrid); NONE is
+    ``downsample_resolution <= 0``. Anything else is refused (the nodelet falls back to a pass-through with a warning)."""
+    if method not in DOWNSAMPLE_METHODS:
+        raise ApdError(APD_ERR_UNSUPPORTED, f"unknown downsample_method {method!r}: VOXELGRID or APPROX_VOXELGRID (NONE = downsample_resolution <= 0)")
+    handle.set_option("downsample_method", DOWNSAMPLE_METHODS[method])
+
+
+def preprocess(handle: Handle, cloud, params: ApdPreprocessParams | None = None, downsample_method: str | None = None, **kw) -> np.ndarray:
     """distance_filter -> downsample -> outlier_removal (preprocessing_nodelet.cpp:812-815) of one host cloud on the GPU.
 
-    ``cloud`` is (n, 4) packed x y z intensity or (n, 8) pcl::PointXYZI memory; the result has the same row layout."""
+    ``cloud`` is (n, 4) packed x y z intensity or (n, 8) pcl::PointXYZI memory; the result has the same row layout.
+    ``downsample_method`` (sticky on the handle): see set_downsample_method."""
+    if downsample_method is not None:
+        set_downsample_method(handle, downsample_method)
     a = np.ascontiguousarray(cloud, dtype=np.float32)
     if a.ndim != 2 or a.shape[1] not in (4, 8):
         raise ValueError("preprocess takes (n, 4) xyzi or (n, 8) pcl::PointXYZI arrays")
@@ -672,9 +687,13 @@ def preprocess(handle: Handle, cloud, params: ApdPreprocessParams | None = None,
     return out[:n_out.value]
 
 
-def build_submap(handle: Handle, keyframes: CloudSet, which, rel_poses, downsample_resolution: float = 0.1, cache_key: int = 0, want_cloud: bool = True):
+def build_submap(handle: Handle, keyframes: CloudSet, which, rel_poses, downsample_resolution: float = 0.1, cache_key: int = 0, want_cloud: bool = True,
+                 downsample_method: str | None = None):
     """apd_build_submap: the keyframe clouds ``which`` moved by ``rel_poses`` (4x4 double each), concatenated and voxel-filtered,
-    become the handle's target (scan_matching_odometry_nodelet.cpp:606-616). Returns the submap as (m, 4) xyzi (or its size)."""
+    become the handle's target (scan_matching_odometry_nodelet.cpp:606-616). Returns the submap as (m, 4) xyzi (or its size).
+    ``downsample_method`` (sticky on the handle): see set_downsample_method."""
+    if downsample_method is not None:
+        set_downsample_method(handle, downsample_method)
     w = np.ascontiguousarray(which, dtype=np.int32)
     P = np.ascontiguousarray(rel_poses, dtype=np.float64).reshape(len(w), 16)
     cap = int(sum(keyframes.offsets[i + 1] - keyframes.offsets[i] for i in w))

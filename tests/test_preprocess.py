@@ -39,13 +39,14 @@ def raw_scan(seed, n=3000, with_bad=True):
 
 
 def oracle_pipeline(cloud, use_distance_filter=1, distance_near_thresh=1.0, distance_far_thresh=100.0, z_low_thresh=-5.0, z_high_thresh=20.0,
-                    downsample_resolution=0.1, outlier_removal=1, radius_radius=0.8, radius_min_neighbors=2, statistical_mean_k=20, statistical_stddev=1.0):
+                    downsample_resolution=0.1, outlier_removal=1, radius_radius=0.8, radius_min_neighbors=2, statistical_mean_k=20, statistical_stddev=1.0,
+                    downsample_method="VOXELGRID"):
     from oracle import oracle as O
     c = cloud
     if use_distance_filter:
         c = O.distance_filter(c, distance_near_thresh, distance_far_thresh, z_low_thresh, z_high_thresh)
     if downsample_resolution > 0:
-        c = O.voxel_grid(c, downsample_resolution)
+        c = O.voxel_grid(c, downsample_resolution) if downsample_method == "VOXELGRID" else O.approx_voxel_grid(c, downsample_resolution)
     else:
         c = c[np.isfinite(c[:, :3]).all(axis=1)]  # pcl::removeNaNFromPointCloud, preprocessing_nodelet.cpp:852-856
     if outlier_removal == 1:
@@ -85,6 +86,69 @@ def twin_voxel_grid(c, leaf):
             s = (s + p[i]).astype(f32)
         out.append(s / f32(len(groups[k])))
     return np.array(out, dtype=f32).reshape(-1, 4)
+
+
+def _approx_cells(c, leaf):
+    inv = np.float32(1.0) / np.float32(leaf)
+    with np.errstate(invalid="ignore", over="ignore"):
+        f = np.floor(c[:, :3].astype(np.float32) * inv)
+    ok = np.isfinite(f) & (f >= -2147483648.0) & (f < 2147483648.0)
+    cells = np.where(ok, np.where(ok, f, 0).astype(np.int64), -2**31)              # cvttss2si: INT_MIN when not representable
+    h = ((cells[:, 0] * 7171 + cells[:, 1] * 3079 + cells[:, 2] * 4231) & 0xFFFFFFFF) & 511
+    return cells, h
+
+
+def twin_approx_voxel_grid(c, leaf):
+    """pcl::ApproximateVoxelGrid as PCL writes it: a pure-Python walk over the points with the 512-entry history table."""
+    cells, hs = _approx_cells(c, leaf)
+    table = {}
+    out = []
+
+    def flush(e):
+        n = np.float32(e[1])
+        out.append(e[2] / n)
+    for i in range(len(c)):
+        key = tuple(cells[i]); h = int(hs[i])
+        e = table.get(h)
+        if e is not None and e[0] != key:
+            flush(e)
+            e = None
+        if e is None:
+            e = [key, 0, np.zeros(4, np.float32)]
+            table[h] = e
+        e[1] += 1
+        e[2] = e[2] + c[i].astype(np.float32)
+    for h in sorted(table):
+        flush(table[h])
+    return np.array(out, dtype=np.float32).reshape(-1, 4)
+
+
+def parallel_approx_voxel_grid(c, leaf):
+    """The data-parallel form the CUDA kernel uses (apd_preprocess.cu, approx_voxel_grid_kernel), in numpy: stable sort by table entry,
+    runs of equal voxels, a flush slot per run from an exclusive scan of the flushing points in input order."""
+    n = len(c)
+    if n == 0:
+        return np.zeros((0, 4), np.float32)
+    cells, hs = _approx_cells(c, leaf)
+    order = np.argsort(hs, kind="stable")
+    sh, sc = hs[order], cells[order]
+    first = np.r_[True, sh[1:] != sh[:-1]]
+    head = first | np.r_[False, (sc[1:] != sc[:-1]).any(axis=1)]
+    flushing = np.zeros(n, np.int64)
+    flushing[order[head & ~first]] = 1
+    before = np.cumsum(flushing) - flushing                     # exclusive scan in INPUT order
+    n_flush = int(flushing.sum())
+    entry_rank = np.cumsum(first) - 1                           # rank of the entry among the non-empty ones, per sorted position
+    starts = np.flatnonzero(head)
+    ends = np.r_[starts[1:], n]
+    out = np.zeros((len(starts), 4), np.float32)
+    for a, b in zip(starts, ends):
+        acc = np.zeros(4, np.float32)
+        for j in range(a, b):
+            acc = acc + c[order[j]].astype(np.float32)
+        slot = before[order[b]] if b < n and sh[b] == sh[a] else n_flush + entry_rank[a]
+        out[slot] = acc / np.float32(b - a)
+    return out
 
 
 def twin_radius_outlier(c, radius, min_pts):
@@ -149,6 +213,33 @@ def test_oracle_voxel_grid_edge_cases():
     assert np.array_equal(O.voxel_grid(far, 0.001), far)
 
 
+@pytest.mark.parametrize("leaf", [0.1, 0.5, 2.0, 25.0])
+def test_oracle_approx_voxel_grid_matches_twins(leaf):
+    """pcl::ApproximateVoxelGrid: the C++ oracle == a pure-Python walk with the history table == the data-parallel form of the kernel.
+    Finite input (what the nodelet's distance filter leaves) and raw input with NaN / inf rows (use_distance_filter = false)."""
+    from oracle import oracle as O
+    for seed, with_bad in ((0, False), (1, False), (2, True)):
+        c = raw_scan(seed, 1200, with_bad=with_bad)
+        got = O.approx_voxel_grid(c, leaf)
+        want = twin_approx_voxel_grid(c, leaf)
+        assert got.shape == want.shape and got.tobytes() == want.tobytes()
+        par = parallel_approx_voxel_grid(c, leaf)
+        assert par.shape == got.shape and par.tobytes() == got.tobytes()
+        if not with_bad:
+            assert len(got) >= len(O.voxel_grid(c, leaf))       # evictions split voxels, they never merge them
+    # collisions are what makes it approximate: a voxel that is evicted and comes back yields two output points
+    a = np.array([[0.05, 0.05, 0.05, 1.0]], np.float32)
+    cells, h = _approx_cells(a, 0.1)
+    k = next(k for k in range(1, 4000) if ((k * 7171) & 511) == 0)                 # same table entry, different voxel
+    b = a + np.array([[0.1 * k, 0, 0, 1.0]], np.float32)
+    assert _approx_cells(b, 0.1)[1][0] == h[0]
+    seq = np.concatenate([a, b, a, a]).astype(np.float32)
+    got = O.approx_voxel_grid(seq, 0.1)
+    assert len(got) == 3 and np.array_equal(got[0], a[0]) and np.array_equal(got[1], b[0]) and np.array_equal(got[2], a[0])
+    assert parallel_approx_voxel_grid(seq, 0.1).tobytes() == got.tobytes()
+    assert O.approx_voxel_grid(np.zeros((0, 4), np.float32), 0.1).shape == (0, 4)
+
+
 @pytest.mark.parametrize("radius,min_pts", [(0.8, 2), (0.5, 5), (0.3, 1)])
 def test_oracle_radius_outlier_matches_twin(radius, min_pts):
     from oracle import oracle as O
@@ -202,6 +293,10 @@ CASES = [
          radius_min_neighbors=5),
     dict(outlier_removal=2),                                        # the nodelet's code defaults: STATISTICAL 20 / 1.0
     dict(outlier_removal=2, statistical_mean_k=30, statistical_stddev=1.2, downsample_resolution=0.2),   # launch-file values of the statistical parameters
+    dict(downsample_method="APPROX_VOXELGRID"),                     # pcl::ApproximateVoxelGrid (preprocessing_nodelet.cpp:145-149) + RADIUS
+    dict(downsample_method="APPROX_VOXELGRID", outlier_removal=0, downsample_resolution=0.5),
+    dict(downsample_method="APPROX_VOXELGRID", use_distance_filter=0, outlier_removal=0),   # NaN / inf rows reach the filter
+    dict(downsample_method="APPROX_VOXELGRID", outlier_removal=2, downsample_resolution=2.0),
 ]
 
 
@@ -210,9 +305,10 @@ CASES = [
 @pytest.mark.parametrize("width", [4, 8])
 def test_preprocess_bit_exact(case, width):
     from riv_slam_b200.fast_apdgicp import preprocess
-    kw = CASES[case]
+    kw = dict(CASES[case])
     c = raw_scan(20 + case, 3000)
     want = oracle_pipeline(c, **kw)
+    kw.setdefault("downsample_method", "VOXELGRID")
     cloud = c
     if width == 8:  # pcl::PointXYZI memory: x y z 1 | intensity pad pad pad
         cloud = np.zeros((len(c), 8), np.float32)
@@ -222,8 +318,15 @@ def test_preprocess_bit_exact(case, width):
         assert np.all(got[:, 3] == 1.0) and np.all(got[:, 5:] == 0.0)
         got = np.ascontiguousarray(got[:, [0, 1, 2, 4]])
     assert got.shape == want.shape
-    assert got.tobytes() == want.tobytes()
+    if np.isnan(want).any():   # raw NaN / inf rows averaged by ApproximateVoxelGrid: NaN where the oracle has NaN (the payload bits of a NaN are not data)
+        assert kw["downsample_method"] == "APPROX_VOXELGRID" and not kw.get("use_distance_filter", 1)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.where(np.isnan(got), np.float32(0), got).tobytes() == np.where(np.isnan(want), np.float32(0), want).tobytes()
+    else:
+        assert got.tobytes() == want.tobytes()
     assert 0 < len(got) < len(c)
+    if kw["downsample_method"] == "APPROX_VOXELGRID" and kw.get("outlier_removal", 1) == 0:   # and it is not the exact filter in disguise
+        assert got.tobytes() != oracle_pipeline(c, **dict(kw, downsample_method="VOXELGRID")).tobytes()
 
 
 @pytest.mark.gpu
@@ -243,6 +346,32 @@ def test_preprocess_edge_cases():
     # a 20k-point raw scan (several CTA-sized segments per thread)
     big = np.concatenate([raw_scan(40 + i, 5000) for i in range(3)])
     assert preprocess(H, big).tobytes() == oracle_pipeline(big).tobytes()
+    # downsample_method: APPROX_VOXELGRID on the same scan, empty / single-point input, and an unknown method refused loudly
+    assert preprocess(H, big, downsample_method="APPROX_VOXELGRID").tobytes() == oracle_pipeline(big, downsample_method="APPROX_VOXELGRID").tobytes()
+    assert preprocess(H, np.zeros((0, 4), np.float32)).shape == (0, 4)
+    assert np.array_equal(preprocess(H, lone, outlier_removal=0), lone)
+    with pytest.raises(ApdError):
+        preprocess(H, lone, downsample_method="OCTREE")
+    assert preprocess(H, big, downsample_method="VOXELGRID").tobytes() == oracle_pipeline(big).tobytes()   # sticky option switched back
+
+
+@pytest.mark.gpu
+def test_build_submap_approx_voxelgrid_bit_exact():
+    """scan_matching_odometry_nodelet.cpp:156-160: the submap downsampled by pcl::ApproximateVoxelGrid (80 k accumulated points)."""
+    from oracle import oracle as O
+    from riv_slam_b200 import datagen
+    from riv_slam_b200.fast_apdgicp import CloudSet, Handle, build_submap
+    scans, poses = datagen.make_drive(9, 4, 17, n_points=5000)
+    clouds = [np.ascontiguousarray(np.concatenate([s[:, :3], np.full((len(s), 1), 1.0 + i, np.float32)], axis=1)) for i, s in enumerate(scans)]
+    which = list(range(16))
+    rel = [np.linalg.inv(poses[i]) @ poses[16] for i in which]
+    H = Handle(0)
+    ks = CloudSet(H, clouds)
+    for leaf in (0.1, 1.0):
+        want = O.accumulate_submap([clouds[i] for i in which], rel, leaf, approx=True)
+        got = build_submap(H, ks, which, rel, leaf, cache_key=5, downsample_method="APPROX_VOXELGRID")
+        assert got.shape == want.shape and got.tobytes() == want.tobytes()
+        assert len(want) > len(O.accumulate_submap([clouds[i] for i in which], rel, leaf))
 
 
 @pytest.mark.gpu
