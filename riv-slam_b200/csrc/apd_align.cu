@@ -636,7 +636,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
   }
   const bool leader = (tc.rank == 0 && threadIdx.x == 0);
   const DeviceParams& P = B.prm;
-  if (threadIdx.x == 0) S.staged_target = -1;
+  __shared__ unsigned long long s_stage_bar;   // completion barrier of the bulk staging copies (leaf_stage_bulk)
+  unsigned stage_parity = 0u;
+  if (threadIdx.x == 0) {
+    S.staged_target = -1;
+    if (STAGED) mbar_init(&s_stage_bar, 1u);
+  }
   __syncthreads();
 
   int pair = tc.id;
@@ -669,7 +674,12 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       const int nleaf = (nt + kLeaf - 1) / kLeaf;
       float4* sbox = sP + (size_t)nleaf * kLeaf;
       if (S.staged_target != t) {  // consecutive pairs on the same target (scan-to-submap) reuse the staged cloud
-        leaf_stage(sP, sbox, B.tgt.spts + tb, B.tgt.lbox + 2 * (size_t)B.tgt.leaf_off[t], nt);
+        if (B.tgt.limg) {
+          // one bulk asynchronous copy of the image the build wrote (points in the pair layout + boxes): no register round trip
+          leaf_stage_bulk(sP, B.tgt.limg + (size_t)kLeafImage * B.tgt.leaf_off[t], nt, &s_stage_bar, stage_parity);
+        } else {
+          leaf_stage(sP, sbox, B.tgt.spts + tb, B.tgt.lbox + 2 * (size_t)B.tgt.leaf_off[t], nt);
+        }
         __syncthreads();
         if (threadIdx.x == 0) S.staged_target = t;
       }
@@ -1021,7 +1031,15 @@ __global__ void __launch_bounds__(256) fitness_leaf_kernel(CloudSetView src, int
   L.nleaf = (nt + kLeaf - 1) / kLeaf;
   float4* sP = reinterpret_cast<float4*>(smem_raw);
   float4* sbox = sP + (size_t)L.nleaf * kLeaf;
-  leaf_stage(sP, sbox, tgt.spts + tb, tgt.lbox + 2 * (size_t)tgt.leaf_off[t], nt);
+  __shared__ unsigned long long s_stage_bar;
+  if (tgt.limg) {
+    unsigned parity = 0u;
+    if (threadIdx.x == 0) mbar_init(&s_stage_bar, 1u);
+    __syncthreads();
+    leaf_stage_bulk(sP, tgt.limg + (size_t)kLeafImage * tgt.leaf_off[t], nt, &s_stage_bar, parity);
+  } else {
+    leaf_stage(sP, sbox, tgt.spts + tb, tgt.lbox + 2 * (size_t)tgt.leaf_off[t], nt);
+  }
   L.P = sP;
   L.box = sbox;
   __syncthreads();

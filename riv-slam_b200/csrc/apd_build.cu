@@ -831,6 +831,19 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
     const int nleaf_b = (n + kLeaf - 1) / kLeaf;
     float4* box_b = cs.lbox + 2 * (size_t)cs.leaf_off[c];
     for (int l = warp; l < nleaf_b; l += (T >> 5)) leaf_box_of(pts, w, nullptr, n, l, lane, box_b);
+    if (cs.limg) {  // the shared-memory image (CloudSetView::limg)
+      float4* img = cs.limg + (size_t)kLeafImage * cs.leaf_off[c];
+      for (int l = warp; l < nleaf_b; l += (T >> 5)) {
+        const int i = l * kLeaf + lane;
+        const float qnan = __int_as_float(0x7fc00000);
+        float4 p = make_float4(qnan, qnan, qnan, 0.f);
+        unsigned idx = 0x7FFFFu;
+        if (i < n) { idx = (unsigned)(w[i] & ((1u << kLeafPosBits) - 1u)); p = pts[idx]; }
+        leaf_image_store_points(img, i, p.x, p.y, p.z, idx, lane);
+        __syncwarp();
+        if (lane < 2) img[(size_t)nleaf_b * kLeaf + 2 * l + lane] = box_b[2 * l + lane];   // written by lane 0 of this warp above
+      }
+    }
     return;
   }
 
@@ -919,18 +932,23 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
   float4* spts = cs.spts + base;
   const int nleaf = (n + kLeaf - 1) / kLeaf;
   float4* box = cs.lbox + 2 * (size_t)cs.leaf_off[c];
+  float4* img = cs.limg ? cs.limg + (size_t)kLeafImage * cs.leaf_off[c] : nullptr;  // the shared-memory image (CloudSetView::limg)
   for (int l = warp; l < nleaf; l += (T >> 5)) {
     const int i = l * kLeaf + lane;
     unsigned lo[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu}, hi[3] = {0u, 0u, 0u};
+    const float qnan = __int_as_float(0x7fc00000);
+    float4 p = make_float4(qnan, qnan, qnan, 0.f);
+    unsigned idx = 0x7FFFFu;
     if (i < n) {
-      const unsigned idx = va[i];
-      const float4 p = pts[idx];
+      idx = va[i];
+      p = pts[idx];
       spts[i] = make_float4(p.x, p.y, p.z, __uint_as_float(idx));
       cs.inv0[base + idx] = i;
       if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
         lo[0] = hi[0] = enc_f(p.x); lo[1] = hi[1] = enc_f(p.y); lo[2] = hi[2] = enc_f(p.z);
       }
     }
+    if (img) leaf_image_store_points(img, i, p.x, p.y, p.z, idx, lane);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
       lo[a] = __reduce_min_sync(0xFFFFFFFFu, lo[a]);
@@ -939,8 +957,14 @@ __global__ void __launch_bounds__(1024) leaf_build_kernel(CloudSetView cs, bool 
     if (lane == 0) {
       const float inf = __int_as_float(0x7f800000);
       const bool empty = lo[0] > hi[0];
-      box[2 * l] = empty ? make_float4(inf, inf, inf, 0.f) : make_float4(dec_f(lo[0]), dec_f(lo[1]), dec_f(lo[2]), 0.f);
-      box[2 * l + 1] = empty ? make_float4(-inf, -inf, -inf, 0.f) : make_float4(dec_f(hi[0]), dec_f(hi[1]), dec_f(hi[2]), 0.f);
+      const float4 blo = empty ? make_float4(inf, inf, inf, 0.f) : make_float4(dec_f(lo[0]), dec_f(lo[1]), dec_f(lo[2]), 0.f);
+      const float4 bhi = empty ? make_float4(-inf, -inf, -inf, 0.f) : make_float4(dec_f(hi[0]), dec_f(hi[1]), dec_f(hi[2]), 0.f);
+      box[2 * l] = blo;
+      box[2 * l + 1] = bhi;
+      if (img) {
+        img[(size_t)nleaf * kLeaf + 2 * l] = blo;
+        img[(size_t)nleaf * kLeaf + 2 * l + 1] = bhi;
+      }
     }
   }
   bstamp(stamps, 8);  // sorted points, inverse order and boxes written

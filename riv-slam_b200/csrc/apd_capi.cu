@@ -119,10 +119,12 @@ struct apd_cloudset_s {
   bool staged = false;      // LEAF mode (apd_leaf.cuh): every cloud fits the shared-memory staging area; Hilbert-sorted leaves, no cell tables
   size_t staged_smem = 0;   // bytes the align kernel stages for the largest cloud
   DevBuf lbox;              // leaf mode: 2 float4 per leaf
+  DevBuf limg;              // leaf mode: the shared-memory image of every cloud (CloudSetView::limg), source of the bulk staging copies
+  bool bulk_stage = true;   // handle option "bulk_stage" at the time the set was made
   int* d_leaf_off = nullptr;
   long long total_leaves = 0;
   explicit apd_cloudset_s(const std::shared_ptr<Pool>& pool) {
-    for (DevBuf* b : {&pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &inv0, &tables, &lbox}) b->pool = pool;
+    for (DevBuf* b : {&pts, &spts, &cells, &grid, &cov0, &cov1, &cov2, &inv0, &tables, &lbox, &limg}) b->pool = pool;
     for (int l = 0; l < kCoarseLevels; l++)
       for (DevBuf* b : {&c_spts[l], &c_cells[l], &c_grid[l]}) b->pool = pool;
   }
@@ -150,6 +152,7 @@ struct apd_cloudset_s {
     v.cov2 = cov2.as<double2>();
     v.inv0 = inv0.as<int>();
     v.lbox = staged ? lbox.as<float4>() : nullptr;
+    v.limg = staged && bulk_stage ? limg.as<float4>() : nullptr;
     v.leaf_off = d_leaf_off;
     for (int l = 0; l < kCoarseLevels; l++) {
       v.coarse[l].spts = c_spts[l].as<float4>();
@@ -186,6 +189,7 @@ struct apd_context {
   int timeline_opt = 0;  // profiling aid: the align kernel stamps its phases (apd_get_timeline)
   // kernel timing (option "kernel_timing"): CUDA events around the hot launches, on the stream they are launched on
   int kernel_timing = 0;
+  bool bulk_stage = true;     // option "bulk_stage": leaf-mode clouds are staged by one cp.async.bulk from the image the build wrote (0: register path)
   int downsample_method = 0;  // option "downsample_method": 0 = VOXELGRID (pcl::VoxelGrid), 1 = APPROX_VOXELGRID (pcl::ApproximateVoxelGrid)
   struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
   std::vector<TimedLaunch> timed;
@@ -450,6 +454,8 @@ int cloudset_layout(apd_handle h, apd_cloudset_s* cs, bool force_grid = false) {
   CK(cs->inv0.reserve(sizeof(int) * np1));
   if (leaf) {
     CK(cs->lbox.reserve(sizeof(float4) * 2 * (size_t)std::max<long long>(cs->total_leaves, 1)));
+    cs->bulk_stage = h->bulk_stage;
+    if (cs->bulk_stage) CK(cs->limg.reserve(sizeof(float4) * kLeafImage * (size_t)std::max<long long>(cs->total_leaves, 1)));
     return APD_OK;  // no cell tables, no pyramid
   }
   CK(cs->cells.reserve(sizeof(unsigned) * (size_t)std::max<long long>(cs->total_cells, 1)));
@@ -980,6 +986,7 @@ int apd_set_option(apd_handle h, const char* name, double value) {
     h->knn_leaf_parts = v;
   }
   else if (n == "kernel_timing") h->kernel_timing = value != 0;
+  else if (n == "bulk_stage") h->bulk_stage = value != 0;   // takes effect for cloud sets made afterwards
   else if (n == "downsample_method") {   // the rosparam of preprocessing_nodelet.cpp:137 / scan_matching_odometry_nodelet.cpp:149 (NONE = downsample_resolution <= 0)
     if (value != 0 && value != 1) return fail(h, APD_ERR_UNSUPPORTED, "downsample_method must be 0 (VOXELGRID) or 1 (APPROX_VOXELGRID)");
     h->downsample_method = (int)value;
@@ -1581,6 +1588,7 @@ int helper_of(apd_handle h, apd_handle* out) {
   x->no_fused_build = h->no_fused_build;
   x->no_smem_build = h->no_smem_build;
   x->kernel_timing = h->kernel_timing;
+  x->bulk_stage = h->bulk_stage;
   x->fitness_max_range = h->fitness_max_range;
   x->knn_fine_rings = h->knn_fine_rings;
   x->knn_leaf_parts = h->knn_leaf_parts;

@@ -67,7 +67,13 @@ struct CloudSetView {
   // there is no cell table and no pyramid. lbox == nullptr: grid mode.
   float4* lbox;               // 2 float4 per leaf (lo, hi)
   const int* leaf_off;        // [n_clouds+1] offsets into lbox / 2 (cloud c owns ceil(n_c / 32) leaves)
+  // The shared-memory IMAGE of every cloud, written by the leaf build: kLeafImage float4 per leaf, cloud c at limg + kLeafImage * leaf_off[c],
+  // [nleaf * 32 float4: points in the pair layout of apd_leaf.cuh][nleaf * 2 float4: boxes] - byte for byte what the search kernels keep in
+  // shared memory, so staging a cloud is ONE bulk asynchronous copy (cp.async.bulk -> mbarrier, apd_leaf.cuh leaf_stage_bulk) instead of
+  // a load / negate / interleave / store loop through registers. nullptr: option "bulk_stage" off (the register path, leaf_stage).
+  float4* limg;
 };
+constexpr int kLeafImage = 34;  // float4 per leaf in limg: 32 points + 2 box corners
 
 #ifdef __CUDACC__
 __device__ __forceinline__ GridView<unsigned> coarse_view(const CloudSetView& cs, int level, int cloud) {

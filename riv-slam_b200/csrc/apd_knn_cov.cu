@@ -354,7 +354,16 @@ knn_cov_leaf_kernel(CloudSetView cs, const int4* __restrict__ tiles, int k, int 
   float4* sP = reinterpret_cast<float4*>(smem_raw);
   float4* sbox = sP + (size_t)L.nleaf * kLeaf;
   unsigned* s_list = reinterpret_cast<unsigned*>(sbox + 2 * (size_t)L.nleaf);
-  leaf_stage(sP, sbox, cs.spts + base, cs.lbox + 2 * (size_t)cs.leaf_off[c], n);
+  __shared__ unsigned long long s_stage_bar;
+  if (cs.limg) {
+    // one bulk asynchronous copy of the image the build wrote (points in the pair layout + boxes), completion on an mbarrier
+    unsigned parity = 0u;
+    if (threadIdx.x == 0) mbar_init(&s_stage_bar, 1u);
+    __syncthreads();
+    leaf_stage_bulk(sP, cs.limg + (size_t)kLeafImage * cs.leaf_off[c], n, &s_stage_bar, parity);
+  } else {
+    leaf_stage(sP, sbox, cs.spts + base, cs.lbox + 2 * (size_t)cs.leaf_off[c], n);
+  }
   L.P = sP;
   L.box = sbox;
   __syncthreads();

@@ -109,6 +109,51 @@ __device__ __forceinline__ void leaf_stage(float4* __restrict__ sP, float4* __re
   for (int j = threadIdx.x; j < 2 * nleaf; j += blockDim.x) sbox[j] = gbox[j];
 }
 
+// ---- staging by the copy engine: cp.async.bulk (global -> shared, completion on an mbarrier) of the image the leaf build wrote ----
+// One elected thread arms the barrier with the byte count and issues the copy; every thread then waits on the barrier's phase. The
+// bytes never pass through registers or the LSU, the issuing warp is free at once, and the data lands in the async proxy's order:
+// the mbarrier wait is what makes it visible to the generic-proxy loads that follow. SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LEAF_MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LEAF_MBAR_DONE_%=;\n"
+      "bra LEAF_MBAR_WAIT_%=;\n"
+      "LEAF_MBAR_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// Whole CTA; the caller has synchronised the CTA since the last read of the destination. `image` = limg of the cloud (16-byte aligned),
+// the destination receives leaf_stage_bytes(n) bytes: points in the pair layout, then the boxes. Returns after the data is visible.
+__device__ __forceinline__ void leaf_stage_bulk(float4* __restrict__ sP, const float4* __restrict__ image, int n, unsigned long long* bar, unsigned& parity) {
+  const unsigned bytes = (unsigned)leaf_stage_bytes(n);
+  if (bytes == 0) return;
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses of the destination are ordered before the copy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sP)), "l"(image), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+  }
+  mbar_wait(bar, parity);
+  parity ^= 1u;
+}
+// The build's side: one leaf's 32 sorted points (lane = slot in the leaf, idx = original index, 0x7FFFF and NaN coordinates beyond n)
+// written into the image in the pair layout: even lanes store (-x0, -x1, -y0, -y1), odd lanes (-z0, -z1, tag0, tag1).
+__device__ __forceinline__ void leaf_image_store_points(float4* __restrict__ image, int slot, float x, float y, float z, unsigned idx, int lane) {
+  const unsigned tag = idx << kLeafPosBits | (unsigned)slot;
+  const float px = __shfl_xor_sync(0xFFFFFFFFu, x, 1), py = __shfl_xor_sync(0xFFFFFFFFu, y, 1), pz = __shfl_xor_sync(0xFFFFFFFFu, z, 1);
+  const unsigned ptag = __shfl_xor_sync(0xFFFFFFFFu, tag, 1);
+  image[slot] = (lane & 1) ? make_float4(-pz, -z, __uint_as_float(ptag), __uint_as_float(tag)) : make_float4(-x, -px, -y, -py);
+}
+
 // the point in slot `pos` of a staged cloud: (x, y, z, tag bits); tag >> 13 = original index
 __device__ __forceinline__ float4 leaf_point(const LeafView& L, int pos) {
   const float4 A = L.P[2 * (pos >> 1)], B = L.P[2 * (pos >> 1) + 1];

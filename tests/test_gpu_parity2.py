@@ -425,3 +425,47 @@ def test_leaf_knn_warp_parts_give_identical_results():
     for parts in (2, 4, 8):
         assert np.array_equal(got[parts][0], got[1][0])
         assert np.array_equal(got[parts][1], got[1][1])   # bit-identical covariances
+
+
+# ---------------------------------------------------------------- staging by the copy engine
+
+def test_bulk_staging_is_bit_identical_to_the_register_path(small_pair):
+    """Leaf-mode clouds reach shared memory by ONE cp.async.bulk of the image the build wrote (option "bulk_stage", default on)
+    instead of a load / negate / interleave / store loop. Same bytes in shared memory, so everything downstream is bit-identical:
+    kNN, covariances, H / b, whole registrations for every team shape, a batch in which every CTA stages many targets in turn
+    (the mbarrier's phase flips per staging), and the stand-alone fitness kernel."""
+    from riv_slam_b200 import datagen
+    from riv_slam_b200 import fast_apdgicp as F
+    src, tgt, _ = small_pair
+    outs = []
+    for bulk in (1, 0):
+        r = {}
+        for team in (0, 1, 4):
+            g = _gpu(LAUNCH_PARAMS)
+            g.setOption("bulk_stage", bulk)
+            g.setOption("team_size", team)
+            g.setInputSource(src); g.setInputTarget(tgt)
+            r[f"knn{team}"] = g.getKnn(0).copy()
+            r[f"cov{team}"] = g.getTargetCovariances().copy()
+            e, H, b = g.evaluateCost(np.eye(4))
+            r[f"lin{team}"] = np.r_[e, H.ravel(), b]
+            g.align(want_output=False)
+            r[f"T{team}"] = g.getFinalTransformation().copy()
+            r[f"fit{team}"] = np.array([g.getFitnessScore(), g.getFitnessScore(1.5), g.nr_iterations()])
+            r[f"trace{team}"] = g.getLMTrace().copy()
+        H = F.Handle(0)
+        H.set_params(**LAUNCH_PARAMS)
+        H.set_option("bulk_stage", bulk)
+        pairs = [datagen.make_pair(2, i % 7, n_src=900 + 37 * (i % 5)) for i in range(14)]
+        srcs = [pairs[i % 14][0] for i in range(330)]     # 330 pairs on 148 SMs: every CTA stages two or three different targets
+        tgts = [pairs[(i * 5) % 14][1] for i in range(330)]
+        res = F.batch_align(H, srcs, tgts)
+        r["batch_T"] = np.array(res["T"]); r["batch_fit"] = np.array(res["fitness"]); r["batch_it"] = np.array(res["iterations"])
+        cs_s, cs_t = F.CloudSet(H, srcs[:40]), F.CloudSet(H, tgts[:40])
+        r["fitness_pairs"] = np.array(F.fitness_pairs(H, cs_s, cs_t, poses=np.tile(np.eye(4, dtype=np.float32), (40, 1, 1))))
+        outs.append(r)
+    a, b = outs
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
+    assert (a["batch_it"] > 0).all()
