@@ -53,3 +53,15 @@ H2.set_params(**LAUNCH_PARAMS)
 H2.set_option("smem_build", 0)
 print(F.batch_align(H2, [src, tgt[:500]], [tgt, src])["iterations"])
 print("done")
+
+# pcl::ApproximateVoxelGrid path (single-CTA radix sort + run scan) and the register staging path (bulk_stage off)
+raw = np.concatenate([np.asarray(src[:, :3], np.float32), np.random.default_rng(0).uniform(0, 30, (len(src), 1)).astype(np.float32)], axis=1)
+Hh = F.Handle(0)
+print("approx voxel grid", len(F.preprocess(Hh, raw, downsample_method="APPROX_VOXELGRID", downsample_resolution=0.5)))
+F.set_downsample_method(Hh, "VOXELGRID")
+r = F.FastAPDGICP(0)
+r.handle().set_params(**LAUNCH_PARAMS)
+r.setOption("bulk_stage", 0)
+r.setInputTarget(tgt, cache_key=901); r.setInputSource(src, cache_key=902)
+r.align(want_output=False); r.getFitnessScore(1.0)
+print("register staging", r.hasConverged(), r.nr_iterations())
