@@ -654,8 +654,8 @@ __global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_co
       pair = S.pair;
     }
     if (pair >= B.n_pairs) break;
-    const int s = B.src_idx ? B.src_idx[pair] : pair;
-    const int t = B.tgt_idx ? B.tgt_idx[pair] : pair;
+    const int s = B.src_idx ? B.src_idx[pair] : pair + B.src_base;
+    const int t = B.tgt_idx ? B.tgt_idx[pair] : pair + B.tgt_base;
     const int sb = B.src.pt_off[s], ns = B.src.pt_off[s + 1] - sb;
     const int tb = B.tgt.pt_off[t], nt = B.tgt.pt_off[t + 1] - tb;
     const float4* sspts = B.src.spts + sb;

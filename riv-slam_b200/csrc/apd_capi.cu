@@ -3,6 +3,7 @@
 // every entry point either moves bytes or enqueues the kernels of apd_build.cu / apd_knn_cov.cu /
 // apd_align.cu on the handle's stream. There is no CPU fallback; without a device apd_create fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -189,6 +190,7 @@ struct apd_context {
   int timeline_opt = 0;  // profiling aid: the align kernel stamps its phases (apd_get_timeline)
   // kernel timing (option "kernel_timing"): CUDA events around the hot launches, on the stream they are launched on
   int kernel_timing = 0;
+  int pipeline_mem = APD_MEM_HOST;  // option "pipeline_device_input": apd_odometry_align / apd_batch_align read their point arrays from device memory
   bool bulk_stage = true;     // option "bulk_stage": leaf-mode clouds are staged by one cp.async.bulk from the image the build wrote (0: register path)
   int downsample_method = 0;  // option "downsample_method": 0 = VOXELGRID (pcl::VoxelGrid), 1 = APPROX_VOXELGRID (pcl::ApproximateVoxelGrid)
   struct TimedLaunch { int kind; cudaEvent_t e0, e1; };
@@ -213,6 +215,14 @@ struct apd_context {
   std::map<std::tuple<int, int, bool, size_t>, int> team_fit;  // cached occupancy answers (max_teams_cached)
   unsigned char* down_host = nullptr;  // pinned landing area of apd_align's result block
   apd_handle helper = nullptr;   // second stream/pool for pipelined batches (pipelined_align)
+  // upload-ahead of pipelined host batches: the whole input array crosses PCIe on a copy stream of its own, one event per chunk
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
+  DevBuf raw_all[2];
+  bool upload_ahead = true;      // option "upload_ahead"
+  int pipe_chunks = 4, pipe_first_waves = 1;   // options "pipeline_chunks" / "pipeline_first_waves" (pipelined_align)
+  bool kernel_uploads = false;      // stage_upload fetches its block with a kernel instead of the copy engine (set while a call uploads ahead)
+  cudaEvent_t fill_wait = nullptr;  // make_cloudset: the stream waits for this event between the table upload and the first read of the points
   long long helper_launches_seen = 0;
 };
 
@@ -298,6 +308,15 @@ size_t staging_budget(apd_handle h) { return h->smem_optin - align_static_smem()
 // buffer, one asynchronous copy moves them. The buffer is reused by the next call, so its previous copy must have
 // completed (an event, normally long signalled); no stream synchronisation is needed and the caller's own host
 // vectors may die at once.
+// While pipelined_align's copy stream keeps the host-to-device copy engine busy with the call's points, a small copy submitted on
+// another stream is not served before that stream runs dry (measured: a chunk's 2 KB table block waited for 110 MB of points). The
+// staging buffer is page-locked, i.e. readable by the SMs through the unified address space: such blocks are then fetched by a
+// kernel (option / handle flag kernel_uploads), which needs no copy engine at all.
+__global__ void host_block_fetch_kernel(unsigned* __restrict__ dst, const unsigned* __restrict__ src_host, size_t n_words) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_words) dst[i] = src_host[i];
+}
+
 template <typename Fill>
 int stage_upload(apd_handle h, int slot, size_t bytes, Fill fill, void* dst) {
   if (bytes == 0) return APD_OK;
@@ -312,7 +331,14 @@ int stage_upload(apd_handle h, int slot, size_t bytes, Fill fill, void* dst) {
     h->stage_cap[slot] = want;
   }
   fill(h->stage_host[slot]);
-  CK(cudaMemcpyAsync(dst, h->stage_host[slot], bytes, cudaMemcpyHostToDevice, h->stream));
+  if (h->kernel_uploads && bytes % 4 == 0 && bytes <= (256u << 10)) {
+    const size_t words = bytes / 4;
+    host_block_fetch_kernel<<<(unsigned)((words + 255) / 256), 256, 0, h->stream>>>(static_cast<unsigned*>(dst), reinterpret_cast<const unsigned*>(h->stage_host[slot]), words);
+    h->stats.launches++;
+    CK(cudaGetLastError());
+  } else {
+    CK(cudaMemcpyAsync(dst, h->stage_host[slot], bytes, cudaMemcpyHostToDevice, h->stream));
+  }
   CK(cudaEventRecord(h->stage_ev[slot], h->stream));
   return APD_OK;
 }
@@ -585,6 +611,11 @@ int make_cloudset(apd_handle h, const float* xyz, int stride_bytes, const int32_
   int rc = cloudset_layout(h, cs.get(), force_grid);
   if (rc) return rc;
   const float* first = xyz ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(xyz) + (size_t)(n_clouds ? offsets[0] : 0) * stride_bytes) : nullptr;
+  if (h->fill_wait) {   // upload-ahead (pipelined_align): the tables above are already on their way; only the points wait for the copy stream
+    cudaEvent_t e = h->fill_wait;
+    h->fill_wait = nullptr;
+    CK(cudaStreamWaitEvent(h->stream, e, 0));
+  }
   rc = cloudset_fill(h, cs.get(), first, stride_bytes, mem);
   if (rc) return rc;
   *out = cs;
@@ -686,6 +717,7 @@ int plan_teams(apd_handle h, const apd_cloudset_s* src, const apd_cloudset_s* tg
 struct AlignCall {
   apd_cloudset_s *src, *tgt;
   const int32_t *src_idx = nullptr, *tgt_idx = nullptr;  // host
+  int src_base = 0, tgt_base = 0;                        // without index arrays: pair p = cloud p + src_base onto cloud p + tgt_base
   const float* guesses = nullptr;                        // host, n_pairs*16
   const double* guesses64 = nullptr;                     // host, n_pairs*16 (wins over guesses)
   int n_pairs = 0;
@@ -743,6 +775,8 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
   memset(&b, 0, sizeof(b));
   b.src = c.src->view();
   b.tgt = c.tgt->view();
+  b.src_base = c.src_base;
+  b.tgt_base = c.tgt_base;
   if (c.src_idx) {
     CK(h->idx_src.reserve(sizeof(int) * np));
     CK(cudaMemcpyAsync(h->idx_src.p, c.src_idx, sizeof(int) * np, cudaMemcpyHostToDevice, h->stream));
@@ -759,7 +793,14 @@ int run_align(apd_handle h, const AlignCall& c, AlignBatch* used = nullptr, Team
     b.guesses64 = h->guesses.as<double>();
   } else if (c.guesses) {
     CK(h->guesses.reserve(sizeof(float) * 16 * np));
-    CK(cudaMemcpyAsync(h->guesses.p, c.guesses, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, h->stream));
+    if (h->kernel_uploads) {  // the copy engine is busy with the call's points (pipelined_align): through the pinned staging block and a kernel
+      const float* g = c.guesses;
+      const size_t gb = sizeof(float) * 16 * np;
+      int rcg = stage_upload(h, 1, gb, [&](unsigned char* host) { memcpy(host, g, gb); }, h->guesses.p);
+      if (rcg) return rcg;
+    } else {
+      CK(cudaMemcpyAsync(h->guesses.p, c.guesses, sizeof(float) * 16 * np, cudaMemcpyHostToDevice, h->stream));
+    }
     b.guesses = h->guesses.as<float>();
   }
   if (c.block) {
@@ -928,6 +969,8 @@ int apd_destroy(apd_handle h) {
   h->src.reset();
   h->tgt.reset();
   if (h->helper) apd_destroy(h->helper);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  for (auto& e : h->copy_events) cudaEventDestroy(e);
   for (int i = 0; i < 2; i++) {
     if (h->stage_host[i]) cudaFreeHost(h->stage_host[i]);
     if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
@@ -986,6 +1029,10 @@ int apd_set_option(apd_handle h, const char* name, double value) {
     h->knn_leaf_parts = v;
   }
   else if (n == "kernel_timing") h->kernel_timing = value != 0;
+  else if (n == "upload_ahead") h->upload_ahead = value != 0;
+  else if (n == "pipeline_chunks") h->pipe_chunks = std::max(1, (int)value);
+  else if (n == "pipeline_first_waves") h->pipe_first_waves = std::max(1, (int)value);
+  else if (n == "pipeline_device_input") h->pipeline_mem = value != 0 ? APD_MEM_DEVICE : APD_MEM_HOST;
   else if (n == "bulk_stage") h->bulk_stage = value != 0;   // takes effect for cloud sets made afterwards
   else if (n == "downsample_method") {   // the rosparam of preprocessing_nodelet.cpp:137 / scan_matching_odometry_nodelet.cpp:149 (NONE = downsample_resolution <= 0)
     if (value != 0 && value != 1) return fail(h, APD_ERR_UNSUPPORTED, "downsample_method must be 0 (VOXELGRID) or 1 (APPROX_VOXELGRID)");
@@ -1614,7 +1661,7 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
                     int n_pairs, apd_result* out, bool odometry) {
   // about four chunks per call, each a whole number of waves of one-pair-per-SM teams: enough to hide
   // all but the first upload, few enough that launch tails and per-chunk host work stay small
-  int kChunkPairs = std::max(kMinChunkPairs, (n_pairs + 3) / 4);
+  int kChunkPairs = std::max(kMinChunkPairs, (n_pairs + h->pipe_chunks - 1) / h->pipe_chunks);
   kChunkPairs = (kChunkPairs + h->sm_count - 1) / h->sm_count * h->sm_count;
   ChunkSlot slots[2];
   slots[0].h = h;
@@ -1635,35 +1682,135 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
     }
   } drain{slots};
   // the first chunk's upload is the one nothing can hide: keep it to a single wave of teams when the batch is large
-  const int first_pairs = (slots[1].h && n_pairs > 3 * h->sm_count) ? h->sm_count : kChunkPairs;  // measured: 74 / 148 / 256 pairs -> 12.85 / 12.31 / 12.54 ms per 1000 pairs
+  const int first_pairs = (slots[1].h && n_pairs > 3 * h->sm_count) ? std::min(kChunkPairs, h->pipe_first_waves * h->sm_count) : kChunkPairs;  // measured: 74 / 148 / 256 pairs -> 12.85 / 12.31 / 12.54 ms per 1000 pairs
   // A chunk of np odometry pairs holds np + 1 scans, and the kNN kernel takes whole scans per CTA, one CTA per SM: 297 scans are
   // three waves where 296 are two (a 1000-pair call ran 2 + 3 + 3 + 2 = 10 waves of kNN instead of 7, +1.4 ms). Odometry chunks
   // therefore hold one pair less than a multiple of the SM count.
   const int odo = odometry && n_pairs > kChunkPairs ? 1 : 0;
-  for (int p0 = 0, np = 0; p0 < n_pairs; p0 += np, chunk++) {
-    np = std::min((chunk == 0 ? first_pairs : kChunkPairs) - odo, n_pairs - p0);
+  // the chunks of this call
+  std::vector<std::pair<int, int>> chunks;  // (first pair, pairs)
+  // Sizes ramp up geometrically from the first wave: chunk k + 1's points must have crossed the link by the time chunk k's kernels
+  // finish, and a pair uploads in about half the time it computes (C4: 320 KB at 54 GB/s = 5.9 us against 11.4 us), so a chunk may be
+  // twice its predecessor but not seven times (measured on C4: 148 then 1036 pairs left the GPU idle for 3.9 ms of a 52 ms call).
+  for (int p0 = 0, np = 0, cap = first_pairs; p0 < n_pairs; p0 += np, cap = std::min(kChunkPairs, 2 * cap)) {
+    np = std::min(cap - odo, n_pairs - p0);
+    chunks.emplace_back(p0, np);
+  }
+  // UPLOAD-AHEAD. With per-chunk uploads on the chunk's own stream, chunk k + 2 cannot start crossing PCIe before chunk k has been
+  // retired (its slot is reused), and the measured timeline (APD_PIPE_TRACE) showed SMs waiting for points twice per call. The input
+  // is one contiguous host array, so when it is page-locked the whole of it is sent at once on a copy stream of its own, in chunk
+  // order, with an event behind every chunk's last byte; a chunk's stream only waits for its event. The link then runs at full rate
+  // from the first microsecond of the call, whatever the kernels do (device raw buffers: stride_bytes per point, the caller's layout).
+  // The copy engine serves its queue in submission order ACROSS streams, and every chunk's cloud set sends a small table block
+  // through the same engine: chunk k's big copy is therefore submitted just before chunk k's tables (k = 0, 1), and everything
+  // that is left right after chunk 1 has been enqueued (measured: with all copies submitted up front the first kernel of the call
+  // waited 2.9 ms for its 2 KB of tables behind 160 MB of points).
+  struct Uploader {
+    int n_arrays = 0, stride = 0, next = 0;
+    bool odometry = false;
+    const char* host_base[2] = {nullptr, nullptr};
+    char* dev_base[2] = {nullptr, nullptr};
+    const int32_t* offs[2] = {nullptr, nullptr};
+    size_t sent[2] = {0, 0};
+    cudaError_t submit_through(int k, const std::vector<std::pair<int, int>>& chunks, apd_handle h) {
+      for (; next <= k && next < (int)chunks.size(); next++) {
+        const int end_cloud = chunks[next].first + chunks[next].second + (odometry ? 1 : 0);   // clouds [.., end_cloud) must be on the device
+        for (int a = 0; a < n_arrays; a++) {
+          const size_t upto = (size_t)offs[a][end_cloud] * stride;
+          if (upto > sent[a]) {
+            cudaError_t e = cudaMemcpyAsync(dev_base[a] + sent[a], host_base[a] + sent[a], upto - sent[a], cudaMemcpyHostToDevice, h->copy_stream);
+            if (e != cudaSuccess) return e;
+            sent[a] = upto;
+          }
+        }
+        cudaError_t e = cudaEventRecord(h->copy_events[next], h->copy_stream);
+        if (e != cudaSuccess) return e;
+      }
+      return cudaSuccess;
+    }
+  } up;
+  up.stride = stride_bytes;
+  up.odometry = odometry;
+  int mem_in = h->pipeline_mem;
+  const float* dev_src = pts_src;
+  const float* dev_tgt = pts_tgt;
+  bool ahead = false;
+  if (mem_in == APD_MEM_HOST && h->upload_ahead && slots[1].h && chunks.size() > 1) {
+    cudaPointerAttributes at{};
+    const bool pinned_s = cudaPointerGetAttributes(&at, pts_src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    const bool pinned_t = odometry || (cudaPointerGetAttributes(&at, pts_tgt) == cudaSuccess && at.type == cudaMemoryTypeHost);
+    cudaGetLastError();
+    ahead = pinned_s && pinned_t;
+  }
+  if (ahead) {
+    if (!h->copy_stream) CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    while (h->copy_events.size() < chunks.size()) {
+      cudaEvent_t e;
+      CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->copy_events.push_back(e);
+    }
+    const int n_arrays = odometry ? 1 : 2;
+    const float* host_base[2] = {pts_src, pts_tgt};
+    const int32_t* offs[2] = {off_src, off_tgt};
+    const int last_cloud = odometry ? n_pairs : n_pairs - 1;   // index of the last cloud a pair touches
+    const char* dev_base[2] = {nullptr, nullptr};
+    for (int a = 0; a < n_arrays; a++) {
+      const size_t first_byte = (size_t)offs[a][0] * stride_bytes, end_byte = (size_t)offs[a][last_cloud + 1] * stride_bytes;
+      CK(h->raw_all[a].reserve(std::max<size_t>(end_byte - first_byte, 16) + 16));
+      dev_base[a] = static_cast<const char*>(h->raw_all[a].p) - first_byte;   // so that dev_base + offset * stride addresses like the host array
+    }
+    up.n_arrays = n_arrays;
+    for (int a = 0; a < 2; a++) { up.host_base[a] = reinterpret_cast<const char*>(host_base[a]); up.dev_base[a] = const_cast<char*>(dev_base[a]); up.offs[a] = offs[a]; }
+    up.sent[0] = (size_t)offs[0][0] * stride_bytes;
+    up.sent[1] = odometry ? 0 : (size_t)offs[1][0] * stride_bytes;
+    dev_src = reinterpret_cast<const float*>(dev_base[0]);
+    dev_tgt = odometry ? nullptr : reinterpret_cast<const float*>(dev_base[1]);
+    mem_in = APD_MEM_DEVICE;
+  }
+  struct DrainCopy {
+    apd_handle h; bool on;
+    ~DrainCopy() {
+      if (on && h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+      h->kernel_uploads = false;
+      if (h->helper) h->helper->kernel_uploads = false;
+    }
+  } drain_copy{h, ahead};
+  if (ahead) h->kernel_uploads = slots[1].h->kernel_uploads = true;
+  // APD_PIPE_TRACE=1: host and device time stamps of every chunk on stderr (diagnostic)
+  static const bool trace = getenv("APD_PIPE_TRACE") != nullptr;
+  struct Tr { double h0, h1, h2, h3; cudaEvent_t e0, e1, e2; int np; };
+  std::vector<Tr> tr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  for (chunk = 0; chunk < (int)chunks.size(); chunk++) {
+    const int p0 = chunks[chunk].first, np = chunks[chunk].second;
     ChunkSlot& s = slots[slots[1].h ? (chunk & 1) : 0];
+    Tr t{};
+    if (trace) t.h0 = now();
     int rc = retire(h, s, &lin, &err);
     if (rc) return rc;
     apd_handle hc = s.h;
+    if (trace) { t.h1 = now(); t.np = np; cudaEventCreate(&t.e0); cudaEventCreate(&t.e1); cudaEventCreate(&t.e2); cudaEventRecord(t.e0, hc->stream); }
+    if (ahead) {
+      CK(up.submit_through(chunk, chunks, h));
+      hc->fill_wait = h->copy_events[chunk];   // consumed by the first make_cloudset below, after its table upload
+    }
     AlignCall c;
     if (odometry) {
-      rc = make_cloudset(hc, pts_src, stride_bytes, off_src + p0, np + 1, APD_MEM_HOST, &s.a);
+      rc = make_cloudset(hc, dev_src, stride_bytes, off_src + p0, np + 1, mem_in, &s.a);
       if (rc) return hc == h ? rc : fail(h, rc, hc->err);
-      idx_s.resize(np);
-      idx_t.resize(np);
-      for (int i = 0; i < np; i++) { idx_s[i] = i + 1; idx_t[i] = i; }
       c.src = c.tgt = s.a.get();
-      c.src_idx = idx_s.data();
-      c.tgt_idx = idx_t.data();
+      c.src_base = 1;   // pair i: scan i + 1 onto scan i; no index arrays to upload
+      c.tgt_base = 0;
     } else {
-      rc = make_cloudset(hc, pts_src, stride_bytes, off_src + p0, np, APD_MEM_HOST, &s.a);
+      rc = make_cloudset(hc, dev_src, stride_bytes, off_src + p0, np, mem_in, &s.a);
       if (rc) return hc == h ? rc : fail(h, rc, hc->err);
-      rc = make_cloudset(hc, pts_tgt, stride_bytes, off_tgt + p0, np, APD_MEM_HOST, &s.b);
+      if (ahead) hc->fill_wait = h->copy_events[chunk];
+      rc = make_cloudset(hc, dev_tgt, stride_bytes, off_tgt + p0, np, mem_in, &s.b);
       if (rc) return hc == h ? rc : fail(h, rc, hc->err);
       c.src = s.a.get();
       c.tgt = s.b.get();
     }
+    if (trace) { t.h2 = now(); cudaEventRecord(t.e1, hc->stream); }
     c.guesses = guesses ? guesses + (size_t)p0 * 16 : nullptr;
     c.n_pairs = np;
     c.plan_for_pairs = n_pairs;
@@ -1676,10 +1823,23 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
       return fail(h, APD_ERR_CUDA, "result copy failed");
     }
     s.pairs = np;
+    if (ahead) CK(up.submit_through(chunk >= 1 ? (int)chunks.size() - 1 : chunk + 1, chunks, h));
+    if (trace) { t.h3 = now(); cudaEventRecord(t.e2, hc->stream); tr.push_back(t); }
   }
   for (ChunkSlot& s : slots) {
     int rc = retire(h, s, &lin, &err);
     if (rc) return rc;
+  }
+  if (trace && !tr.empty()) {
+    const double hend = now();
+    for (size_t i = 0; i < tr.size(); i++) {
+      float a = 0, b = 0, c2 = 0;
+      cudaEventElapsedTime(&a, tr[0].e0, tr[i].e0); cudaEventElapsedTime(&b, tr[0].e0, tr[i].e1); cudaEventElapsedTime(&c2, tr[0].e0, tr[i].e2);
+      fprintf(stderr, "chunk %zu pairs %d | host: enter %.3f retired %.3f prepared-enqueued %.3f align-enqueued %.3f | device: start %.3f upload+build+knn done %.3f align+d2h done %.3f\n", i,
+              tr[i].np, tr[i].h0 - tr[0].h0, tr[i].h1 - tr[0].h0, tr[i].h2 - tr[0].h0, tr[i].h3 - tr[0].h0, a, b, c2);
+    }
+    fprintf(stderr, "call returned at host %.3f ms\n", hend - tr[0].h0);
+    for (Tr& t : tr) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); cudaEventDestroy(t.e2); }
   }
   h->work_lin = lin;
   h->work_err = err;

@@ -181,6 +181,7 @@ struct AlignBatch {
   CloudSetView src, tgt;
   const int* src_idx;      // [n_pairs] or nullptr (identity map)
   const int* tgt_idx;
+  int src_base, tgt_base;  // without an index array pair p registers cloud p + src_base onto cloud p + tgt_base (odometry: 1 and 0)
   const float* guesses;    // [n_pairs*16] row-major or nullptr (identity)
   const double* guesses64; // [n_pairs*16] row-major double poses (the protected linearize / compute_error hooks take an Isometry3d); wins over guesses
   apd_result* out;         // [n_pairs] device
