@@ -469,3 +469,51 @@ def test_bulk_staging_is_bit_identical_to_the_register_path(small_pair):
     for k in a:
         assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
     assert (a["batch_it"] > 0).all()
+
+
+# ---------------------------------------------------------------- the host pipeline's upload-ahead path
+
+def test_upload_ahead_pipeline_is_bit_identical():
+    """apd_odometry_align / apd_batch_align on PAGE-LOCKED input send the whole array ahead on a copy stream, fetch their table blocks
+    and guesses with a kernel and address odometry pairs by index bases; pageable input (and option upload_ahead = 0) keeps the
+    per-chunk path. Same records, bit for bit, with and without initial guesses, and equal to one un-pipelined launch."""
+    import ctypes as C
+    import torch
+    from riv_slam_b200 import datagen
+    from riv_slam_b200 import fast_apdgicp as F
+    n_scans = 701                                            # 700 pairs: chunks of 147, 295, 258
+    base, _ = datagen.make_drive(2, 5, 24, 700, workers=4)
+    scans = [base[i % 24] for i in range(n_scans)]
+    pts, off = F._ragged([np.ascontiguousarray(s[:, :4]) for s in scans])
+    pinned = torch.from_numpy(pts.copy()).pin_memory()
+    rng = np.random.default_rng(3)
+    guesses = np.tile(np.eye(4, dtype=np.float32), (n_scans - 1, 1, 1))
+    guesses[:, :3, 3] += rng.normal(0, 0.05, (n_scans - 1, 3)).astype(np.float32)
+    H = F.Handle(0)
+    H.set_params(**LAUNCH_PARAMS)
+
+    def run(points, ahead, g):
+        H.set_option("upload_ahead", ahead)
+        return F.odometry_align(H, (points, off), guesses=g).copy()
+
+    for g in (None, guesses):
+        a = run(pinned, 1, g)                                # page-locked: upload-ahead
+        b = run(pinned, 0, g)                                # page-locked, per-chunk uploads
+        c = run(pts, 1, g)                                   # pageable: per-chunk uploads whatever the option says
+        assert a.tobytes() == b.tobytes() == c.tobytes()
+        assert (a["status"] == 0).all() and (a["iterations"] >= 0).all()
+        cs = F.CloudSet(H, [np.ascontiguousarray(s[:, :4]) for s in scans])
+        idx = np.arange(n_scans - 1, dtype=np.int32)
+        one = F.align_pairs(H, cs, cs, src_idx=idx + 1, tgt_idx=idx, guesses=g)
+        assert np.array_equal(one["T"], a["T"]) and np.array_equal(one["iterations"], a["iterations"]) and np.array_equal(one["fitness"], a["fitness"])
+    # the batch entry point: separate source and target arrays, both page-locked
+    src_pts, src_off = F._ragged([np.ascontiguousarray(s[:, :4]) for s in scans[1:]])
+    tgt_pts, tgt_off = F._ragged([np.ascontiguousarray(s[:, :4]) for s in scans[:-1]])
+    ps, pt = torch.from_numpy(src_pts.copy()).pin_memory(), torch.from_numpy(tgt_pts.copy()).pin_memory()
+    res = np.zeros(n_scans - 1, dtype=F.RESULT_DTYPE)
+    ip = C.POINTER(C.c_int32)
+    for ahead in (1, 0):
+        H.set_option("upload_ahead", ahead)
+        H.check(H.L.apd_batch_align(H.h, C.c_void_p(ps.data_ptr()), src_off.ctypes.data_as(ip), C.c_void_p(pt.data_ptr()), tgt_off.ctypes.data_as(ip), 16,
+                                    guesses.ctypes.data_as(C.POINTER(C.c_float)), n_scans - 1, C.c_void_p(res.ctypes.data)))
+        assert res.tobytes() == a.tobytes()
