@@ -1735,7 +1735,10 @@ int pipelined_align(apd_handle h, const float* pts_src, const int32_t* off_src, 
   const float* dev_src = pts_src;
   const float* dev_tgt = pts_tgt;
   bool ahead = false;
-  if (mem_in == APD_MEM_HOST && h->upload_ahead && slots[1].h && chunks.size() > 1) {
+  // (the device copy of the raw input is bounded: beyond 4 GB a call keeps the per-chunk path, whose staging buffer is one chunk long)
+  const int last_cloud_in = odometry ? n_pairs : n_pairs - 1;
+  const size_t raw_total = (size_t)(off_src[last_cloud_in + 1] - off_src[0]) * stride_bytes + (odometry ? 0 : (size_t)(off_tgt[last_cloud_in + 1] - off_tgt[0]) * stride_bytes);
+  if (mem_in == APD_MEM_HOST && h->upload_ahead && slots[1].h && chunks.size() > 1 && raw_total <= ((size_t)4 << 30)) {
     cudaPointerAttributes at{};
     const bool pinned_s = cudaPointerGetAttributes(&at, pts_src) == cudaSuccess && at.type == cudaMemoryTypeHost;
     const bool pinned_t = odometry || (cudaPointerGetAttributes(&at, pts_tgt) == cudaSuccess && at.type == cudaMemoryTypeHost);
