@@ -617,7 +617,7 @@ __device__ __forceinline__ void fitness_pass(const AlignBatch& B, AlignShared& S
 }
 
 template <int TEAM, bool STAGED>
-__global__ void __launch_bounds__(kAlignThreads, 1) align_kernel(const __grid_constant__ AlignBatch B) {
+__global__ void __launch_bounds__(kAlignThreads, APD_ALIGN_MIN_BLOCKS) align_kernel(const __grid_constant__ AlignBatch B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ AlignShared S;
   typedef unsigned CellT;  // grid mode reads the 32-bit cell table from HBM; leaf mode (STAGED) has no cell table at all

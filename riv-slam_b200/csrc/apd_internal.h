@@ -171,6 +171,9 @@ enum TeamKind { TEAM_CTA = 0, TEAM_CLUSTER = 1, TEAM_GRID = 2 };
 #define APD_ALIGN_THREADS 512
 #endif
 constexpr int kAlignThreads = APD_ALIGN_THREADS;
+#ifndef APD_ALIGN_MIN_BLOCKS
+#define APD_ALIGN_MIN_BLOCKS 1   // CTAs per SM the align kernel is compiled for (experiments: 256 threads x 2)
+#endif
 #ifndef APD_KNN_THREADS
 #define APD_KNN_THREADS 640
 #endif
