@@ -28,9 +28,11 @@ def main():
     src, tgt, _ = R.make_pair()
     out = {"version": np.array(refapd.lib().ref_apd_version().decode())}
 
+    clouds = {"src": src, "tgt": tgt}
+
     def fresh(params):
         r = refapd.RefAPD(**params)
-        r.set_source(src); r.set_target(tgt)
+        r.set_source(clouds["src"]); r.set_target(clouds["tgt"])
         return r
 
     for name, p in R.COV_CASES.items():
@@ -86,6 +88,37 @@ def main():
         r = fresh(lm_cases.case_params(name))
         r.set_covariances(0, cov_src); r.set_covariances(1, cov_tgt)
         store_align(f"lm_{name}", r, None)
+
+    # BASELINE size: a 5000-point pair and an odometry chain with swapSourceAndTarget between the pairs
+    s5, t5, _ = R.make_pair5k()
+    r = refapd.RefAPD(**R.LIN_CASES["launch"])
+    r.set_source(s5); r.set_target(t5)
+    assert r.compute_covariances() == 0
+    out["p5k_cov_src"] = r.covariances(0); out["p5k_cov_tgt"] = r.covariances(1)
+    for i, P in enumerate(R.poses()[:2]):
+        e, H, b = r.linearize_d(P)
+        corr, sq = r.correspondences()
+        out[f"p5k_lin_{i}_e"] = np.array(e); out[f"p5k_lin_{i}_H"] = H; out[f"p5k_lin_{i}_b"] = b
+        out[f"p5k_lin_{i}_corr"] = corr; out[f"p5k_lin_{i}_sq"] = sq
+    clouds["src"], clouds["tgt"] = s5, t5
+    store_align("p5k_align", fresh(R.ALIGN_CASES["launch"]), None)
+    store_align("p5k_align_eps_1e-4", fresh(R.ALIGN_CASES["eps_1e-4"]), None)
+    scans = R.make_chain5k()
+    r = refapd.RefAPD(**R.LIN_CASES["launch"])
+    Ts, st = [], []
+    for i in range(1, len(scans)):
+        # the nodelet's own sequence (scan_matching_odometry_nodelet.cpp:449-468, 584-592): setInputTarget(previous) + setInputSource(new).
+        # (After swapSourceAndTarget the reference's getFitnessScore would use PCL's tree_ of the OLD target - swap does not raise
+        # target_cloud_updated_ - see tests/test_reference_apdgicp.py::test_fitness_after_swap_uses_pcls_stale_tree; no RIV-SLAM caller swaps.)
+        r.set_target(scans[i - 1])
+        r.set_source(scans[i])
+        rc, T, conv, it = r.align()
+        assert rc == 0
+        tr = r.trace()
+        assert (np.abs(tr[:, 2] - tr[:, 3]) > 1e-11 * np.abs(tr[:, 2])).all() and (np.abs(tr[:, 4]) > 1e-3).all()
+        Ts.append(T); st.append([int(conv), it, r.fitness()])
+    out["chain5k_T"] = np.array(Ts); out["chain5k_state"] = np.array(st)
+    print("chain:", st)
 
     path = os.path.join(HERE, "apd_ref_golden_v1.npz")
     np.savez_compressed(path, **out)

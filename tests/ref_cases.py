@@ -47,3 +47,20 @@ def guess():
 def make_pair():
     from riv_slam_b200 import datagen
     return datagen.make_pair(PAIR["config"], PAIR["index"], n_src=PAIR["n_src"], n_tgt=PAIR["n_tgt"])
+
+
+# BASELINE.json size: one C2 / C4 pair of 5000-point scans (= test_gpu_parity.pair5k) and a short odometry chain of 5000-point scans in
+# which every scan is target once and source once (scan_matching_odometry_nodelet.cpp:449-468, 584-592)
+PAIR5K = dict(config=4, index=0, n_src=5000)
+CHAIN5K = dict(config=2, index=0, n_scans=5, n_points=5000)
+
+
+def make_pair5k():
+    from riv_slam_b200 import datagen
+    return datagen.make_pair(PAIR5K["config"], PAIR5K["index"], n_src=PAIR5K["n_src"])
+
+
+def make_chain5k():
+    from riv_slam_b200 import datagen
+    scans, _ = datagen.make_drive(CHAIN5K["config"], CHAIN5K["index"], CHAIN5K["n_scans"], CHAIN5K["n_points"], workers=4)
+    return scans

@@ -118,3 +118,45 @@ def test_lm_branches(gold, pair, team):
         g.setSourceCovariances(cov_src); g.setTargetCovariances(lm_cases.injected_target_covariances(name, cov_tgt0))
         got, _ = _run(g)
         check_align(got, gold, f"lm_{name}", t_tol=1e-6, h_tol=REL_TOL)
+
+
+def test_baseline_size_pair_and_chain(gold):
+    """BASELINE.json's size against the reference sources' own results: a 5000-point pair (kNN-dependent covariances, correspondences,
+    H / b, two registrations) and an odometry chain of 5000-point scans through the single-pair call sequence AND through
+    apd_odometry_align (the benchmarked entry point)."""
+    from riv_slam_b200 import fast_apdgicp as F
+    s5, t5, _ = R.make_pair5k()
+    g = _gpu(R.LIN_CASES["launch"], (s5, t5))
+    g.computeCovariances()
+    for C, side in ((g.getSourceCovariances(), "src"), (g.getTargetCovariances(), "tgt")):
+        C1 = gold[f"p5k_cov_{side}"]
+        err = np.abs(C[:, :3, :3] - C1).max(axis=(1, 2)) / np.abs(C1).max(axis=(1, 2))
+        assert (err <= REL_TOL).all() and np.median(err) < 1e-11
+    for i, P in enumerate(R.poses()[:2]):
+        e, H, b = g.linearize(P)
+        corr, sq = g.getCorrespondences()
+        c1 = gold[f"p5k_lin_{i}_corr"]
+        assert np.array_equal(corr, c1) and np.array_equal(sq[c1 >= 0], gold[f"p5k_lin_{i}_sq"][c1 >= 0])
+        assert abs(e - float(gold[f"p5k_lin_{i}_e"])) <= 1e-9 * abs(e) and _rel(H, gold[f"p5k_lin_{i}_H"]) <= 1e-9 and _rel(b, gold[f"p5k_lin_{i}_b"]) <= 1e-9
+    for key, name in (("p5k_align", "launch"), ("p5k_align_eps_1e-4", "eps_1e-4")):
+        got, _ = _run(_gpu(R.ALIGN_CASES[name], (s5, t5)))
+        check_align(got, gold, key, t_tol=1e-6, h_tol=REL_TOL)
+    scans = R.make_chain5k()
+    Tg, st = gold["chain5k_T"], gold["chain5k_state"]
+    reg = F.FastAPDGICP(0)
+    reg.handle().set_params(**R.LIN_CASES["launch"])
+    reg.setInputTarget(scans[0])
+    for i in range(1, len(scans)):
+        if i > 1:
+            reg.swapSourceAndTarget()
+        reg.setInputSource(scans[i])
+        reg.align(want_output=False)
+        assert [int(reg.hasConverged()), reg.nr_iterations()] == list(st[i - 1, :2].astype(int))
+        assert np.abs(reg.getFinalTransformation().astype(np.float64) - Tg[i - 1]).max() <= 1e-6
+        assert abs(reg.getFitnessScore() - st[i - 1, 2]) <= REL_TOL * st[i - 1, 2]
+    H = F.Handle(0)
+    H.set_params(**R.LIN_CASES["launch"])
+    res = F.odometry_align(H, [np.ascontiguousarray(s[:, :4]) for s in scans])
+    assert np.array_equal(res["converged"] != 0, st[:, 0] != 0) and np.array_equal(res["iterations"], st[:, 1].astype(int))
+    assert np.abs(res["T"].reshape(-1, 4, 4).astype(np.float64) - Tg).max() <= 1e-6
+    assert np.allclose(res["fitness"], st[:, 2], rtol=REL_TOL)

@@ -119,3 +119,36 @@ def test_lm_branches(gold, pair):
         check_align(_run(o), gold, f"lm_{name}")
     rej = sum(int((gold[f"lm_{n}_trace"][:, 7] == 0).sum()) for n in lm_cases.CASES)
     assert rej >= 9 and list(gold["lm_lm_failed_1_state"]) == [0, 0, 1] and gold["lm_rejected_but_converged_trace"][-1, 7] == 0
+
+
+def test_baseline_size_pair_and_chain(gold):
+    """BASELINE.json's size: a 5000-point pair (covariances, H / b at two poses, two registrations) and an odometry chain of
+    5000-point scans with swapSourceAndTarget between the pairs, as the reference's own sources computed them."""
+    from oracle.oracle import Oracle
+    s5, t5, _ = R.make_pair5k()
+    o = Oracle(**R.LIN_CASES["launch"])
+    o.set_source(s5); o.set_target(t5)
+    assert o.compute_covariances() == 0
+    for which, side in ((0, "src"), (1, "tgt")):
+        C0, C1 = o.covariances(which), gold[f"p5k_cov_{side}"]
+        assert (np.abs(C0 - C1).max(axis=(1, 2)) <= TIGHT * np.abs(C1).max(axis=(1, 2))).all()
+    for i, P in enumerate(R.poses()[:2]):
+        e, H, b = o.linearize_d(P)
+        corr, sq = o.correspondences()
+        assert np.array_equal(corr, gold[f"p5k_lin_{i}_corr"]) and np.array_equal(sq, gold[f"p5k_lin_{i}_sq"])
+        assert abs(e - float(gold[f"p5k_lin_{i}_e"])) <= TIGHT * abs(e) and _rel(H, gold[f"p5k_lin_{i}_H"]) <= TIGHT and _rel(b, gold[f"p5k_lin_{i}_b"]) <= TIGHT
+    for key, name in (("p5k_align", "launch"), ("p5k_align_eps_1e-4", "eps_1e-4")):
+        o = Oracle(**R.ALIGN_CASES[name])
+        o.set_source(s5); o.set_target(t5)
+        check_align(_run(o), gold, key)
+    scans = R.make_chain5k()
+    o = Oracle(**R.LIN_CASES["launch"])
+    o.set_target(scans[0])
+    for i in range(1, len(scans)):
+        if i > 1:
+            o.swap()      # the oracle (and the product) keep the previous source's covariances; same numbers as a fresh setInputTarget
+        o.set_source(scans[i])
+        rc, T, conv, it = o.align()
+        assert rc == 0 and [int(conv), it] == list(gold["chain5k_state"][i - 1, :2].astype(int))
+        assert np.abs(T.astype(np.float64) - gold["chain5k_T"][i - 1]).max() <= 1e-7
+        assert abs(o.fitness() - gold["chain5k_state"][i - 1, 2]) <= 1e-6 * gold["chain5k_state"][i - 1, 2]

@@ -334,3 +334,30 @@ def test_libc_atan2f_sensitivity(small_pair):
     rc0, T0, conv0, it0 = o.align()
     rc1, T1, conv1, it1 = r.align()
     assert (conv0, it0) == (conv1, it1) and np.abs(T0 - T1).max() <= 1e-6
+
+
+def test_fitness_after_swap_uses_pcls_stale_tree(small_pair):
+    """A quirk the compiled reference surfaced: FastAPDGICP::swapSourceAndTarget (APD_I:68-75) swaps input_ / target_ and its own
+    kd-trees but does not raise pcl::Registration's target_cloud_updated_, so initCompute does not rebuild PCL's tree_ and the base
+    class's getFitnessScore keeps measuring against the PREVIOUS target. The registration itself is unaffected (it uses the class's own
+    trees). No RIV-SLAM caller swaps (grep finds none), so the product does not reproduce it: its drop-in header marks the
+    target as updated on swap and its fitness is taken against the current target, like the oracle's."""
+    from oracle.oracle import Oracle
+    src, tgt, _ = small_pair
+    third = np.array(src, copy=True); third[:, 0] += 0.15
+    o, r = _both(LAUNCH_PARAMS)
+    for x in (o, r):
+        x.set_source(src); x.set_target(tgt)
+    _compare_align(o, r)
+    assert abs(o.fitness() - r.fitness()) <= 1e-6 * r.fitness()
+    for x in (o, r):
+        x.swap()                   # src becomes the target
+        x.set_source(third)
+    T = _compare_align(o, r)[0]    # same registration
+    stale = Oracle(**LAUNCH_PARAMS)
+    stale.set_source(third); stale.set_target(tgt)          # the OLD target
+    assert abs(r.fitness() - stale.fitness_score(T)) <= 1e-6 * r.fitness()
+    assert abs(o.fitness() - r.fitness()) > 1e-3 * r.fitness()     # the oracle measures against the current target
+    r.set_target(src)                                              # a real setInputTarget raises the flag: the next align refreshes tree_
+    r.align()
+    assert abs(o.fitness() - r.fitness()) <= 1e-6 * r.fitness()
