@@ -65,3 +65,16 @@ r.setOption("bulk_stage", 0)
 r.setInputTarget(tgt, cache_key=901); r.setInputSource(src, cache_key=902)
 r.align(want_output=False); r.getFitnessScore(1.0)
 print("register staging", r.hasConverged(), r.nr_iterations())
+
+# the upload-ahead host pipeline: page-locked input (copy stream + events, kernel-fetched table blocks and guesses, index bases)
+import torch
+drive, _ = datagen.make_drive(2, 1, 12, 400, workers=2)
+many = [drive[i % 12] for i in range(331)]            # 330 pairs: three chunks
+pts, off = F._ragged([np.ascontiguousarray(s[:, :4]) for s in many])
+pin = torch.from_numpy(pts.copy()).pin_memory()
+Hp = F.Handle(0); Hp.set_params(**LAUNCH_PARAMS)
+gs = np.tile(np.eye(4, dtype=np.float32), (330, 1, 1))
+ra = F.odometry_align(Hp, (pin, off), guesses=gs).copy()
+Hp.set_option("upload_ahead", 0)
+rb = F.odometry_align(Hp, (pin, off), guesses=gs).copy()
+print("upload ahead", ra.tobytes() == rb.tobytes(), int((ra["converged"] != 0).sum()))
