@@ -282,5 +282,45 @@ void ref_so3_exp(const double* omega3, double* quat_wxyz, double* R9) {
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R9[i * 3 + j] = m(i, j);
 }
 
+// ---- the stand-in linear algebra itself (oracle/ref_standins/Eigen), exposed so that tests can hold it against numpy / LAPACK ----
+void ref_eigen_svd3(const double* in9, double* U9, double* S3, double* V9) {
+  Eigen::Matrix3d m;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = in9[i * 3 + j];
+  Eigen::JacobiSVD<Eigen::Matrix3d> svd(m, Eigen::ComputeFullU | Eigen::ComputeFullV);
+  for (int i = 0; i < 3; i++) {
+    S3[i] = svd.singularValues()(i);
+    for (int j = 0; j < 3; j++) { U9[i * 3 + j] = svd.matrixU()(i, j); V9[i * 3 + j] = svd.matrixV()(i, j); }
+  }
+}
+void ref_eigen_ldlt6_solve(const double* A36, const double* b6, double* x6) {
+  Eigen::Matrix<double, 6, 6> A;
+  Eigen::Matrix<double, 6, 1> b;
+  for (int i = 0; i < 6; i++) { b(i) = b6[i]; for (int j = 0; j < 6; j++) A(i, j) = A36[i * 6 + j]; }
+  Eigen::LDLT<Eigen::Matrix<double, 6, 6>> solver(A);
+  const Eigen::Matrix<double, 6, 1> x = solver.solve(b);
+  for (int i = 0; i < 6; i++) x6[i] = x(i);
+}
+void ref_eigen_inverse(const double* in, int n, double* out) {
+  if (n == 3) {
+    Eigen::Matrix3d m;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = in[i * 3 + j];
+    const Eigen::Matrix3d r = m.inverse();
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) out[i * 3 + j] = r(i, j);
+  } else {
+    Eigen::Matrix4d m;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m(i, j) = in[i * 4 + j];
+    const Eigen::Matrix4d r = m.inverse();
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) out[i * 4 + j] = r(i, j);
+  }
+}
+// AngleAxisd(yaw, Z) * AngleAxisd(pitch, Y) -> Matrix3d, as APD_I:174-177 writes it
+void ref_eigen_yaw_pitch(double yaw, double pitch, double* R9) {
+  Eigen::AngleAxisd pitchAngle(Eigen::AngleAxisd(pitch, Eigen::Vector3d::UnitY()));
+  Eigen::AngleAxisd yawAngle(Eigen::AngleAxisd(yaw, Eigen::Vector3d::UnitZ()));
+  Eigen::Matrix3d R;
+  R = yawAngle * pitchAngle;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) R9[i * 3 + j] = R(i, j);
+}
+
 const char* ref_apd_version() { return "fast_gicp::FastAPDGICP<pcl::PointXYZI, pcl::PointXYZI> compiled from /root/reference/fast_apdgicp/include over stand-in Eigen / PCL / Boost headers"; }
 }

@@ -67,6 +67,10 @@ def lib():
         L.ref_skewd.argtypes = [dp, dp]
         L.ref_so3_exp.argtypes = [dp, dp, dp]
         L.ref_apd_version.restype = C.c_char_p
+        L.ref_eigen_svd3.argtypes = [dp, dp, dp, dp]
+        L.ref_eigen_ldlt6_solve.argtypes = [dp, dp, dp]
+        L.ref_eigen_inverse.argtypes = [dp, C.c_int, dp]
+        L.ref_eigen_yaw_pitch.argtypes = [C.c_double, C.c_double, dp]
         L.ref_apd_set_atan2f_mode.argtypes = [C.c_int]
         _lib = L
     return _lib
@@ -98,6 +102,37 @@ def so3_exp(omega):
     R = np.zeros(9)
     lib().ref_so3_exp(_ptr(a, C.c_double), _ptr(q, C.c_double), _ptr(R, C.c_double))
     return q, R.reshape(3, 3)
+
+
+# ---- the stand-in Eigen pieces on their own (tests/test_reference_apdgicp.py holds them against numpy / LAPACK) ----
+
+def eigen_svd3(m):
+    a = np.ascontiguousarray(m, dtype=np.float64).reshape(9)
+    U, S, V = np.zeros(9), np.zeros(3), np.zeros(9)
+    lib().ref_eigen_svd3(_ptr(a, C.c_double), _ptr(U, C.c_double), _ptr(S, C.c_double), _ptr(V, C.c_double))
+    return U.reshape(3, 3), S, V.reshape(3, 3)
+
+
+def eigen_ldlt6_solve(A, b):
+    a = np.ascontiguousarray(A, dtype=np.float64).reshape(36)
+    bb = np.ascontiguousarray(b, dtype=np.float64).reshape(6)
+    x = np.zeros(6)
+    lib().ref_eigen_ldlt6_solve(_ptr(a, C.c_double), _ptr(bb, C.c_double), _ptr(x, C.c_double))
+    return x
+
+
+def eigen_inverse(m):
+    a = np.ascontiguousarray(m, dtype=np.float64)
+    n = a.shape[0]
+    out = np.zeros(n * n)
+    lib().ref_eigen_inverse(_ptr(a.reshape(-1), C.c_double), n, _ptr(out, C.c_double))
+    return out.reshape(n, n)
+
+
+def eigen_yaw_pitch(yaw, pitch):
+    R = np.zeros(9)
+    lib().ref_eigen_yaw_pitch(float(yaw), float(pitch), _ptr(R, C.c_double))
+    return R.reshape(3, 3)
 
 
 def parse_lm_table(text: str) -> np.ndarray:

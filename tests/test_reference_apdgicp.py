@@ -384,3 +384,41 @@ def test_reference_thread_count_only_moves_noise_level_decisions(small_pair):
             assert np.array_equal(tr[~noise, 7], tr0[~noise, 7]) and not noise[:-3].any()
             flips += int((tr[:, 7] != tr0[:, 7]).sum())
     print("accept / reject flips between thread counts (noise-level trials only):", flips)
+
+
+def test_stand_in_linear_algebra_against_lapack():
+    """The stand-in Eigen the reference sources are compiled over (oracle/ref_standins/Eigen), piece by piece against numpy / LAPACK:
+    JacobiSVD (orthonormal U and V, descending non-negative singular values, U S V^T = A; rank-deficient and zero matrices), LDLT solve
+    (SPD, indefinite, and a singular matrix's zero pivots), 3x3 / 4x4 inverse, AngleAxis * AngleAxis."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(9)
+    mats = [rng.normal(size=(3, 3)) for _ in range(40)]
+    mats += [(lambda a: a @ a.T)(rng.normal(size=(3, 3))) for _ in range(40)]                       # SPD, as covariances are
+    mats += [np.outer(v, v) for v in rng.normal(size=(10, 3))]                                        # rank 1 (collinear neighbourhoods)
+    mats += [(lambda a: a @ a.T)(np.c_[rng.normal(size=(3, 2)), np.zeros(3)]) for _ in range(10)]     # rank 2 (planar)
+    mats += [np.zeros((3, 3)), np.eye(3), np.diag([5.0, 5.0, 1e-12]), 1e-200 * np.ones((3, 3)), 1e150 * rng.normal(size=(3, 3))]
+    for A in mats:
+        U, S, V = refapd.eigen_svd3(A)
+        scale = max(np.abs(A).max(), 1e-300)
+        assert np.abs(U @ U.T - np.eye(3)).max() < 1e-13 and np.abs(V @ V.T - np.eye(3)).max() < 1e-13
+        assert (S >= 0).all() and S[0] >= S[1] >= S[2]
+        assert np.abs(U @ np.diag(S) @ V.T - A).max() <= 1e-13 * scale
+        assert np.abs(S - np.linalg.svd(A, compute_uv=False)).max() <= 1e-13 * scale
+    for _ in range(40):
+        B = rng.normal(size=(6, 6))
+        b = rng.normal(size=6)
+        for A in (B @ B.T + 1e-3 * np.eye(6), B + B.T):                                                # SPD (H + lambda I) and indefinite
+            x = refapd.eigen_ldlt6_solve(A, b)
+            assert np.abs(A @ x - b).max() <= 1e-9 * max(1.0, np.abs(x).max()) * np.abs(A).max()
+            assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-7, atol=1e-9)
+    assert np.array_equal(refapd.eigen_ldlt6_solve(np.zeros((6, 6)), np.ones(6)), np.zeros(6))        # all pivots zero: the pseudo-inverse gives 0
+    D = np.diag([4.0, 0.0, 2.0, 0.0, 1.0, 3.0])
+    assert np.allclose(refapd.eigen_ldlt6_solve(D, np.arange(1.0, 7.0)), [0.25, 0, 1.5, 0, 5.0, 2.0])
+    for n in (3, 4):
+        for _ in range(20):
+            A = rng.normal(size=(n, n)) + 2 * np.eye(n)
+            assert np.allclose(refapd.eigen_inverse(A), np.linalg.inv(A), rtol=1e-10, atol=1e-12)
+    for _ in range(20):
+        yaw, pitch = rng.uniform(-np.pi, np.pi, 2)
+        want = Rotation.from_euler("z", yaw).as_matrix() @ Rotation.from_euler("y", pitch).as_matrix()
+        assert np.abs(refapd.eigen_yaw_pitch(yaw, pitch) - want).max() < 1e-15
