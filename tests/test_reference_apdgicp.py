@@ -422,3 +422,47 @@ def test_stand_in_linear_algebra_against_lapack():
         yaw, pitch = rng.uniform(-np.pi, np.pi, 2)
         want = Rotation.from_euler("z", yaw).as_matrix() @ Rotation.from_euler("y", pitch).as_matrix()
         assert np.abs(refapd.eigen_yaw_pitch(yaw, pitch) - want).max() < 1e-15
+
+
+def test_randomised_sweep():
+    """80 seeded random cases - cloud sizes 25..700, every regularisation, k = 5..20, gates from 0.3 m to unbounded, LM and Gauss-Newton,
+    outer / inner iteration caps down to 1, APD variances on and off, non-identity guesses, clouds pushed metres apart (few or no
+    correspondences): the oracle walks exactly as the reference's own sources do (converged flag, iteration count, "lm not
+    converged", every accept / reject decision outside rounding noise, y0 / yi / lambda, the float transform)."""
+    from oracle.oracle import Oracle
+    from riv_slam_b200 import datagen
+    rng = np.random.default_rng(2026)
+    done = rejected = failed = empty = 0
+    for _ in range(80):
+        n_s, n_t = int(rng.integers(25, 700)), int(rng.integers(25, 700))
+        src, tgt, _ = datagen.make_pair(int(rng.choice([1, 2, 4])), int(rng.integers(0, 50)), n_src=n_s, n_tgt=n_t)
+        if rng.random() < 0.2:
+            src = src.copy(); src[:, 0] += rng.uniform(1.5, 30)
+        p = dict(k_correspondences=int(rng.choice([5, 10, 15, 20])), regularization=int(rng.integers(0, 5)),
+                 max_corr_dist=float(rng.choice([0.3, 1.0, 2.0, 5.0, 3.4e38])), max_iterations=int(rng.choice([1, 3, 16, 64])),
+                 optimizer=int(rng.random() < 0.8), lm_max_iterations=int(rng.choice([1, 3, 10])),
+                 transformation_epsilon=float(rng.choice([0.1, 5e-4, 1e-3])), rotation_epsilon=float(rng.choice([2e-3, 1e-3])),
+                 lm_init_lambda_factor=float(rng.choice([1e-9, 1e-6, 1e-2])), dist_var=float(rng.choice([0.0, 0.86, 2.0])),
+                 azimuth_var=float(rng.choice([0.0, 0.5, 1.0])), elevation_var=float(rng.choice([0.0, 1.0, 3.0])))
+        if min(n_s, n_t) <= p["k_correspondences"]:
+            continue
+        o, r = Oracle(**p), refapd.RefAPD(**p)
+        for x in (o, r):
+            x.set_source(src); x.set_target(tgt)
+        G = np.eye(4, dtype=np.float32); G[:3, 3] = rng.normal(0, 0.2, 3)
+        rc0, T0, conv0, it0 = o.align(G)
+        rc1, T1, conv1, it1 = r.align(G)
+        assert (rc0, conv0, it0) == (rc1, conv1, it1), p
+        assert np.abs(T0.astype(np.float64) - T1).max() <= 1e-6 and o.lm_failed() == r.lm_failed(), p
+        tr0, tr1 = o.trace(), r.trace()
+        assert tr0.shape == tr1.shape, p
+        if tr1.size:
+            noise = np.abs(tr1[:, 2] - tr1[:, 3]) <= 1e-10 * np.abs(tr1[:, 2])
+            assert np.array_equal(tr0[~noise, 7], tr1[~noise, 7]), p
+            assert np.allclose(tr0[:, [2, 3, 5]], tr1[:, [2, 3, 5]], rtol=1e-7, atol=1e-300), p
+            rejected += int((tr1[:, 7] == 0).sum())
+        failed += int(r.lm_failed())
+        empty += int((r.correspondences()[0] < 0).all())
+        done += 1
+    assert done >= 60
+    print(f"randomised sweep: {done} cases, {rejected} rejected LM trials, {failed} LM failures, {empty} cases without any correspondence")
