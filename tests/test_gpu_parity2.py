@@ -517,3 +517,49 @@ def test_upload_ahead_pipeline_is_bit_identical():
         H.check(H.L.apd_batch_align(H.h, C.c_void_p(ps.data_ptr()), src_off.ctypes.data_as(ip), C.c_void_p(pt.data_ptr()), tgt_off.ctypes.data_as(ip), 16,
                                     guesses.ctypes.data_as(C.POINTER(C.c_float)), n_scans - 1, C.c_void_p(res.ctypes.data)))
         assert res.tobytes() == a.tobytes()
+
+
+# ---------------------------------------------------------------- randomised sweep
+
+def test_randomised_sweep_against_the_oracle():
+    """The 80 seeded cases of tests/test_reference_apdgicp.py::test_randomised_sweep (there: oracle == the reference's compiled sources)
+    through the CUDA path: cloud sizes 25..700, every regularisation, k = 5..20, gates from 0.3 m to unbounded, LM and Gauss-Newton,
+    iteration caps down to 1, APD variances on and off, non-identity guesses, clouds metres apart."""
+    from riv_slam_b200 import datagen
+    from riv_slam_b200 import fast_apdgicp as F
+    rng = np.random.default_rng(2026)
+    done = 0
+    for _ in range(80):
+        n_s, n_t = int(rng.integers(25, 700)), int(rng.integers(25, 700))
+        src, tgt, _ = datagen.make_pair(int(rng.choice([1, 2, 4])), int(rng.integers(0, 50)), n_src=n_s, n_tgt=n_t)
+        if rng.random() < 0.2:
+            src = src.copy(); src[:, 0] += rng.uniform(1.5, 30)
+        p = dict(k_correspondences=int(rng.choice([5, 10, 15, 20])), regularization=int(rng.integers(0, 5)),
+                 max_corr_dist=float(rng.choice([0.3, 1.0, 2.0, 5.0, 3.4e38])), max_iterations=int(rng.choice([1, 3, 16, 64])),
+                 optimizer=int(rng.random() < 0.8), lm_max_iterations=int(rng.choice([1, 3, 10])),
+                 transformation_epsilon=float(rng.choice([0.1, 5e-4, 1e-3])), rotation_epsilon=float(rng.choice([2e-3, 1e-3])),
+                 lm_init_lambda_factor=float(rng.choice([1e-9, 1e-6, 1e-2])), dist_var=float(rng.choice([0.0, 0.86, 2.0])),
+                 azimuth_var=float(rng.choice([0.0, 0.5, 1.0])), elevation_var=float(rng.choice([0.0, 1.0, 3.0])))
+        if min(n_s, n_t) <= p["k_correspondences"]:
+            continue
+        G = np.eye(4, dtype=np.float32); G[:3, 3] = rng.normal(0, 0.2, 3)
+        o = _oracle(p)
+        o.set_source(src); o.set_target(tgt)
+        rc0, T0, conv0, it0 = o.align(G)
+        g = _gpu(p)
+        g.setInputSource(src); g.setInputTarget(tgt)
+        g.align(G, want_output=False)
+        assert rc0 == 0 and (g.hasConverged(), g.nr_iterations()) == (conv0, it0), p
+        assert (g.status() == F.APD_STATUS_LM_FAILED) == o.lm_failed(), p
+        _assert_same_transform(g.getFinalTransformation(), T0)
+        assert np.array_equal(g.getKnn(0), o.knn(0)) and np.array_equal(g.getKnn(1), o.knn(1)), p
+        tr0, tr1 = o.trace(), g.getLMTrace()
+        assert tr0.shape == tr1.shape, p
+        if tr0.size:
+            noise = np.abs(tr0[:, 2] - tr0[:, 3]) <= 1e-9 * np.abs(tr0[:, 2])
+            assert np.array_equal(tr0[~noise, 7], tr1[~noise, 7]), p
+            assert np.allclose(tr0[:, [2, 3]], tr1[:, [2, 3]], rtol=1e-7, atol=1e-300), p
+        f0 = o.fitness()
+        assert abs(g.getFitnessScore() - f0) <= REL_TOL * f0, p
+        done += 1
+    assert done >= 60
